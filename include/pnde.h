@@ -1,0 +1,177 @@
+/*
+ * pnde.h -- C ABI of libpnde.so, the B200-native ODE-filter hot path.
+ *
+ * Drop-in boundary for ProbNumDiffEq.jl v0.1.5 (nathanaelbosch/ODEFilters.jl).  The
+ * reference has no FFI: its hot path is reached through OrdinaryDiffEq's plugin hooks
+ *   alg_cache      src/caches.jl:42-43        -> pnde_create
+ *   initialize!    src/perform_step.jl:2-12   -> inside pnde_run (Taylor-mode init on device)
+ *   perform_step!  src/perform_step.jl:27-93  -> inside pnde_run (the persistent filter kernel)
+ *   savevalues!    src/integrator_utils.jl:33-48 -> history buffers, pnde_get_history
+ *   postamble!     src/integrator_utils.jl:2-30  -> static-diffusion rescale + pnde_smooth
+ *   build_solution src/solution.jl:45-80      -> pnde_get_final / pnde_get_history / pnde_get_counts
+ * and through the external OrdinaryDiffEq loop (solve!, loopheader!, loopfooter!, PI controller,
+ * initdt), which a per-step ccall cannot keep on a GPU; the boundary therefore sits one level
+ * up: Julia's DiffEqBase.__solve(prob, alg::AbstractEK; ...) / __solve(::EnsembleProblem, ...)
+ * marshal to structure-of-arrays and ccall the functions below once per ensemble.
+ * INTEGRATION.md shows the Julia ccall stubs.
+ *
+ * Conventions: plain C, no exceptions; all reals are double, all sizes int64_t.  Return code 0 =
+ * ok, <0 = argument / CUDA error (text via pnde_last_error).  Per-trajectory numerical failures are
+ * DATA (the retcode array), never a failed call.  The caller allocates every output buffer; the
+ * library owns device memory inside the handle.  A handle is bound to one CUDA device and is not
+ * re-entrant; distinct handles may be used from distinct host threads / processes (one per GPU).
+ * There is no CPU fallback: every entry point that computes fails with PNDE_ERR_CUDA when no
+ * device is present.
+ *
+ * Array layout: structure-of-arrays with the TRAJECTORY INDEX FASTEST, e.g. u0[c * n_traj + i]
+ * is component c of trajectory i.
+ */
+#ifndef PNDE_H
+#define PNDE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNDE_ABI_VERSION 1
+
+/* return codes */
+#define PNDE_OK 0
+#define PNDE_ERR_ARG (-1)
+#define PNDE_ERR_CUDA (-2)
+#define PNDE_ERR_UNSUPPORTED (-3)
+#define PNDE_ERR_STATE (-4)
+#define PNDE_ERR_ALLOC (-5)
+
+/* algorithms: src/algorithms.jl:23-51 */
+#define PNDE_ALG_EK0 0
+#define PNDE_ALG_EK1 1
+
+/* diffusion models: src/caches.jl:89-96 / src/diffusions.jl */
+#define PNDE_DIFF_DYNAMIC 0
+#define PNDE_DIFF_FIXED 1
+#define PNDE_DIFF_FIXED_MAP 2
+#define PNDE_DIFF_DYNAMIC_MV 3
+#define PNDE_DIFF_FIXED_MV 4
+
+/* built-in vector-field catalogue (Julia closures cannot run on the device) */
+#define PNDE_VF_FHN_README 0     /* README.md:36-40, p = (a,b,c) */
+#define PNDE_VF_FHN_LIB 1        /* prob_ode_fitzhughnagumo, p = (a,b,tauinv,l) */
+#define PNDE_VF_LOTKA_VOLTERRA 2 /* prob_ode_lotkavoltera, p = (a,b,c,d) */
+#define PNDE_VF_VANDERPOL 3      /* prob_ode_vanstiff ordering u=(y,x), p = (mu) */
+#define PNDE_VF_LINEAR2 4        /* du_i = p_i u_i, d = 2 (test/state_init.jl:15) */
+#define PNDE_VF_LOGISTIC 5       /* du = p u (1-u), d = 1 (test/specific_problems.jl:62) */
+#define PNDE_VF_LORENZ96 6       /* d given in the config, p = (F) */
+#define PNDE_VF_LINEAR1 7        /* du = p u, d = 1 (test/convergence.jl:10) */
+
+/* what is written to the device-side history */
+#define PNDE_SAVE_FINAL 0  /* final state only */
+#define PNDE_SAVE_EVERY 1  /* every accepted step (what the reference does, integrator_utils.jl:43-45) */
+#define PNDE_SAVE_STRIDE 2 /* every save_stride-th accepted step and the last one */
+
+/* per-trajectory return codes (data) */
+#define PNDE_RET_SUCCESS 0
+#define PNDE_RET_MAXITERS 1
+#define PNDE_RET_DTNAN 2
+#define PNDE_RET_NONFINITE 3
+#define PNDE_RET_HISTORY_FULL 4
+#define PNDE_RET_DTMIN 5
+
+/* which states pnde_get_history returns */
+#define PNDE_HIST_FILTERED 0
+#define PNDE_HIST_SMOOTHED 1
+
+typedef struct pnde_config {
+  int32_t abi_version; /* PNDE_ABI_VERSION */
+  int32_t alg;         /* PNDE_ALG_* */
+  int32_t order;       /* q, src/algorithms.jl:25 */
+  int32_t d;           /* ODE dimension (fixed by the vector field except Lorenz-96) */
+  int32_t vf_kind;     /* PNDE_VF_* */
+  int32_t diffusion;   /* PNDE_DIFF_* */
+  int32_t smooth;      /* run the RTS pass in pnde_solve_ensemble (needs PNDE_SAVE_EVERY) */
+  int32_t adaptive;    /* 1: PI-controlled steps, 0: fixed dt */
+  int32_t save_mode;   /* PNDE_SAVE_* */
+  int32_t save_stride; /* for PNDE_SAVE_STRIDE */
+  int32_t device;      /* CUDA device ordinal, -1 = current device */
+  int32_t reserved0;
+  double abstol, reltol; /* defaults 1e-6 / 1e-3 (OrdinaryDiffEq) */
+  double dt;             /* fixed step, or initial step when adaptive (<= 0: Hairer initdt) */
+  double t0, t1;
+  /* PI controller, OrdinaryDiffEq defaults + src/alg_utils.jl:23-24; beta <= 0 selects the default */
+  double qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit, beta1, beta2, dtmin, dtmax;
+  int64_t maxiters;  /* attempted steps per trajectory (default 100000) */
+  int64_t max_saved; /* history slots per trajectory incl. the initial state; 0 = derive (fixed step) */
+} pnde_config;
+
+typedef struct pnde_handle pnde_handle;
+
+/* Fill cfg with the reference defaults for (alg, order): EK*(order=q), dynamic diffusion,
+ * smooth=false, adaptive=true, abstol=1e-6, reltol=1e-3, PI controller of src/alg_utils.jl:13-24. */
+int pnde_default_config(pnde_config* cfg, int32_t alg, int32_t order, int32_t vf_kind);
+
+/* alg_cache (src/caches.jl:42-114): validates the configuration, builds the IWP constants
+ * (src/priors.jl:7-59), binds the device. */
+int pnde_create(const pnde_config* cfg, pnde_handle** out);
+int pnde_destroy(pnde_handle* h);
+const char* pnde_last_error(const pnde_handle* h); /* h may be NULL: last create error */
+
+/* Dimension helpers. */
+int64_t pnde_state_dim(const pnde_handle* h);    /* D = d (q+1) */
+int64_t pnde_n_params(const pnde_handle* h);     /* parameters per trajectory */
+int64_t pnde_record_len(const pnde_handle* h);   /* doubles per saved state in the device history */
+
+/* One call = one EnsembleProblem solve: host buffers in, results kept on the device.
+ * u0: [d][n_traj], p: [n_params][n_traj].  Equivalent to pnde_upload + pnde_run (+ pnde_smooth). */
+int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const double* p);
+
+/* Split form, so that inputs can stay resident in HBM across runs. */
+int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* p);
+int pnde_run(pnde_handle* h);         /* initialize! + the whole solve! loop, asynchronous */
+int pnde_synchronize(pnde_handle* h); /* wait for the handle's stream */
+/* device time (ms, CUDA events on the handle's stream) of the last pnde_run / pnde_smooth */
+int pnde_last_run_ms(pnde_handle* h, double* filter_ms, double* smooth_ms);
+/* number of kernels the last pnde_run / pnde_smooth launched */
+int64_t pnde_last_launch_count(const pnde_handle* h);
+
+/* postamble! (src/integrator_utils.jl:2-30): RTS smoother over the saved history
+ * (src/smoothing.jl:4-63).  Requires PNDE_SAVE_EVERY. */
+int pnde_smooth(pnde_handle* h);
+
+/* Sizes for the getters: total saved states over all trajectories and the per-trajectory maximum. */
+int pnde_query_sizes(pnde_handle* h, int64_t* n_saved_total, int64_t* max_saved);
+
+/* destats / retcode.  Any pointer may be NULL.  Arrays of n_traj. */
+int pnde_get_counts(pnde_handle* h, int64_t* naccept, int64_t* nreject, int64_t* nf, int64_t* njacs,
+                    int32_t* retcode, int64_t* n_saved);
+
+/* Final filtering state: mean [D][n], cov packed lower triangle by rows [D(D+1)/2][n]
+ * (entry (i,j), j<=i, at i(i+1)/2+j), t_final [n], log-likelihood [n] (NaN for static diffusion
+ * models, src/integrator_utils.jl:6).  Any pointer may be NULL. */
+int pnde_get_final(pnde_handle* h, double* mean, double* cov, double* t_final, double* loglik);
+
+/* History of trajectory range [traj_begin, traj_end) in CSR form: offsets[i - traj_begin] ..
+ * offsets[i - traj_begin + 1] index the saved states of trajectory i in the flat outputs.
+ *   t         [total]           time stamps (sol.t)
+ *   mean      [total][D]        state means (x_filt.mu / x_smooth.mu)
+ *   cov       [total][D(D+1)/2] packed lower covariance (Sigma = S S')
+ *   diffusion [total][nd]       sol.diffusions: entry k of a trajectory belongs to the interval
+ *                               ending at saved state k (entry 0 is unused); nd = 1, or d for MV models
+ * offsets has traj_end - traj_begin + 1 entries and is an OUTPUT (query sizes first). */
+int pnde_get_history(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end,
+                     int64_t* offsets, double* t, double* mean, double* cov, double* diffusion);
+
+/* sol.pu (src/integrator_utils.jl:45): marginals of the solution block, same CSR layout:
+ * u [total][d], cov_u [total][d(d+1)/2]. */
+int pnde_get_marginals(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end,
+                       int64_t* offsets, double* t, double* u, double* cov_u);
+
+/* Device micro-benchmarks used as roofline denominators by bench.py (not part of the path). */
+int pnde_measure_fp64_peak(int32_t device, double* tflops);
+int pnde_measure_hbm_copy(int32_t device, double* gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNDE_H */

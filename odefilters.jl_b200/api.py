@@ -1,0 +1,437 @@
+"""Host-side interface (see package docstring).  Mirrors the reference's user API:
+
+    prob = ODEProblem("fhn_readme", u0=[-1.0, 1.0], tspan=(0.0, 20.0), p=(0.2, 0.2, 3.0))
+    sol = solve(prob, EK0(order=1), abstol=1e-1, reltol=1e-2)          # README.md:47
+    eprob = EnsembleProblem(prob, p=P)                                   # P: [N, n_params]
+    esol = solve(eprob, EK1(order=3), EnsembleB200(), trajectories=N, adaptive=False, dt=0.01)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------------------------
+# Algorithm / problem types (src/algorithms.jl:23-51; DiffEqBase ODEProblem / EnsembleProblem)
+# --------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class _EK:
+    order: int = 3
+    diffusionmodel: str = "dynamic"
+    smooth: bool = True
+    prior: str = "ibm"
+    kind: int = L.ALG_EK1
+
+    def __post_init__(self):
+        if self.prior != "ibm":
+            raise ValueError("Only the ibm prior is implemented so far")  # src/caches.jl:69
+        if self.diffusionmodel not in L.DIFFUSIONS:
+            raise ValueError(f"diffusionmodel must be one of {list(L.DIFFUSIONS)}")
+
+
+def EK0(order: int = 3, diffusionmodel: str = "dynamic", smooth: bool = True, prior: str = "ibm") -> _EK:
+    """Gaussian ODE filtering with zeroth order extended Kalman filtering (src/algorithms.jl:23-28)."""
+    return _EK(order, diffusionmodel, smooth, prior, L.ALG_EK0)
+
+
+def EK1(order: int = 3, diffusionmodel: str = "dynamic", smooth: bool = True, prior: str = "ibm") -> _EK:
+    """Gaussian ODE filtering with first order extended Kalman filtering (src/algorithms.jl:46-51)."""
+    return _EK(order, diffusionmodel, smooth, prior, L.ALG_EK1)
+
+
+@dataclass
+class ODEProblem:
+    """ODEProblem(f, u0, tspan, p) with ``f`` a name from the built-in catalogue (include/pnde.h)."""
+
+    f: str
+    u0: Sequence[float]
+    tspan: Sequence[float]
+    p: Sequence[float] = ()
+
+    def __post_init__(self):
+        if self.f not in L.VF_DIMS:
+            raise ValueError(f"unknown vector field {self.f!r}; catalogue: {sorted(L.VF_DIMS)}")
+        u0 = np.asarray(self.u0, dtype=np.float64)
+        if u0.ndim != 1:
+            # src/caches.jl:46-49
+            raise ValueError("Problems which are not scalar- or vector-valued (e.g. u0 is a scalar or a matrix) "
+                             "are currently not supported")
+        d, npar = L.VF_DIMS[self.f]
+        if u0.shape[0] != d:
+            raise ValueError(f"{self.f} has dimension {d}")
+        p = np.atleast_1d(np.asarray(self.p, dtype=np.float64))
+        if p.shape[0] != npar:
+            raise ValueError(f"{self.f} takes {npar} parameters")
+        self.u0, self.p = u0, p
+
+
+@dataclass
+class EnsembleProblem:
+    """EnsembleProblem(prob; prob_func): the per-trajectory remake is given as arrays.
+
+    ``u0``: [N, d] or None (broadcast prob.u0); ``p``: [N, n_params] or None (broadcast prob.p).
+    """
+
+    prob: ODEProblem
+    u0: Optional[np.ndarray] = None
+    p: Optional[np.ndarray] = None
+
+
+class EnsembleB200:
+    """Ensemble algorithm: all trajectories in one device launch (stands where EnsembleThreads does)."""
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block partition [lo, hi) of n trajectories: remainder to the last rank."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    per = n // world
+    lo = rank * per
+    hi = n if rank == world - 1 else lo + per
+    return lo, hi
+
+
+# --------------------------------------------------------------------------------------------
+# Result containers (src/squarerootmatrix.jl, GaussianDistributions.Gaussian, src/solution.jl:8-24)
+# --------------------------------------------------------------------------------------------
+class SRMatrix:
+    """PSD matrix with a square-root factor (src/squarerootmatrix.jl:9-16).  ``mat`` comes from the
+    device; ``squareroot`` (any S with S S' = mat, not unique in the reference either) is derived lazily."""
+
+    def __init__(self, mat: np.ndarray):
+        self.mat = mat
+        self._sr = None
+
+    @property
+    def squareroot(self) -> np.ndarray:
+        if self._sr is None:
+            w, v = np.linalg.eigh((self.mat + self.mat.T) / 2)
+            self._sr = v * np.sqrt(np.clip(w, 0.0, None))
+        return self._sr
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.mat, dtype=dtype)
+
+    @property
+    def shape(self):
+        return self.mat.shape
+
+
+@dataclass
+class Gaussian:
+    mu: np.ndarray
+    Sigma: SRMatrix
+
+
+def _unpack_lower(packed: np.ndarray, D: int) -> np.ndarray:
+    """[..., D(D+1)/2] packed lower triangle (rows) -> [..., D, D] symmetric."""
+    out = np.zeros(packed.shape[:-1] + (D, D))
+    il = np.tril_indices(D)
+    out[..., il[0], il[1]] = packed
+    out[..., il[1], il[0]] = packed
+    return out
+
+
+class _GaussianList:
+    """StructArray{Gaussian} over SoA buffers (src/solution.jl:60-64): ``.mu`` [N, D], ``.Sigma`` [N, D, D]."""
+
+    def __init__(self, mu: np.ndarray, cov: np.ndarray):
+        self.mu, self.Sigma = mu, cov
+
+    def __len__(self):
+        return self.mu.shape[0]
+
+    def __getitem__(self, i) -> Gaussian:
+        return Gaussian(self.mu[i], SRMatrix(self.Sigma[i]))
+
+
+@dataclass
+class ProbODESolution:
+    """Fields of the reference's ProbODESolution (src/solution.jl:8-24)."""
+
+    t: np.ndarray
+    u: np.ndarray
+    pu: _GaussianList
+    x_filt: _GaussianList
+    x_smooth: Optional[_GaussianList]
+    diffusions: np.ndarray
+    log_likelihood: float
+    destats: dict
+    retcode: str
+    prob: ODEProblem = None
+    alg: _EK = None
+
+    def __len__(self):
+        return len(self.t)
+
+
+@dataclass
+class EnsembleSolution:
+    """EnsembleSolution over the device results: final states for every trajectory plus lazily
+    fetched per-trajectory histories."""
+
+    solver: "FilterSolver"
+    n: int
+    mean: np.ndarray        # [N, D] final filtering mean
+    cov: np.ndarray         # [N, D(D+1)/2] packed
+    t_final: np.ndarray
+    log_likelihood: np.ndarray
+    destats: dict
+    retcode: np.ndarray
+    converged: bool = True
+    _cache: dict = field(default_factory=dict)
+
+    def __len__(self):
+        return self.n
+
+    @property
+    def u(self) -> np.ndarray:
+        return self.mean[:, : self.solver.d]
+
+    def __getitem__(self, i: int) -> ProbODESolution:
+        return self.solver.solution(i)
+
+
+# --------------------------------------------------------------------------------------------
+# Low-level handle wrapper
+# --------------------------------------------------------------------------------------------
+class FilterSolver:
+    """One pnde_handle: alg_cache + the device buffers of one ensemble (include/pnde.h)."""
+
+    def __init__(self, prob: ODEProblem, alg: _EK, *, abstol=1e-6, reltol=1e-3, adaptive=True, dt=None,
+                 save_everystep=True, save_stride=None, smooth=None, maxiters=100000, max_saved=0, device=-1,
+                 dtmin=0.0, dtmax=None, qmin=None, qmax=None, gamma=None, beta1=None, beta2=None):
+        if not adaptive and dt is None:
+            raise ValueError("Fixed timestep methods require a choice of dt")  # test/errors.jl:16-20
+        self.lib = L.load()
+        self.prob, self.alg = prob, alg
+        cfg = L.PndeConfig()
+        self.lib.pnde_default_config(C.byref(cfg), alg.kind, alg.order, L.VF_KINDS[prob.f])
+        cfg.diffusion = L.DIFFUSIONS[alg.diffusionmodel]
+        smooth = alg.smooth if smooth is None else smooth
+        cfg.smooth = 1 if (smooth and save_everystep) else 0
+        cfg.adaptive = 1 if adaptive else 0
+        cfg.save_mode = L.SAVE_EVERY if save_everystep else (L.SAVE_STRIDE if save_stride else L.SAVE_FINAL)
+        cfg.save_stride = int(save_stride or 1)
+        cfg.device = device
+        cfg.abstol, cfg.reltol = float(abstol), float(reltol)
+        cfg.dt = float(dt) if dt is not None else 0.0
+        cfg.t0, cfg.t1 = float(prob.tspan[0]), float(prob.tspan[1])
+        cfg.maxiters = int(maxiters)
+        cfg.max_saved = int(max_saved)
+        cfg.dtmin = float(dtmin)
+        for name, val in (("dtmax", dtmax), ("qmin", qmin), ("qmax", qmax), ("gamma", gamma), ("beta1", beta1),
+                          ("beta2", beta2)):
+            if val is not None:
+                setattr(cfg, name, float(val))
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = self.lib.pnde_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"pnde_create failed ({rc}): {self.lib.pnde_last_error(None).decode()}")
+        self.d, self.npar = L.VF_DIMS[prob.f]
+        self.D = int(self.lib.pnde_state_dim(self._h))
+        self.n = 0
+        self.is_mv = alg.diffusionmodel in ("dynamicMV", "fixedMV")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.pnde_last_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.pnde_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- data movement / execution ---------------------------------------------------------
+    @staticmethod
+    def _soa(a: np.ndarray) -> np.ndarray:
+        """[N, k] -> C-contiguous [k, N] (trajectory index fastest)."""
+        return np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)
+
+    def upload(self, u0: np.ndarray, p: np.ndarray, soa: bool = False):
+        u0s = u0 if soa else self._soa(u0)
+        ps = p if soa else self._soa(p)
+        n = u0s.shape[1]
+        assert u0s.shape == (self.d, n) and ps.shape == (self.npar, n)
+        self._keep = (u0s, ps)
+        self._check(self.lib.pnde_upload(self._h, n, u0s.ctypes.data, ps.ctypes.data), "pnde_upload")
+        self.n = n
+
+    def run(self, sync: bool = True):
+        self._check(self.lib.pnde_run(self._h), "pnde_run")
+        if sync:
+            self.synchronize()
+
+    def smooth(self, sync: bool = True):
+        self._check(self.lib.pnde_smooth(self._h), "pnde_smooth")
+        if sync:
+            self.synchronize()
+
+    def synchronize(self):
+        self._check(self.lib.pnde_synchronize(self._h), "pnde_synchronize")
+
+    def solve_ensemble(self, u0: np.ndarray, p: np.ndarray, soa: bool = False):
+        u0s = u0 if soa else self._soa(u0)
+        ps = p if soa else self._soa(p)
+        n = u0s.shape[1]
+        self._keep = (u0s, ps)
+        self._check(self.lib.pnde_solve_ensemble(self._h, n, u0s.ctypes.data, ps.ctypes.data), "pnde_solve_ensemble")
+        self.n = n
+
+    def last_run_ms(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.pnde_last_run_ms(self._h, C.byref(a), C.byref(b)), "pnde_last_run_ms")
+        return a.value, b.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.pnde_last_launch_count(self._h))
+
+    # --- results --------------------------------------------------------------------------
+    def counts(self) -> dict:
+        n = self.n
+        arrs = {k: np.zeros(n, dtype=np.int64) for k in ("naccept", "nreject", "nf", "njacs", "n_saved")}
+        ret = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.pnde_get_counts(self._h, arrs["naccept"].ctypes.data, arrs["nreject"].ctypes.data,
+                                             arrs["nf"].ctypes.data, arrs["njacs"].ctypes.data, ret.ctypes.data,
+                                             arrs["n_saved"].ctypes.data), "pnde_get_counts")
+        arrs["retcode"] = ret
+        return arrs
+
+    def final(self):
+        """(mean [N, D], cov packed [N, D(D+1)/2], t_final [N], loglik [N])."""
+        n, D = self.n, self.D
+        mean = np.empty((D, n))
+        cov = np.empty((D * (D + 1) // 2, n))
+        tf = np.empty(n)
+        ll = np.empty(n)
+        self._check(self.lib.pnde_get_final(self._h, mean.ctypes.data, cov.ctypes.data, tf.ctypes.data,
+                                            ll.ctypes.data), "pnde_get_final")
+        return mean.T.copy(), cov.T.copy(), tf, ll
+
+    def final_u(self):
+        """Only the solution block of the final mean and the final time (small D2H read)."""
+        n, D = self.n, self.D
+        mean = np.empty((D, n))
+        tf = np.empty(n)
+        self._check(self.lib.pnde_get_final(self._h, mean.ctypes.data, None, tf.ctypes.data, None), "pnde_get_final")
+        return mean[: self.d].T.copy(), tf
+
+    def history(self, which: int, lo: int, hi: int, marginals: bool = False):
+        """CSR history of trajectories [lo, hi): (offsets, t, mean, cov_packed, diffusion)."""
+        tot, mx = C.c_int64(), C.c_int64()
+        self._check(self.lib.pnde_query_sizes(self._h, C.byref(tot), C.byref(mx)), "pnde_query_sizes")
+        cnt = self.counts()["n_saved"][lo:hi]
+        total = int(cnt.sum())
+        DM = self.d if marginals else self.D
+        offsets = np.zeros(hi - lo + 1, dtype=np.int64)
+        t = np.empty(total)
+        mean = np.empty((total, DM))
+        cov = np.empty((total, DM * (DM + 1) // 2))
+        if marginals:
+            self._check(self.lib.pnde_get_marginals(self._h, which, lo, hi, offsets.ctypes.data, t.ctypes.data,
+                                                    mean.ctypes.data, cov.ctypes.data), "pnde_get_marginals")
+            return offsets, t, mean, cov, None
+        nd = self.d if self.is_mv else 1
+        diff = np.empty((total, nd))
+        self._check(self.lib.pnde_get_history(self._h, which, lo, hi, offsets.ctypes.data, t.ctypes.data,
+                                              mean.ctypes.data, cov.ctypes.data, diff.ctypes.data), "pnde_get_history")
+        return offsets, t, mean, cov, diff
+
+    def solution(self, i: int, counts: Optional[dict] = None, final=None) -> ProbODESolution:
+        """build_solution for trajectory i (src/solution.jl:45-80, src/integrator_utils.jl:20-26)."""
+        counts = counts or self.counts()
+        D, d = self.D, self.d
+        smoothed = bool(self.cfg.smooth)
+        if self.cfg.save_mode == L.SAVE_FINAL:
+            mean, cov, tf, ll = final or self.final()
+            xf = _GaussianList(mean[i:i + 1], _unpack_lower(cov[i:i + 1], D))
+            t = tf[i:i + 1]
+            diffs = np.zeros((0, 1))
+            xs = None
+            llv = ll[i]
+        else:
+            _, t, mean, cov, diffs = self.history(L.HIST_FILTERED, i, i + 1)
+            xf = _GaussianList(mean, _unpack_lower(cov, D))
+            xs = None
+            if smoothed:
+                _, _, ms, cs, _ = self.history(L.HIST_SMOOTHED, i, i + 1)
+                xs = _GaussianList(ms, _unpack_lower(cs, D))
+            diffs = diffs[1:]  # entry 0 belongs to no interval
+            llv = (final or self.final())[3][i]
+        src = xs if xs is not None else xf
+        pu = _GaussianList(src.mu[:, :d].copy(), src.Sigma[:, :d, :d].copy())
+        return ProbODESolution(
+            t=t, u=pu.mu, pu=pu, x_filt=xf, x_smooth=xs,
+            diffusions=diffs if self.is_mv else diffs[:, 0],
+            log_likelihood=float(llv),
+            destats={k: int(counts[k][i]) for k in ("naccept", "nreject", "nf", "njacs")},
+            retcode=L.RETCODES.get(int(counts["retcode"][i]), "Failure"), prob=self.prob, alg=self.alg)
+
+
+# --------------------------------------------------------------------------------------------
+# solve
+# --------------------------------------------------------------------------------------------
+def _ensemble_arrays(eprob: EnsembleProblem, trajectories: Optional[int]):
+    prob = eprob.prob
+    n = trajectories
+    for a in (eprob.u0, eprob.p):
+        if a is not None:
+            n = len(a) if n is None else n
+    if n is None:
+        raise ValueError("trajectories must be given")
+    u0 = np.broadcast_to(prob.u0, (n, len(prob.u0))) if eprob.u0 is None else np.asarray(eprob.u0, dtype=np.float64)[:n]
+    p = np.broadcast_to(prob.p, (n, len(prob.p))) if eprob.p is None else np.asarray(eprob.p, dtype=np.float64)[:n]
+    return u0, p, n
+
+
+def solve(prob, alg: _EK, ensemblealg: Optional[EnsembleB200] = None, *, trajectories: Optional[int] = None,
+          abstol=1e-6, reltol=1e-3, adaptive=True, dt=None, dense=None, save_everystep=None, save_stride=None,
+          maxiters=100000, max_saved=0, device=-1, **ctrl):
+    """solve(prob, EK0/EK1(order=q); abstol, reltol, adaptive, dt) -> ProbODESolution, or
+    solve(EnsembleProblem, alg, EnsembleB200(); trajectories=N, ...) -> EnsembleSolution.
+
+    ``dense`` must equal ``alg.smooth`` (the reference asserts this, src/perform_step.jl:3); it defaults to it.
+    """
+    if dense is not None and bool(dense) != bool(alg.smooth):
+        raise ValueError("`dense` and `smooth` should have the same value! ")
+    ensemble = isinstance(prob, EnsembleProblem)
+    if save_everystep is None:
+        save_everystep = not ensemble
+    if ensemble:
+        u0, p, n = _ensemble_arrays(prob, trajectories)
+        base = prob.prob
+    else:
+        base = prob
+        u0, p, n = base.u0[None, :], base.p[None, :], 1
+    user_cap = max_saved
+    if save_everystep and adaptive and not max_saved:
+        max_saved = 1024 if ensemble else 8192
+    while True:
+        solver = FilterSolver(base, alg, abstol=abstol, reltol=reltol, adaptive=adaptive, dt=dt,
+                              save_everystep=save_everystep, save_stride=save_stride, maxiters=maxiters,
+                              max_saved=max_saved, device=device, **ctrl)
+        solver.solve_ensemble(u0, p)
+        counts = solver.counts()
+        if (counts["retcode"] == 4).any() and not user_cap and max_saved < maxiters + 1:
+            solver.close()
+            max_saved = min(max_saved * 4, maxiters + 1)  # history full: grow and redo
+            continue
+        break
+    if not ensemble:
+        return solver.solution(0, counts)
+    mean, cov, tf, ll = solver.final()
+    return EnsembleSolution(solver=solver, n=n, mean=mean, cov=cov, t_final=tf, log_likelihood=ll,
+                            destats={k: counts[k] for k in ("naccept", "nreject", "nf", "njacs")},
+                            retcode=counts["retcode"], converged=bool((counts["retcode"] == 0).all()))

@@ -1,0 +1,653 @@
+// The persistent ensemble filter kernel: one trajectory per thread, the whole solve! loop of
+// OrdinaryDiffEq on the device with lockstep, masked per-trajectory step control.
+//
+// Reference path being replaced (relative to the reference checkout):
+//   initialize!      src/perform_step.jl:2-12  (+ src/state_initialization.jl:2-53)
+//   perform_step!    src/perform_step.jl:27-93
+//   measure!         src/perform_step.jl:95-132
+//   estimate_errors  src/perform_step.jl:148-158
+//   estimate_diffusion src/diffusions.jl:11-153
+//   savevalues!      src/integrator_utils.jl:33-48
+//   controller       src/alg_utils.jl:13-24 + OrdinaryDiffEq (external)
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "cov_engine.cuh"
+#include "vector_fields.cuh"
+
+namespace pnde {
+
+enum { DIFF_DYNAMIC = 0, DIFF_FIXED = 1, DIFF_FIXED_MAP = 2, DIFF_DYNAMIC_MV = 3, DIFF_FIXED_MV = 4 };
+enum { SAVE_FINAL = 0, SAVE_EVERY = 1, SAVE_STRIDE = 2 };
+enum { RET_SUCCESS = 0, RET_MAXITERS = 1, RET_DTNAN = 2, RET_NONFINITE = 3, RET_HISTORY_FULL = 4, RET_DTMIN = 5 };
+
+struct CtrlParams {
+  double abstol, reltol, dt, t0, t1;
+  double qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit, beta1, beta2, dtmin, dtmax;
+  long long maxiters;
+};
+
+struct FilterParams {
+  long long n;
+  const double* u0;  // [d][n]
+  const double* p;   // [np][n]
+  double* mean;      // [D][n]
+  double* cov;       // [D(D+1)/2][n]
+  double* t_final;   // [n]
+  double* loglik;    // [n]
+  double* final_diff;  // [ND][n]
+  int* retcode;
+  int* naccept;
+  int* nreject;
+  int* nf;
+  int* njacs;
+  int* n_saved;
+  double* hist;  // [max_saved][REC][n]
+  long long max_saved;
+  int save_mode, save_stride, diffusion;
+  IwpConsts C;
+  CtrlParams K;
+};
+
+// P(h) block scales h^(k-q-1/2) (src/preconditioning.jl:4-13) and their inverses.
+template <int q>
+__device__ __forceinline__ void precond_scales(double h, double (&P)[q + 1], double (&PI)[q + 1]) {
+  // PI_k = h^(q+1/2-k): PI_q = sqrt(h), PI_{k-1} = PI_k * h
+  double v = sqrt(h);
+  PI[q] = v;
+#pragma unroll
+  for (int k = q - 1; k >= 0; --k) {
+    v *= h;
+    PI[k] = v;
+  }
+#pragma unroll
+  for (int k = 0; k <= q; ++k) P[k] = 1.0 / PI[k];
+}
+
+__device__ __forceinline__ double ulp_of(double x) {  // Julia eps(x)
+  x = fabs(x);
+  if (x == 0.0) return 4.9406564584124654e-324;
+  const long long bits = __double_as_longlong(x);
+  return __longlong_as_double(bits + 1) - x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Model: EK1 with the full D x D covariance (src/perform_step.jl, alg isa EK1)
+// ---------------------------------------------------------------------------------------------
+template <class VF_, int q_>
+struct DenseEK1 {
+  using VF = VF_;
+  static constexpr int d = VF::d, q = q_, D = d * (q + 1), ND = 1;
+  static constexpr bool IS_EK1 = true;
+  using Fac = Factor<d, q>;
+  static constexpr int REC = 1 + ND + D + Fac::LEN;  // t, diffusion, mean, factor
+
+  struct State {
+    double m[D];
+    Fac F;
+  };
+
+  __device__ __forceinline__ static void scale(State& s, const double (&sc)[q + 1]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) s.m[i] *= sc[i / d];
+    s.F.scale_blocks(sc);
+  }
+
+  // One attempted step in P(h) coordinates.  diffusion in {dynamic, fixed, fixedMAP}.
+  __device__ __forceinline__ static void step(State& s, const double* p, double pi0, double pi1, int diffusion,
+                                              const IwpConsts& C, double (&u_new)[d], double (&err)[d],
+                                              double (&local)[ND], double& loglik) {
+    apply_A<d, q>(s.m);  // predict_mean!  src/filtering.jl:22-25
+    double uhat[d], fu[d], J[d][d], Jp[d][d], z[d];
+#pragma unroll
+    for (int i = 0; i < d; ++i) uhat[i] = pi0 * s.m[i];  // src/perform_step.jl:44
+    VF::template f<double>(uhat, p, fu);                  // :106
+    VF::jac(uhat, p, J);                                  // :116-122
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+      z[i] = fma(pi1, s.m[d + i], -fu[i]);  // :108
+#pragma unroll
+      for (int j = 0; j < d; ++j) Jp[i][j] = pi0 * J[i][j];
+    }
+    // B = H Q H' with H = (E1 - J E0) P^-1  (:125; src/diffusions.jl:77)
+    double B[d][d];
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < d; ++k) acc = fma(Jp[i][k], Jp[j][k], acc);
+        acc *= C.Qt[0][0];
+        acc = fma(-pi1 * C.Qt[0][1], Jp[i][j] + Jp[j][i], acc);
+        if (i == j) acc = fma(pi1 * pi1, C.Qt[1][1], acc);
+        B[i][j] = acc;
+        B[j][i] = acc;
+      }
+    }
+    double sig = 1.0;
+    if (diffusion == DIFF_DYNAMIC) {
+      // sigma^2 = z' B^-1 z / d via Cholesky of the d x d matrix (src/diffusions.jl:77-79)
+      double Lb[d][d], yb[d];
+      double ss = 0.0;
+#pragma unroll
+      for (int j = 0; j < d; ++j) {
+        double djj = B[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) djj = fma(-Lb[j][k], Lb[j][k], djj);
+        const double ljj = sqrt(djj);
+        const double il = 1.0 / ljj;
+        Lb[j][j] = ljj;
+#pragma unroll
+        for (int i = j + 1; i < d; ++i) {
+          double v = B[i][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) v = fma(-Lb[i][k], Lb[j][k], v);
+          Lb[i][j] = v * il;
+        }
+        double yy = z[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) yy = fma(-Lb[j][k], yb[k], yy);
+        yb[j] = yy * il;
+        ss = fma(yb[j], yb[j], ss);
+      }
+      local[0] = ss / double(d);
+      sig = sqrt(local[0]);
+    }
+    double Rtop[d][D];
+    cov_filter_step<d, q, true>(s.F, Jp, sig, pi1, 1.0 / pi1, C, Rtop);  // predict_cov! + update!
+    // innovation: S_z = G G', G = Rtop[:, :d]' lower triangular; y = G^-1 z
+    double y[d];
+    double yy2 = 0.0, logdet = 0.0;
+#pragma unroll
+    for (int a = 0; a < d; ++a) {
+      double acc = z[a];
+#pragma unroll
+      for (int b = 0; b < a; ++b) acc = fma(-Rtop[b][a], y[b], acc);
+      const double raa = Rtop[a][a];
+      y[a] = (raa != 0.0) ? acc / raa : 0.0;
+      yy2 = fma(y[a], y[a], yy2);
+      logdet += log(fabs(raa));
+    }
+    loglik = -0.5 * (yy2 + 2.0 * logdet + double(d) * 1.8378770664093453);  // :66
+    if (diffusion != DIFF_DYNAMIC) local[0] = yy2 / double(d);              // src/diffusions.jl:25,52
+    // mean update: mu+ = mu- - K z  (src/filtering.jl:87) in primed coordinates
+    double m0old[d];
+#pragma unroll
+    for (int b = 0; b < d; ++b) {
+      m0old[b] = s.m[b];
+      double acc = s.m[b];
+#pragma unroll
+      for (int a = 0; a < d; ++a) acc = fma(-Rtop[a][d + b], y[a], acc);
+      s.m[b] = acc;
+    }
+#pragma unroll
+    for (int i = 2 * d; i < D; ++i) {
+      double acc = s.m[i];
+#pragma unroll
+      for (int a = 0; a < d; ++a) acc = fma(-Rtop[a][i], y[a], acc);
+      s.m[i] = acc;
+    }
+    const double ipi1 = 1.0 / pi1;
+#pragma unroll
+    for (int b = 0; b < d; ++b) {
+      double acc = fu[b];
+#pragma unroll
+      for (int bb = 0; bb < d; ++bb) acc = fma(Jp[b][bb], s.m[bb] - m0old[bb], acc);
+      s.m[d + b] = acc * ipi1;
+    }
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+      u_new[i] = pi0 * s.m[i];              // src/perform_step.jl:70
+      err[i] = sqrt(local[0] * B[i][i]);    // :155
+    }
+  }
+
+  __device__ __forceinline__ static void store(const State& s, double* base, long long stride) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) base[(long long)i * stride] = s.m[i];
+    s.F.store(base + (long long)D * stride, stride);
+  }
+  __device__ __forceinline__ static void load(State& s, const double* base, long long stride) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) s.m[i] = base[(long long)i * stride];
+    s.F.load(base + (long long)D * stride, stride);
+  }
+  __device__ __forceinline__ static void final_cov(const State& s, const double (&sc)[q + 1], double* cov,
+                                                   long long stride) {
+    s.F.cov_entry_all(sc, cov, stride);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Model: EK0 with the Kronecker-factored covariance Sigma = Ctilde (x) I_d (not in
+// the reference, which is dense: src/caches.jl:73).  MV = dynamicMV keeps one factor per dimension.
+// ---------------------------------------------------------------------------------------------
+template <class VF_, int q_, bool MVDYN>
+struct KronEK0 {
+  using VF = VF_;
+  static constexpr int d = VF::d, q = q_, D = d * (q + 1);
+  static constexpr bool IS_EK1 = false;
+  static constexpr int NF = MVDYN ? d : 1;  // covariance factors
+  static constexpr int ND = d;              // diffusion slots (scalar models use slot 0, MV all)
+  using Fac = Factor<1, q>;
+  static constexpr int REC = 1 + ND + D + NF * Fac::LEN;
+
+  struct State {
+    double m[D];
+    Fac F[NF];
+  };
+
+  __device__ __forceinline__ static void scale(State& s, const double (&sc)[q + 1]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) s.m[i] *= sc[i / d];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) s.F[f].scale_blocks(sc);
+  }
+
+  __device__ __forceinline__ static void step(State& s, const double* p, double pi0, double pi1, int diffusion,
+                                              const IwpConsts& C, double (&u_new)[d], double (&err)[d],
+                                              double (&local)[ND], double& loglik) {
+    apply_A<d, q>(s.m);
+    double uhat[d], fu[d], z[d];
+#pragma unroll
+    for (int i = 0; i < d; ++i) uhat[i] = pi0 * s.m[i];
+    VF::template f<double>(uhat, p, fu);
+    double zz = 0.0;
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+      z[i] = fma(pi1, s.m[d + i], -fu[i]);
+      zz = fma(z[i], z[i], zz);
+    }
+    const double B = pi1 * pi1 * C.Qt[1][1];  // H Q H' = B I_d for EK0 (src/diffusions.jl:101-103)
+    const double Jp0[1][1] = {{0.0}};
+    const double ipi1 = 1.0 / pi1;
+    double R[NF][1][q + 1];
+    if (MVDYN) {
+      // src/diffusions.jl:104-108: Sigma_ii = max(z_i^2 / Q0_11, eps)
+#pragma unroll
+      for (int a = 0; a < d; ++a) {
+        local[a] = fmax(z[a] * z[a] / B, 2.220446049250313e-16);
+        cov_filter_step<1, q, false>(s.F[a < NF ? a : 0], Jp0, sqrt(local[a]), pi1, ipi1, C, R[a < NF ? a : 0]);
+      }
+    } else {
+      double sig = 1.0;
+      if (diffusion == DIFF_DYNAMIC) {
+        local[0] = zz / (double(d) * B);
+        sig = sqrt(local[0]);
+      }
+      cov_filter_step<1, q, false>(s.F[0], Jp0, sig, pi1, ipi1, C, R[0]);
+    }
+    double yy2 = 0.0, logdet = 0.0;
+#pragma unroll
+    for (int a = 0; a < d; ++a) {
+      const int f = MVDYN ? a : 0;
+      const double r00 = R[f][0][0];
+      const double ya = (r00 != 0.0) ? z[a] / r00 : 0.0;
+      yy2 = fma(ya, ya, yy2);
+      logdet += log(fabs(r00));
+      s.m[a] = fma(-R[f][0][1], ya, s.m[a]);
+#pragma unroll
+      for (int k = 2; k <= q; ++k) s.m[k * d + a] = fma(-R[f][0][k], ya, s.m[k * d + a]);
+      s.m[d + a] = fu[a] * ipi1;
+    }
+    loglik = -0.5 * (yy2 + 2.0 * logdet + double(d) * 1.8378770664093453);
+    if (diffusion == DIFF_FIXED || diffusion == DIFF_FIXED_MAP) local[0] = yy2 / double(d);
+    if (diffusion == DIFF_FIXED_MV) {
+      const double S11 = R[0][0][0] * R[0][0][0];  // src/diffusions.jl:136-138
+#pragma unroll
+      for (int a = 0; a < d; ++a) local[a] = z[a] * z[a] / S11;
+    }
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+      u_new[i] = pi0 * s.m[i];
+      const bool mv = (diffusion == DIFF_DYNAMIC_MV || diffusion == DIFF_FIXED_MV);
+      err[i] = sqrt((mv ? local[i] : local[0]) * B);
+    }
+  }
+
+  __device__ __forceinline__ static void store(const State& s, double* base, long long stride) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) base[(long long)i * stride] = s.m[i];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) s.F[f].store(base + (long long)(D + f * Fac::LEN) * stride, stride);
+  }
+  __device__ __forceinline__ static void load(State& s, const double* base, long long stride) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) s.m[i] = base[(long long)i * stride];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) s.F[f].load(base + (long long)(D + f * Fac::LEN) * stride, stride);
+  }
+  // calibration by the final global diffusion (src/integrator_utils.jl:7-12): scalar or per dimension
+  // (only ever called for static models, where NF == 1); gmv: per-dimension scales used at output.
+  __device__ __forceinline__ static void final_cov(const State& s, const double (&sc)[q + 1], double* cov,
+                                                   long long stride, const double (&dimscale)[d]) {
+    // Sigma[(k,a),(k',a')] = delta_aa' * dimscale[a] * sc[k] sc[k'] * (F_a F_a')[k][k']
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        const int ki = i / d, ai = i % d, kj = j / d, aj = j % d;
+        double v = 0.0;
+        if (ai == aj) {
+          const Fac& F = s.F[MVDYN ? ai : 0];
+          // rows of the 1-d factor: row 0 = block 0, row 1 = block 1, ...
+#pragma unroll
+          for (int c = 0; c < 1; ++c) v = fma(F.W[c][ki], F.W[c][kj], v);
+#pragma unroll
+          for (int c = 0; c < Fac::NZ; ++c)
+            if (ki >= 2 + c && kj >= 2 + c) v = fma(F.Lz[Fac::lz(c, ki - 2)], F.Lz[Fac::lz(c, kj - 2)], v);
+          v *= sc[ki] * sc[kj] * dimscale[ai];
+        }
+        cov[(long long)(i * (i + 1) / 2 + j) * stride] = v;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// ode_determine_initdt (Hairer; OrdinaryDiffEq).  Two f evaluations.
+// ---------------------------------------------------------------------------------------------
+template <class VF, int q>
+__device__ __forceinline__ double initdt(const double* u0, const double* p, const CtrlParams& K) {
+  constexpr int d = VF::d;
+  double f0[d], f1[d], u1[d], sk[d];
+  VF::template f<double>(u0, p, f0);
+  double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < d; ++i) {
+    sk[i] = K.abstol + fabs(u0[i]) * K.reltol;
+    const double a = u0[i] / sk[i], b = f0[i] / sk[i];
+    d0 = fma(a, a, d0);
+    d1 = fma(b, b, d1);
+  }
+  d0 = sqrt(d0 / double(d));
+  d1 = sqrt(d1 / double(d));
+  double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+  dt0 = fmin(dt0, K.dtmax);
+  if (dt0 < 10.0 * 2.220446049250313e-16) return 1e-6;
+#pragma unroll
+  for (int i = 0; i < d; ++i) u1[i] = fma(dt0, f0[i], u0[i]);
+  VF::template f<double>(u1, p, f1);
+  double d2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < d; ++i) {
+    const double c = (f1[i] - f0[i]) / sk[i];
+    d2 = fma(c, c, d2);
+  }
+  d2 = sqrt(d2 / double(d)) / dt0;
+  const double mx = fmax(d1, d2);
+  double dt1;
+  if (mx <= 1e-15)
+    dt1 = fmax(1e-6, dt0 * 1e-3);
+  else
+    dt1 = pow(10.0, -(2.0 + log10(mx)) / double(q + 1));
+  return fmin(fmin(100.0 * dt0, dt1), K.dtmax);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------
+template <class M, bool ADAPTIVE>
+__global__ void __launch_bounds__(128) filter_kernel(const FilterParams prm) {
+  using VF = typename M::VF;
+  constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= prm.n) return;
+  const long long n = prm.n;
+  const CtrlParams& K = prm.K;
+  const int diffusion = prm.diffusion;
+  const bool is_static = (diffusion == DIFF_FIXED || diffusion == DIFF_FIXED_MAP || diffusion == DIFF_FIXED_MV);
+  const bool is_mv = (diffusion == DIFF_DYNAMIC_MV || diffusion == DIFF_FIXED_MV);
+
+  double p[VF::np], u0[d];
+#pragma unroll
+  for (int i = 0; i < VF::np; ++i) p[i] = prm.p[(long long)i * n + tid];
+#pragma unroll
+  for (int i = 0; i < d; ++i) u0[i] = prm.u0[(long long)i * n + tid];
+
+  typename M::State st;  // natural coordinates between steps when ADAPTIVE, P(hcur) coordinates otherwise
+  taylor_init<VF, q>(u0, p, st.m);
+  if constexpr (M::IS_EK1) {
+    st.F.zero();
+  } else {
+#pragma unroll
+    for (int f = 0; f < M::NF; ++f) st.F[f].zero();
+  }
+
+  double t = K.t0;
+  int iter = 0, nacc = 0, nrej = 0, nfe = 0, ret = RET_SUCCESS, nsaved = 0;
+  double gsaved[ND];  // last saved global diffusion (sol.diffusions[end])
+#pragma unroll
+  for (int i = 0; i < ND; ++i) gsaved[i] = 1.0;  // initial_diffusion, src/diffusions.jl:8
+  double uprev[d];
+#pragma unroll
+  for (int i = 0; i < d; ++i) uprev[i] = u0[i];
+  double ll = 0.0;
+
+  auto save = [&](const typename M::State& sv, double tt, const double (&g)[ND]) {
+    if (nsaved >= prm.max_saved) {
+      ret = RET_HISTORY_FULL;
+      return;
+    }
+    double* base = prm.hist + ((long long)nsaved * REC) * n + tid;
+    base[0] = tt;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) base[(long long)(1 + i) * n] = g[i];
+    M::store(sv, base + (long long)(1 + ND) * n, n);
+    ++nsaved;
+  };
+  if (prm.save_mode != SAVE_FINAL) save(st, t, gsaved);
+
+  double dt;
+  if (ADAPTIVE) {
+    if (K.dt > 0.0) {
+      dt = K.dt;
+    } else {
+      dt = initdt<VF, q>(u0, p, K);
+      nfe += 2;
+    }
+  } else {
+    dt = K.dt;
+  }
+  double dtpropose = dt, qold = K.qoldinit, q11 = 1.0;
+  bool accepted_prev = true;
+  double hcur = -1.0;  // fixed-step mode: the h the state is currently preconditioned with (<0: natural)
+  double Pk[q + 1], PIk[q + 1];
+#pragma unroll
+  for (int k = 0; k <= q; ++k) Pk[k] = PIk[k] = 1.0;
+
+  while (t < K.t1) {
+    // ---- loopheader! ----
+    if (iter > 0) {
+      if (accepted_prev)
+        dt = dtpropose;
+      else
+        dt = dt / fmin(1.0 / K.qmin, q11 / K.gamma);
+    }
+    ++iter;
+    if (iter > K.maxiters) {
+      ret = RET_MAXITERS;
+      break;
+    }
+    if (ADAPTIVE) {
+      dt = fmin(dt, K.dtmax);
+      dt = fmax(dt, K.dtmin);
+      dt = fmin(dt, K.t1 - t);
+    } else {
+      dt = fmin(K.dt, K.t1 - t);
+    }
+    if (dt != dt) {
+      ret = RET_DTNAN;
+      break;
+    }
+    if (ADAPTIVE && iter > 1 && !accepted_prev && fabs(dt) <= fabs(K.dtmin)) {
+      ret = RET_DTMIN;
+      break;
+    }
+    // ---- perform_step! ----
+    typename M::State old;
+    if (ADAPTIVE) {
+      old = st;
+      precond_scales<q>(dt, Pk, PIk);
+      M::scale(st, Pk);  // x = P * x   (src/perform_step.jl:38)
+    } else if (dt != hcur) {
+      double Pn[q + 1], PIn[q + 1], sc[q + 1];
+      precond_scales<q>(dt, Pn, PIn);
+#pragma unroll
+      for (int k = 0; k <= q; ++k) {
+        sc[k] = Pn[k] * PIk[k];
+        Pk[k] = Pn[k];
+        PIk[k] = PIn[k];
+      }
+      M::scale(st, sc);
+      hcur = dt;
+    }
+    double unew[d], err[d], local[ND], lls;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) local[i] = 1.0;
+    M::step(st, p, PIk[0], PIk[1], diffusion, prm.C, unew, err, local, lls);
+    ++nfe;
+    // global diffusion (src/diffusions.jl): success_iter == number of accepted steps so far
+    double gcur[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      if (!is_mv && i > 0) {
+        gcur[i] = 1.0;
+        continue;
+      }
+      if (diffusion == DIFF_DYNAMIC || diffusion == DIFF_DYNAMIC_MV) {
+        gcur[i] = local[i];
+      } else if (diffusion == DIFF_FIXED || diffusion == DIFF_FIXED_MV) {
+        gcur[i] = (nacc == 0) ? local[i] : gsaved[i] + (local[i] - gsaved[i]) / double(nacc);  // :33,:150
+      } else {  // fixedMAP :46-68
+        const double Nn = double(nacc + 1), al = 0.5, be = 0.5;
+        if (nacc == 0) {
+          gcur[i] = (be + 0.5 * local[i]) / (al + Nn * d / 2.0 + 1.0);
+        } else {
+          const double res_prev = (gsaved[i] * (al + (Nn - 1.0) * d / 2.0 + 1.0) - be) * 2.0;
+          gcur[i] = (be + 0.5 * (res_prev + local[i])) / (al + Nn * d / 2.0 + 1.0);
+        }
+      }
+    }
+    double EEst = 0.0;
+    bool finite = true;
+    if (ADAPTIVE) {
+      // calculate_residuals! + ODE_DEFAULT_NORM (src/perform_step.jl:78-84)
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < d; ++i) {
+        const double r = dt * err[i] / (K.abstol + fmax(fabs(uprev[i]), fabs(unew[i])) * K.reltol);
+        acc = fma(r, r, acc);
+      }
+      EEst = sqrt(acc / double(d));
+    }
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+      uprev[i] = unew[i];  // integ.u .= u_filt, even when rejected (:86)
+      finite = finite && (fabs(unew[i]) <= 1.79769313486231570e308);
+    }
+    const bool commit = !ADAPTIVE || (EEst < 1.0);  // :89
+    const bool accept = !ADAPTIVE || (EEst <= 1.0); // loopfooter!
+    if (ADAPTIVE) {
+      if (commit) {
+        M::scale(st, PIk);  // PI * x_filt (:75)
+      } else {
+        st = old;
+      }
+    }
+    if (commit) ll += lls;
+    if (!finite) {
+      ret = RET_NONFINITE;  // OrdinaryDiffEq check_error!: unstable_check
+      break;
+    }
+    // ---- loopfooter! ----
+    const double ttmp = t + dt;
+    if (ADAPTIVE) {
+      double qc;
+      if (EEst == 0.0) {
+        qc = 1.0 / K.qmax;
+      } else {
+        q11 = pow(EEst, K.beta1);
+        qc = q11 / pow(qold, K.beta2);
+        qc = fmax(1.0 / K.qmax, fmin(1.0 / K.qmin, qc / K.gamma));
+      }
+      if (accept) {
+        ++nacc;
+        if (K.qsteady_min <= qc && qc <= K.qsteady_max) qc = 1.0;
+        qold = fmax(EEst, K.qoldinit);
+        const double dtnew = dt / qc;
+        t = (fabs(ttmp - K.t1) < 10.0 * ulp_of(fmax(t, K.t1))) ? K.t1 : ttmp;
+        dtpropose = fmax(K.dtmin, fmin(K.dtmax, dtnew));
+      } else {
+        ++nrej;
+      }
+    } else {
+      ++nacc;
+      t = (fabs(ttmp - K.t1) < 10.0 * ulp_of(fmax(t, K.t1))) ? K.t1 : ttmp;
+      dtpropose = dt;
+    }
+    accepted_prev = accept;
+    if (accept) {
+#pragma unroll
+      for (int i = 0; i < ND; ++i) gsaved[i] = gcur[i];
+      // savevalues! (src/integrator_utils.jl:33-48)
+      const bool want = (prm.save_mode == SAVE_EVERY) ||
+                        (prm.save_mode == SAVE_STRIDE && (nacc % prm.save_stride == 0 || !(t < K.t1)));
+      if (want) {
+        if (ADAPTIVE) {
+          save(st, t, gsaved);
+        } else {
+          typename M::State nat = st;
+          M::scale(nat, PIk);
+          save(nat, t, gsaved);
+        }
+        if (ret == RET_HISTORY_FULL) break;
+      }
+    }
+  }
+
+  // ---- outputs ----
+  double sc[q + 1];
+#pragma unroll
+  for (int k = 0; k <= q; ++k) sc[k] = (ADAPTIVE || hcur < 0.0) ? 1.0 : PIk[k];
+  if (prm.mean) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) prm.mean[(long long)i * n + tid] = st.m[i] * sc[i / d];
+  }
+  // postamble! calibration for static models (src/integrator_utils.jl:4-18)
+  double dimscale[d];
+#pragma unroll
+  for (int a = 0; a < d; ++a) dimscale[a] = 1.0;
+  if (is_static && nacc > 0) {
+#pragma unroll
+    for (int a = 0; a < d; ++a) dimscale[a] = is_mv ? gsaved[a < ND ? a : 0] : gsaved[0];
+    ll = nan("");
+  }
+  if (prm.cov) {
+    if constexpr (M::IS_EK1) {
+      double sc2[q + 1];
+      const double g = sqrt(dimscale[0]);
+#pragma unroll
+      for (int k = 0; k <= q; ++k) sc2[k] = sc[k] * g;
+      M::final_cov(st, sc2, prm.cov + tid, n);
+    } else {
+      M::final_cov(st, sc, prm.cov + tid, n, dimscale);
+    }
+  }
+  if (prm.final_diff) {
+#pragma unroll
+    for (int i = 0; i < ND; ++i) prm.final_diff[(long long)i * n + tid] = gsaved[i];
+  }
+  if (prm.t_final) prm.t_final[tid] = t;
+  if (prm.loglik) prm.loglik[tid] = ll;
+  prm.retcode[tid] = ret;
+  prm.naccept[tid] = nacc;
+  prm.nreject[tid] = nrej;
+  prm.nf[tid] = nfe;
+  prm.njacs[tid] = M::IS_EK1 ? (nfe - ((ADAPTIVE && !(K.dt > 0.0)) ? 2 : 0)) : 0;
+  prm.n_saved[tid] = nsaved;
+}
+
+}  // namespace pnde

@@ -1,0 +1,6 @@
+// Template instantiations for the fhn_readme vector field (one translation unit per field so that the
+// build parallelises).
+#include "inst_common.cuh"
+namespace pnde {
+PNDE_DEFINE_OPS(ops_fhn_readme, VfFhnReadme)
+}  // namespace pnde

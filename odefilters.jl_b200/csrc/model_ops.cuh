@@ -1,0 +1,60 @@
+// Per-model dispatch table: every (vector field, order, algorithm) combination is a separate
+// template instantiation; the C-ABI layer (pnde_api.cu) looks its launchers up at pnde_create time.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "filter_kernel.cuh"
+
+namespace pnde {
+
+struct ConvertParams {
+  long long n;           // trajectories in the ensemble
+  long long traj_begin, traj_end;
+  long long max_saved;
+  const int* n_saved;        // [n]
+  const long long* offsets;  // [traj_end - traj_begin + 1] (device)
+  const double* hist;        // filtered records
+  const double* smooth;      // smoothed records (or nullptr)
+  const double* final_diff;  // [ND][n]
+  int which;                 // 0 filtered, 1 smoothed
+  int calibrate;             // static diffusion model: scale by the final global diffusion
+  int is_mv;
+  int marginals;             // 1: write u / cov_u only
+  double* t;                 // [total]
+  double* mean;              // [total][D] or [total][d]
+  double* cov;               // [total][D(D+1)/2] or [total][d(d+1)/2]
+  double* diffusion;         // [total][nd_out]
+  int nd_out;
+};
+
+struct SmoothParams {
+  long long n;
+  long long max_saved;
+  const int* n_saved;
+  const double* hist;
+  double* smooth;            // [max_saved][SREC][n]
+  const double* final_diff;  // [ND][n]
+  int calibrate;
+  int is_mv;
+  int* status;               // [n] non-zero: non-finite / negative-variance flag (src/smoothing.jl:25,59)
+  IwpConsts C;
+};
+
+struct ModelOps {
+  int d, q, D, nd, rec, srec, np;
+  bool ek1;
+  cudaError_t (*launch_filter)(const FilterParams&, bool adaptive, cudaStream_t);
+  cudaError_t (*launch_convert)(const ConvertParams&, cudaStream_t);
+  cudaError_t (*launch_smooth)(const SmoothParams&, cudaStream_t);
+};
+
+// defined in inst_*.cu
+const ModelOps* ops_fhn_readme(int alg, int q, bool mvdyn);
+const ModelOps* ops_fhn_lib(int alg, int q, bool mvdyn);
+const ModelOps* ops_lotka_volterra(int alg, int q, bool mvdyn);
+const ModelOps* ops_vanderpol(int alg, int q, bool mvdyn);
+const ModelOps* ops_linear2(int alg, int q, bool mvdyn);
+const ModelOps* ops_logistic(int alg, int q, bool mvdyn);
+const ModelOps* ops_linear1(int alg, int q, bool mvdyn);
+
+}  // namespace pnde

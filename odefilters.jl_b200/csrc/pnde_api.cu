@@ -1,0 +1,680 @@
+// C-ABI layer of libpnde.so (see include/pnde.h).  Host logic only: configuration checks, IWP
+// constants (src/priors.jl:7-59), device buffers, kernel dispatch, result marshalling.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pnde.h"
+#include "model_ops.cuh"
+
+using namespace pnde;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= bytes && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    if (want == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// Qtilde and its Cholesky factor for the once-per-solve constants (src/priors.jl:29-55, d = 1).
+bool build_iwp(int q, IwpConsts& C) {
+  memset(&C, 0, sizeof(C));
+  double fact[2 * QMAX + 2];
+  fact[0] = 1.0;
+  for (int i = 1; i < 2 * QMAX + 2; ++i) fact[i] = fact[i - 1] * i;
+  for (int r = 0; r <= q; ++r)
+    for (int c = 0; c <= q; ++c) C.Qt[r][c] = 1.0 / (double(2 * q + 1 - r - c) * fact[q - r] * fact[q - c]);
+  for (int j = 0; j <= q; ++j) {
+    double s = C.Qt[j][j];
+    for (int k = 0; k < j; ++k) s -= C.Lt[j][k] * C.Lt[j][k];
+    if (!(s > 0.0)) return false;
+    C.Lt[j][j] = sqrt(s);
+    for (int i = j + 1; i <= q; ++i) {
+      double t = C.Qt[i][j];
+      for (int k = 0; k < j; ++k) t -= C.Lt[i][k] * C.Lt[j][k];
+      C.Lt[i][j] = t / C.Lt[j][j];
+    }
+  }
+  return true;
+}
+
+const ModelOps* find_ops(int vf, int alg, int q, bool mvdyn) {
+  switch (vf) {
+    case PNDE_VF_FHN_README: return ops_fhn_readme(alg, q, mvdyn);
+    case PNDE_VF_FHN_LIB: return ops_fhn_lib(alg, q, mvdyn);
+    case PNDE_VF_LOTKA_VOLTERRA: return ops_lotka_volterra(alg, q, mvdyn);
+    case PNDE_VF_VANDERPOL: return ops_vanderpol(alg, q, mvdyn);
+    case PNDE_VF_LINEAR2: return ops_linear2(alg, q, mvdyn);
+    case PNDE_VF_LOGISTIC: return ops_logistic(alg, q, mvdyn);
+    case PNDE_VF_LINEAR1: return ops_linear1(alg, q, mvdyn);
+    default: return nullptr;
+  }
+}
+
+}  // namespace
+
+struct pnde_handle {
+  pnde_config cfg;
+  const ModelOps* ops = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  IwpConsts C;
+  long long n = 0;
+  long long max_saved = 0;
+  bool ran = false, smoothed = false;
+  double filter_ms = 0.0, smooth_ms = 0.0;
+  long long launches = 0;
+  DevBuf u0, p, mean, cov, t_final, loglik, final_diff, retcode, naccept, nreject, nf, njacs, n_saved, hist, smooth,
+      sstatus, scratch_off, scratch_out;
+  std::string err;
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char* what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return PNDE_ERR_CUDA;
+  }
+};
+
+#define CK(call, what)                                   \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return h->cuda_fail(e__, what); \
+  } while (0)
+
+extern "C" {
+
+int pnde_default_config(pnde_config* cfg, int32_t alg, int32_t order, int32_t vf_kind) {
+  if (!cfg) return PNDE_ERR_ARG;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = PNDE_ABI_VERSION;
+  cfg->alg = alg;
+  cfg->order = order;
+  cfg->vf_kind = vf_kind;
+  cfg->d = 0;
+  cfg->diffusion = PNDE_DIFF_DYNAMIC;
+  cfg->smooth = 0;
+  cfg->adaptive = 1;
+  cfg->save_mode = PNDE_SAVE_FINAL;
+  cfg->save_stride = 1;
+  cfg->device = -1;
+  cfg->abstol = 1e-6;
+  cfg->reltol = 1e-3;
+  cfg->dt = 0.0;
+  cfg->t0 = 0.0;
+  cfg->t1 = 1.0;
+  cfg->qmin = 1.0 / 5.0;
+  cfg->qmax = 10.0;
+  cfg->gamma = 9.0 / 10.0;
+  cfg->qsteady_min = 1.0;
+  cfg->qsteady_max = 1.0;
+  cfg->qoldinit = 1e-4;
+  cfg->beta1 = 0.0;  // <= 0: 7/(10(q+1)), src/alg_utils.jl:24
+  cfg->beta2 = 0.0;  // <= 0: 2/(5(q+1)),  src/alg_utils.jl:23
+  cfg->dtmin = 0.0;
+  cfg->dtmax = 0.0;  // <= 0: t1 - t0
+  cfg->maxiters = 100000;
+  cfg->max_saved = 0;
+  return PNDE_OK;
+}
+
+int pnde_create(const pnde_config* cfg, pnde_handle** out) {
+  if (!cfg || !out) {
+    g_create_error = "null argument";
+    return PNDE_ERR_ARG;
+  }
+  *out = nullptr;
+  if (cfg->abi_version != PNDE_ABI_VERSION) {
+    g_create_error = "abi_version mismatch";
+    return PNDE_ERR_ARG;
+  }
+  if (cfg->alg != PNDE_ALG_EK0 && cfg->alg != PNDE_ALG_EK1) {
+    g_create_error = "alg must be PNDE_ALG_EK0 or PNDE_ALG_EK1";
+    return PNDE_ERR_ARG;
+  }
+  if (cfg->order < 1 || cfg->order > 5) {
+    g_create_error = "order must be in 1..5 for the built-in kernels";
+    return PNDE_ERR_UNSUPPORTED;
+  }
+  if (cfg->diffusion < 0 || cfg->diffusion > 4) {
+    g_create_error = "unknown diffusion model";
+    return PNDE_ERR_ARG;
+  }
+  const bool mv = (cfg->diffusion == PNDE_DIFF_DYNAMIC_MV || cfg->diffusion == PNDE_DIFF_FIXED_MV);
+  if (mv && cfg->alg != PNDE_ALG_EK0) {
+    // the reference asserts this (src/diffusions.jl:97-101,128,134)
+    g_create_error = "MV diffusion models are EK0-only (src/diffusions.jl:97)";
+    return PNDE_ERR_ARG;
+  }
+  if (!cfg->adaptive && !(cfg->dt > 0.0)) {
+    g_create_error = "Fixed timestep methods require a choice of dt";  // test/errors.jl:16-20
+    return PNDE_ERR_ARG;
+  }
+  if (!(cfg->t1 > cfg->t0)) {
+    g_create_error = "tspan must satisfy t1 > t0";
+    return PNDE_ERR_ARG;
+  }
+  if (cfg->smooth && cfg->save_mode != PNDE_SAVE_EVERY) {
+    g_create_error = "smooth requires save_mode = PNDE_SAVE_EVERY (src/perform_step.jl:3)";
+    return PNDE_ERR_ARG;
+  }
+  if (cfg->save_mode == PNDE_SAVE_STRIDE && cfg->save_stride < 1) {
+    g_create_error = "save_stride must be >= 1";
+    return PNDE_ERR_ARG;
+  }
+  const ModelOps* ops = find_ops(cfg->vf_kind, cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV);
+  if (!ops) {
+    g_create_error = "no built-in kernel for this (vf_kind, alg, order)";
+    return PNDE_ERR_UNSUPPORTED;
+  }
+  if (cfg->d != 0 && cfg->d != ops->d) {
+    g_create_error = "d does not match the vector field";
+    return PNDE_ERR_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+    return PNDE_ERR_CUDA;
+  }
+  int dev = cfg->device;
+  if (dev < 0) {
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+      g_create_error = std::string("cudaGetDevice: ") + cudaGetErrorString(e);
+      return PNDE_ERR_CUDA;
+    }
+  }
+  if (dev >= ndev) {
+    g_create_error = "device ordinal out of range";
+    return PNDE_ERR_ARG;
+  }
+  pnde_handle* h = new pnde_handle();
+  h->cfg = *cfg;
+  h->cfg.d = ops->d;
+  h->ops = ops;
+  h->device = dev;
+  if (!build_iwp(cfg->order, h->C)) {
+    delete h;
+    g_create_error = "IWP process-noise Cholesky failed";
+    return PNDE_ERR_ARG;
+  }
+  const int q = cfg->order;
+  if (!(h->cfg.beta2 > 0.0)) h->cfg.beta2 = 2.0 / (5.0 * (q + 1));
+  if (!(h->cfg.beta1 > 0.0)) h->cfg.beta1 = 7.0 / (10.0 * (q + 1));
+  if (!(h->cfg.dtmax > 0.0)) h->cfg.dtmax = cfg->t1 - cfg->t0;
+  if (h->cfg.maxiters <= 0) h->cfg.maxiters = 100000;
+  e = cudaSetDevice(dev);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("stream/event creation: ") + cudaGetErrorString(e);
+    delete h;
+    return PNDE_ERR_CUDA;
+  }
+  *out = h;
+  return PNDE_OK;
+}
+
+int pnde_destroy(pnde_handle* h) {
+  if (!h) return PNDE_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->u0,      &h->p,      &h->mean,  &h->cov,     &h->t_final, &h->loglik,
+                    &h->final_diff, &h->retcode, &h->naccept, &h->nreject, &h->nf,      &h->njacs,
+                    &h->n_saved, &h->hist,   &h->smooth, &h->sstatus, &h->scratch_off, &h->scratch_out};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return PNDE_OK;
+}
+
+const char* pnde_last_error(const pnde_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t pnde_state_dim(const pnde_handle* h) { return h ? h->ops->D : 0; }
+int64_t pnde_n_params(const pnde_handle* h) { return h ? h->ops->np : 0; }
+int64_t pnde_record_len(const pnde_handle* h) { return h ? h->ops->rec : 0; }
+
+static long long derive_max_saved(const pnde_handle* h) {
+  const pnde_config& c = h->cfg;
+  if (c.save_mode == PNDE_SAVE_FINAL) return 0;
+  if (c.max_saved > 0) return c.max_saved;
+  if (c.adaptive) return 0;  // must be given
+  // fixed step: number of steps of the t += dt loop (+ possible sliver step) + initial state
+  long long steps = (long long)ceil((c.t1 - c.t0) / c.dt) + 2;
+  if (c.save_mode == PNDE_SAVE_STRIDE) steps = steps / c.save_stride + 3;
+  return steps + 1;
+}
+
+int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* p) {
+  if (!h) return PNDE_ERR_ARG;
+  if (n_traj <= 0 || !u0 || (!p && h->ops->np > 0)) return h->fail(PNDE_ERR_ARG, "pnde_upload: bad arguments");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const ModelOps* o = h->ops;
+  const size_t n = (size_t)n_traj;
+  const long long ms = derive_max_saved(h);
+  if (h->cfg.save_mode != PNDE_SAVE_FINAL && ms <= 0)
+    return h->fail(PNDE_ERR_ARG, "adaptive runs that save history need cfg.max_saved > 0");
+  h->max_saved = ms;
+  CK(h->u0.ensure(n * o->d * 8), "alloc u0");
+  CK(h->p.ensure(n * (o->np > 0 ? o->np : 1) * 8), "alloc p");
+  CK(h->mean.ensure(n * o->D * 8), "alloc mean");
+  CK(h->cov.ensure(n * (size_t)(o->D * (o->D + 1) / 2) * 8), "alloc cov");
+  CK(h->t_final.ensure(n * 8), "alloc t_final");
+  CK(h->loglik.ensure(n * 8), "alloc loglik");
+  CK(h->final_diff.ensure(n * o->nd * 8), "alloc final_diff");
+  CK(h->retcode.ensure(n * 4), "alloc retcode");
+  CK(h->naccept.ensure(n * 4), "alloc naccept");
+  CK(h->nreject.ensure(n * 4), "alloc nreject");
+  CK(h->nf.ensure(n * 4), "alloc nf");
+  CK(h->njacs.ensure(n * 4), "alloc njacs");
+  CK(h->n_saved.ensure(n * 4), "alloc n_saved");
+  if (ms > 0) {
+    cudaError_t e = h->hist.ensure(n * (size_t)ms * o->rec * 8);
+    if (e != cudaSuccess) {
+      h->err = std::string("history allocation (") + std::to_string(n * (size_t)ms * o->rec * 8) +
+               " bytes): " + cudaGetErrorString(e);
+      cudaGetLastError();
+      return PNDE_ERR_ALLOC;
+    }
+  }
+  CK(cudaMemcpyAsync(h->u0.p, u0, n * o->d * 8, cudaMemcpyHostToDevice, h->stream), "H2D u0");
+  if (o->np > 0) CK(cudaMemcpyAsync(h->p.p, p, n * o->np * 8, cudaMemcpyHostToDevice, h->stream), "H2D p");
+  h->n = n_traj;
+  h->ran = false;
+  h->smoothed = false;
+  return PNDE_OK;
+}
+
+int pnde_run(pnde_handle* h) {
+  if (!h) return PNDE_ERR_ARG;
+  if (h->n <= 0) return h->fail(PNDE_ERR_STATE, "pnde_run: nothing uploaded");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const pnde_config& c = h->cfg;
+  FilterParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.n = h->n;
+  fp.u0 = h->u0.as<double>();
+  fp.p = h->p.as<double>();
+  fp.mean = h->mean.as<double>();
+  fp.cov = h->cov.as<double>();
+  fp.t_final = h->t_final.as<double>();
+  fp.loglik = h->loglik.as<double>();
+  fp.final_diff = h->final_diff.as<double>();
+  fp.retcode = h->retcode.as<int>();
+  fp.naccept = h->naccept.as<int>();
+  fp.nreject = h->nreject.as<int>();
+  fp.nf = h->nf.as<int>();
+  fp.njacs = h->njacs.as<int>();
+  fp.n_saved = h->n_saved.as<int>();
+  fp.hist = h->hist.as<double>();
+  fp.max_saved = h->max_saved;
+  fp.save_mode = c.save_mode;
+  fp.save_stride = c.save_stride > 0 ? c.save_stride : 1;
+  fp.diffusion = c.diffusion;
+  fp.C = h->C;
+  fp.K.abstol = c.abstol;
+  fp.K.reltol = c.reltol;
+  fp.K.dt = c.dt;
+  fp.K.t0 = c.t0;
+  fp.K.t1 = c.t1;
+  fp.K.qmin = c.qmin;
+  fp.K.qmax = c.qmax;
+  fp.K.gamma = c.gamma;
+  fp.K.qsteady_min = c.qsteady_min;
+  fp.K.qsteady_max = c.qsteady_max;
+  fp.K.qoldinit = c.qoldinit;
+  fp.K.beta1 = c.beta1;
+  fp.K.beta2 = c.beta2;
+  fp.K.dtmin = c.dtmin;
+  fp.K.dtmax = c.dtmax;
+  fp.K.maxiters = c.maxiters;
+  CK(cudaEventRecord(h->ev[0], h->stream), "event record");
+  CK(h->ops->launch_filter(fp, c.adaptive != 0, h->stream), "filter kernel launch");
+  CK(cudaEventRecord(h->ev[1], h->stream), "event record");
+  h->launches = 1;
+  h->ran = true;
+  h->smoothed = false;
+  h->smooth_ms = 0.0;
+  return PNDE_OK;
+}
+
+int pnde_smooth(pnde_handle* h) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ran) return h->fail(PNDE_ERR_STATE, "pnde_smooth: run the filter first");
+  if (h->cfg.save_mode != PNDE_SAVE_EVERY)
+    return h->fail(PNDE_ERR_STATE, "pnde_smooth needs save_mode = PNDE_SAVE_EVERY");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const ModelOps* o = h->ops;
+  cudaError_t e = h->smooth.ensure((size_t)h->n * (size_t)h->max_saved * o->srec * 8);
+  if (e != cudaSuccess) {
+    h->err = std::string("smoothed-history allocation: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return PNDE_ERR_ALLOC;
+  }
+  CK(h->sstatus.ensure((size_t)h->n * 4), "alloc smoother status");
+  SmoothParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.n = h->n;
+  sp.max_saved = h->max_saved;
+  sp.n_saved = h->n_saved.as<int>();
+  sp.hist = h->hist.as<double>();
+  sp.smooth = h->smooth.as<double>();
+  sp.final_diff = h->final_diff.as<double>();
+  const int df = h->cfg.diffusion;
+  sp.calibrate = (df == PNDE_DIFF_FIXED || df == PNDE_DIFF_FIXED_MAP || df == PNDE_DIFF_FIXED_MV);
+  sp.is_mv = (df == PNDE_DIFF_DYNAMIC_MV || df == PNDE_DIFF_FIXED_MV);
+  sp.status = h->sstatus.as<int>();
+  sp.C = h->C;
+  CK(cudaEventRecord(h->ev[2], h->stream), "event record");
+  CK(o->launch_smooth(sp, h->stream), "smoother kernel launch");
+  CK(cudaEventRecord(h->ev[3], h->stream), "event record");
+  h->launches += 1;
+  h->smoothed = true;
+  return PNDE_OK;
+}
+
+int pnde_synchronize(pnde_handle* h) {
+  if (!h) return PNDE_ERR_ARG;
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  return PNDE_OK;
+}
+
+int pnde_last_run_ms(pnde_handle* h, double* filter_ms, double* smooth_ms) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]), "event elapsed");
+  h->filter_ms = ms;
+  if (h->smoothed) {
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]), "event elapsed");
+    h->smooth_ms = ms;
+  }
+  if (filter_ms) *filter_ms = h->filter_ms;
+  if (smooth_ms) *smooth_ms = h->smooth_ms;
+  return PNDE_OK;
+}
+
+int64_t pnde_last_launch_count(const pnde_handle* h) { return h ? h->launches : 0; }
+
+int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const double* p) {
+  int rc = pnde_upload(h, n_traj, u0, p);
+  if (rc != PNDE_OK) return rc;
+  rc = pnde_run(h);
+  if (rc != PNDE_OK) return rc;
+  if (h->cfg.smooth) {
+    rc = pnde_smooth(h);
+    if (rc != PNDE_OK) return rc;
+  }
+  return pnde_synchronize(h);
+}
+
+static int fetch_i32(pnde_handle* h, const DevBuf& b, std::vector<int>& out) {
+  out.resize((size_t)h->n);
+  CK(cudaMemcpyAsync(out.data(), b.p, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream), "D2H counts");
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  return PNDE_OK;
+}
+
+int pnde_query_sizes(pnde_handle* h, int64_t* n_saved_total, int64_t* max_saved) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  std::vector<int> ns;
+  int rc = fetch_i32(h, h->n_saved, ns);
+  if (rc != PNDE_OK) return rc;
+  long long tot = 0;
+  int mx = 0;
+  for (int v : ns) {
+    tot += v;
+    if (v > mx) mx = v;
+  }
+  if (n_saved_total) *n_saved_total = tot;
+  if (max_saved) *max_saved = mx;
+  return PNDE_OK;
+}
+
+int pnde_get_counts(pnde_handle* h, int64_t* naccept, int64_t* nreject, int64_t* nf, int64_t* njacs, int32_t* retcode,
+                    int64_t* n_saved) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  std::vector<int> tmp;
+  struct {
+    int64_t* dst;
+    const DevBuf* src;
+  } items[] = {{naccept, &h->naccept}, {nreject, &h->nreject}, {nf, &h->nf}, {njacs, &h->njacs}, {n_saved, &h->n_saved}};
+  for (auto& it : items) {
+    if (!it.dst) continue;
+    int rc = fetch_i32(h, *it.src, tmp);
+    if (rc != PNDE_OK) return rc;
+    for (long long i = 0; i < h->n; ++i) it.dst[i] = tmp[(size_t)i];
+  }
+  if (retcode) {
+    CK(cudaMemcpyAsync(retcode, h->retcode.p, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream), "D2H retcode");
+    CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  }
+  return PNDE_OK;
+}
+
+int pnde_get_final(pnde_handle* h, double* mean, double* cov, double* t_final, double* loglik) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const size_t n = (size_t)h->n;
+  const ModelOps* o = h->ops;
+  if (mean) CK(cudaMemcpyAsync(mean, h->mean.p, n * o->D * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
+  if (cov)
+    CK(cudaMemcpyAsync(cov, h->cov.p, n * (size_t)(o->D * (o->D + 1) / 2) * 8, cudaMemcpyDeviceToHost, h->stream),
+       "D2H cov");
+  if (t_final) CK(cudaMemcpyAsync(t_final, h->t_final.p, n * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
+  if (loglik) CK(cudaMemcpyAsync(loglik, h->loglik.p, n * 8, cudaMemcpyDeviceToHost, h->stream), "D2H loglik");
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  return PNDE_OK;
+}
+
+static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t te, int64_t* offsets, double* t,
+                            double* mean, double* cov, double* diffusion, bool marginals) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  if (h->cfg.save_mode == PNDE_SAVE_FINAL) return h->fail(PNDE_ERR_STATE, "no history was saved (save_mode = final)");
+  if (which == PNDE_HIST_SMOOTHED && !h->smoothed) return h->fail(PNDE_ERR_STATE, "history has not been smoothed");
+  if (which != PNDE_HIST_FILTERED && which != PNDE_HIST_SMOOTHED) return h->fail(PNDE_ERR_ARG, "bad 'which'");
+  if (tb < 0 || te > h->n || tb >= te || !offsets) return h->fail(PNDE_ERR_ARG, "bad trajectory range");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const ModelOps* o = h->ops;
+  std::vector<int> ns;
+  int rc = fetch_i32(h, h->n_saved, ns);
+  if (rc != PNDE_OK) return rc;
+  const long long ntr = te - tb;
+  std::vector<long long> off((size_t)ntr + 1);
+  off[0] = 0;
+  for (long long i = 0; i < ntr; ++i) off[(size_t)i + 1] = off[(size_t)i] + ns[(size_t)(tb + i)];
+  const long long total = off[(size_t)ntr];
+  for (long long i = 0; i <= ntr; ++i) offsets[i] = off[(size_t)i];
+  const int df = h->cfg.diffusion;
+  const bool is_mv = (df == PNDE_DIFF_DYNAMIC_MV || df == PNDE_DIFF_FIXED_MV);
+  const int nd_out = is_mv ? o->d : 1;
+  const int DM = marginals ? o->d : o->D;
+  const size_t nm = (size_t)total * DM, nc = (size_t)total * (size_t)(DM * (DM + 1) / 2), ndif = (size_t)total * nd_out;
+  CK(h->scratch_off.ensure(((size_t)ntr + 1) * 8), "alloc offsets");
+  CK(h->scratch_out.ensure(((size_t)total + nm + nc + ndif) * 8 + 64), "alloc history staging");
+  CK(cudaMemcpyAsync(h->scratch_off.p, off.data(), ((size_t)ntr + 1) * 8, cudaMemcpyHostToDevice, h->stream), "H2D offsets");
+  double* dt_ = h->scratch_out.as<double>();
+  double* dmean = dt_ + total;
+  double* dcov = dmean + nm;
+  double* ddif = dcov + nc;
+  ConvertParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.n = h->n;
+  cp.traj_begin = tb;
+  cp.traj_end = te;
+  cp.max_saved = h->max_saved;
+  cp.n_saved = h->n_saved.as<int>();
+  cp.offsets = h->scratch_off.as<long long>();
+  cp.hist = h->hist.as<double>();
+  cp.smooth = h->smooth.as<double>();
+  cp.final_diff = h->final_diff.as<double>();
+  cp.which = which;
+  cp.calibrate = (df == PNDE_DIFF_FIXED || df == PNDE_DIFF_FIXED_MAP || df == PNDE_DIFF_FIXED_MV);
+  cp.is_mv = is_mv;
+  cp.marginals = marginals ? 1 : 0;
+  cp.t = dt_;
+  cp.mean = dmean;
+  cp.cov = dcov;
+  cp.diffusion = ddif;
+  cp.nd_out = nd_out;
+  CK(o->launch_convert(cp, h->stream), "convert kernel launch");
+  if (t) CK(cudaMemcpyAsync(t, dt_, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
+  if (mean) CK(cudaMemcpyAsync(mean, dmean, nm * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
+  if (cov) CK(cudaMemcpyAsync(cov, dcov, nc * 8, cudaMemcpyDeviceToHost, h->stream), "D2H cov");
+  if (diffusion) CK(cudaMemcpyAsync(diffusion, ddif, ndif * 8, cudaMemcpyDeviceToHost, h->stream), "D2H diffusion");
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  return PNDE_OK;
+}
+
+int pnde_get_history(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end, int64_t* offsets, double* t,
+                     double* mean, double* cov, double* diffusion) {
+  return get_history_impl(h, which, traj_begin, traj_end, offsets, t, mean, cov, diffusion, false);
+}
+
+int pnde_get_marginals(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end, int64_t* offsets, double* t,
+                       double* u, double* cov_u) {
+  return get_history_impl(h, which, traj_begin, traj_end, offsets, t, u, cov_u, nullptr, true);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Roofline denominators (bench.py): FP64 FMA peak and HBM copy bandwidth of the bound device.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0,
+         x6 = x0 + 6.0, x7 = x0 + 7.0;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b);
+    x1 = fma(x1, a, b);
+    x2 = fma(x2, a, b);
+    x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b);
+    x5 = fma(x5, a, b);
+    x6 = fma(x6, a, b);
+    x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ a, double2* __restrict__ b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) b[i] = a[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+int pnde_measure_fp64_peak(int32_t device, double* tflops) {
+  if (!tflops) return PNDE_ERR_ARG;
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PNDE_ERR_CUDA;
+  cudaDeviceProp prop;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return PNDE_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  double* out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * 8) != cudaSuccess) return PNDE_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess || best == 0.0) return PNDE_ERR_CUDA;
+  *tflops = best;
+  return PNDE_OK;
+}
+
+int pnde_measure_hbm_copy(int32_t device, double* gbs) {
+  if (!gbs) return PNDE_ERR_ARG;
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PNDE_ERR_CUDA;
+  cudaDeviceProp prop;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return PNDE_ERR_CUDA;
+  const size_t bytes = (size_t)1 << 30;
+  double2 *a = nullptr, *b = nullptr;
+  if (cudaMalloc(&a, bytes) != cudaSuccess || cudaMalloc(&b, bytes) != cudaSuccess) {
+    if (a) cudaFree(a);
+    return PNDE_ERR_CUDA;
+  }
+  cudaMemset(a, 1, bytes);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    copy_kernel<<<prop.multiProcessorCount * 16, 256>>>(a, b, bytes / sizeof(double2));
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double g = 2.0 * bytes / (ms * 1e-3) / 1e9;
+    if (rep > 0 && g > best) best = g;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(a);
+  cudaFree(b);
+  if (cudaGetLastError() != cudaSuccess || best == 0.0) return PNDE_ERR_CUDA;
+  *gbs = best;
+  return PNDE_OK;
+}
+
+}  // extern "C"

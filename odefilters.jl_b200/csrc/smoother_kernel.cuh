@@ -1,0 +1,425 @@
+// Backward Rauch-Tung-Striebel pass over the saved filter history, one trajectory per thread.
+//
+// Reference being replaced: smooth_all! / smooth!  src/smoothing.jl:4-63  (algebra twin: smooth,
+// src/filtering.jl:136-154).  The reference forms G = Sigma A' inv(Sigma-) with a dense LU inverse
+// and triangularises the 3D x D stack [S'(I-GA)'; Q_L'G'; S_next'G'].  Here:
+//   stage 1  one Householder sweep over  [sig Q_L' | 0 ; (A S)' | S']  (the filter's own predict QR
+//            carried through D extra columns) gives  [R- X ; 0 Y]  with  G' = R-^-1 X  and
+//            Y'Y = Sigma - G Sigma- G'  (= (I-GA) Sigma (I-GA)' + G Q G', the backward-kernel noise);
+//   stage 2  Z = R-^-T S_next (lower triangular), T = X' Z = G S_next, mean += X' R-^-T (m_next - m-);
+//   stage 3  triangularise [Y ; T'] -> the smoothed factor, lower triangular.
+// G is never formed and no matrix is inverted.
+#pragma once
+#include "model_ops.cuh"
+
+namespace pnde {
+
+template <int dc, int q>
+struct SmoothCov {
+  static constexpr int D = dc * (q + 1);
+  static constexpr int R = D - dc;
+  static constexpr int NP = D * (D + 1) / 2;
+  __host__ __device__ static constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
+
+  // Householder triangularisation of the (NR1 + D) x D stack [Y ; T'] -> packed lower factor L (= R').
+  // Y: NR1 x D dense rows.  Tt: D x D where Tt[c][i] = T[i][c]; rows of the stack are Tt[c][:].
+  template <int NR1>
+  __device__ __forceinline__ static void triangularize(double (&Y)[NR1 > 0 ? NR1 : 1][D], double (&Tt)[D][D],
+                                                       double (&L)[NP], int& status) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      // pivot: Tt row c is NOT special here; use a virtual zero pivot row -> plain Householder on all
+      // rows with the first active row as pivot.  Rows are consumed in order: Y rows then Tt rows.
+      // Active rows at step c: all rows with index >= c in the concatenated order.
+      double n2 = 0.0;
+#pragma unroll
+      for (int i = c; i < NR1 + D; ++i) {
+        const double v = (i < NR1) ? Y[i < NR1 ? i : 0][c] : Tt[i - NR1 >= 0 ? i - NR1 : 0][c];
+        n2 = fma(v, v, n2);
+      }
+      const double pv = (c < NR1) ? Y[c < NR1 ? c : 0][c] : Tt[c - NR1 >= 0 ? c - NR1 : 0][c];
+      const double nrm = sqrt(n2);
+      const double snrm = copysign(nrm, pv);
+      const double v0 = pv + snrm;
+      const double beta = (n2 > 0.0) ? 1.0 / fma(fabs(pv), nrm, n2) : 0.0;
+      L[tri(c, c)] = -snrm;
+#pragma unroll
+      for (int j = c + 1; j < D; ++j) {
+        const double prj = (c < NR1) ? Y[c < NR1 ? c : 0][j] : Tt[c - NR1 >= 0 ? c - NR1 : 0][j];
+        double w = v0 * prj;
+#pragma unroll
+        for (int i = c + 1; i < NR1 + D; ++i) {
+          const double vc = (i < NR1) ? Y[i < NR1 ? i : 0][c] : Tt[i - NR1 >= 0 ? i - NR1 : 0][c];
+          const double vj = (i < NR1) ? Y[i < NR1 ? i : 0][j] : Tt[i - NR1 >= 0 ? i - NR1 : 0][j];
+          w = fma(vc, vj, w);
+        }
+        const double s = beta * w;
+        L[tri(j, c)] = fma(-s, v0, prj);
+#pragma unroll
+        for (int i = c + 1; i < NR1 + D; ++i) {
+          if (i < NR1) {
+            Y[i < NR1 ? i : 0][j] = fma(-s, Y[i < NR1 ? i : 0][c], Y[i < NR1 ? i : 0][j]);
+          } else {
+            Tt[i - NR1 >= 0 ? i - NR1 : 0][j] =
+                fma(-s, Tt[i - NR1 >= 0 ? i - NR1 : 0][c], Tt[i - NR1 >= 0 ? i - NR1 : 0][j]);
+          }
+        }
+      }
+      if (!(n2 == n2)) status |= 1;  // NaN  (src/smoothing.jl:25)
+    }
+  }
+
+  // One RTS step of the covariance.
+  //   F   : filtered factor at i in P(h) coordinates (already scaled by the caller)
+  //   Ls  : smoothed factor at i+1 in P(h) coordinates, packed lower; overwritten by the smoothed
+  //         factor at i (still P(h) coordinates)
+  //   delta: in  m_next_smoothed - A m  ->  out  G * delta          (ND_M mean replicas)
+  template <int NREP>
+  __device__ __forceinline__ static void step(const Factor<dc, q>& F, const double sig, const IwpConsts& C,
+                                              double (&Ls)[NP], double (&delta)[NREP][D], int& status) {
+    double sL[q + 1][q + 1];
+#pragma unroll
+    for (int k = 0; k <= q; ++k)
+#pragma unroll
+      for (int kk = 0; kk <= k; ++kk) sL[k][kk] = sig * C.Lt[k][kk];
+    // bottom rows: left = (A s)', right = s'
+    double El[R][D], Er[R][D];
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      double w[D];
+      if (c < dc) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) w[i] = F.W[c < dc ? c : 0][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+          w[i] = (i >= 2 * dc + (c - dc)) ? F.Lz[Factor<dc, q>::lz(c - dc >= 0 ? c - dc : 0, i - 2 * dc >= 0 ? i - 2 * dc : 0)] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) Er[c][i] = w[i];
+      apply_A<dc, q>(w);
+#pragma unroll
+      for (int i = 0; i < D; ++i) El[c][i] = w[i];
+    }
+    // stage 1: Householder sweep, natural coordinate order; prior rows are sparse pivots
+    double Rm[NP];    // R- stored as its transpose (lower packed): Rm[tri(j,c)] = R-[c][j]
+    double X[D][D];   // top-right block
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const int kc = c / dc, ac = c % dc;
+      const double pv = sL[kc][kc];
+      double n2 = pv * pv;
+#pragma unroll
+      for (int i = 0; i < R; ++i) n2 = fma(El[i][c], El[i][c], n2);
+      const double nrm = sqrt(n2);
+      const double v0 = pv + nrm;
+      const double beta = (n2 > 0.0) ? 1.0 / fma(pv, nrm, n2) : 0.0;
+      Rm[tri(c, c)] = -nrm;
+#pragma unroll
+      for (int j = c + 1; j < D; ++j) {
+        const bool pnz = (j % dc == ac);
+        const double prj = pnz ? sL[j / dc][kc] : 0.0;
+        double w = pnz ? v0 * prj : 0.0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) w = (i == 0 && !pnz) ? El[i][c] * El[i][j] : fma(El[i][c], El[i][j], w);
+        const double s = beta * w;
+        Rm[tri(j, c)] = pnz ? fma(-s, v0, prj) : -s * v0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) El[i][j] = fma(-s, El[i][c], El[i][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double w = El[0][c] * Er[0][j];
+#pragma unroll
+        for (int i = 1; i < R; ++i) w = fma(El[i][c], Er[i][j], w);
+        const double s = beta * w;
+        X[c][j] = -s * v0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) Er[i][j] = fma(-s, El[i][c], Er[i][j]);
+      }
+    }
+    // stage 2a: mean  G delta = X' (R-^-T delta);  R-^T is lower triangular = Rm as stored
+    double rinv[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) rinv[c] = (Rm[tri(c, c)] != 0.0) ? 1.0 / Rm[tri(c, c)] : 0.0;
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      double y[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double acc = delta[r][i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc = fma(-Rm[tri(i, k)], y[k], acc);
+        y[i] = acc * rinv[i];
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc = fma(X[k][i], y[k], acc);
+        delta[r][i] = acc;
+      }
+    }
+    // stage 2b: Z = R-^-T Ls (lower triangular), column by column (forward substitution)
+    double Z[NP];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+#pragma unroll
+      for (int i = c; i < D; ++i) {
+        double acc = Ls[tri(i, c)];
+#pragma unroll
+        for (int k = c; k < i; ++k) acc = fma(-Rm[tri(i, k)], Z[tri(k, c)], acc);
+        Z[tri(i, c)] = acc * rinv[i];
+      }
+    }
+    // T = X' Z  (D x D), stored transposed: Tt[c][i] = T[i][c] = sum_{k>=c} X[k][i] Z[k][c]
+    double Tt[D][D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double acc = X[c][i] * Z[tri(c, c)];
+#pragma unroll
+        for (int k = c + 1; k < D; ++k) acc = fma(X[k][i], Z[tri(k, c)], acc);
+        Tt[c][i] = acc;
+      }
+    }
+    // stage 3: smoothed factor = triangularisation of [Y ; T']
+    triangularize<R>(Er, Tt, Ls, status);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Smoothed-record layout and the kernel
+// ---------------------------------------------------------------------------------------------
+template <class M>
+struct SmoothModel;
+
+template <class VF, int q_>
+struct SmoothModel<DenseEK1<VF, q_>> {
+  using M = DenseEK1<VF, q_>;
+  static constexpr int d = M::d, q = M::q, D = M::D, NF = 1, DC = d;
+  using SC = SmoothCov<d, q>;
+  static constexpr int SREC = D + SC::NP;
+  __device__ static void load_cov(const double* sb, long long n, double* mean, double* cov) {
+    double L[SC::NP];
+#pragma unroll
+    for (int i = 0; i < D; ++i) mean[i] = sb[(long long)i * n];
+#pragma unroll
+    for (int i = 0; i < SC::NP; ++i) L[i] = sb[(long long)(D + i) * n];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k <= j; ++k) acc = fma(L[SC::tri(i, k)], L[SC::tri(j, k)], acc);
+        cov[SC::tri(i, j)] = acc;
+      }
+  }
+};
+
+template <class VF, int q_, bool MVDYN>
+struct SmoothModel<KronEK0<VF, q_, MVDYN>> {
+  using M = KronEK0<VF, q_, MVDYN>;
+  static constexpr int d = M::d, q = M::q, D = M::D, NF = M::NF, DC = 1;
+  using SC = SmoothCov<1, q>;
+  static constexpr int SREC = D + NF * SC::NP + d;  // mean, factors, per-dimension calibration scale
+  __device__ static void load_cov(const double* sb, long long n, double* mean, double* cov) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) mean[i] = sb[(long long)i * n];
+    double L[NF][SC::NP];
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+      for (int i = 0; i < SC::NP; ++i) L[f][i] = sb[(long long)(D + f * SC::NP + i) * n];
+    double ds[d];
+#pragma unroll
+    for (int a = 0; a < d; ++a) ds[a] = sb[(long long)(D + NF * SC::NP + a) * n];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        const int ki = i / d, ai = i % d, kj = j / d, aj = j % d;
+        double acc = 0.0;
+        if (ai == aj) {
+          const int f = MVDYN ? ai : 0;
+          const int lo = ki < kj ? ki : kj;
+#pragma unroll
+          for (int k = 0; k <= q; ++k)
+            if (k <= lo) acc = fma(L[f][SC::tri(ki, k)], L[f][SC::tri(kj, k)], acc);
+          acc *= ds[ai];
+        }
+        cov[i * (i + 1) / 2 + j] = acc;
+      }
+  }
+};
+
+template <class M>
+__global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
+  using SM = SmoothModel<M>;
+  using SC = typename SM::SC;
+  constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, SREC = SM::SREC, NF = SM::NF, DC = SM::DC;
+  constexpr int DCOV = DC * (q + 1);  // dimension of one covariance factor
+  constexpr int NREP = D / DCOV;      // mean replicas per factor group (1 dense, d Kronecker)
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= sp.n) return;
+  const long long n = sp.n;
+  const int ns = sp.n_saved[tid];
+  int status = 0;
+  if (ns <= 0) {
+    sp.status[tid] = 0;
+    return;
+  }
+  // calibration (static diffusion models): every filtered covariance is scaled by the final global
+  // diffusion (src/integrator_utils.jl:7-12); for fixedMV this is a per-dimension scale which the
+  // Kronecker form carries OUTSIDE the (shared) factor.
+  double gfin[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) gfin[i] = sp.calibrate ? sp.final_diff[(long long)i * n + tid] : 1.0;
+  double dimscale[d];
+#pragma unroll
+  for (int a = 0; a < d; ++a) dimscale[a] = (sp.calibrate && !M::IS_EK1) ? (sp.is_mv ? gfin[a < ND ? a : 0] : gfin[0]) : 1.0;
+  const double dense_cal = (sp.calibrate && M::IS_EK1) ? sqrt(gfin[0]) : 1.0;
+
+  auto rec = [&](int slot) { return sp.hist + ((long long)slot * REC) * n + tid; };
+  auto srec = [&](int slot) { return sp.smooth + ((long long)slot * SREC) * n + tid; };
+
+  double ms[D];          // smoothed mean at i+1 (natural coordinates)
+  double Ls[NF][SC::NP]; // smoothed factor(s) at i+1 (natural coordinates), packed lower
+  auto write = [&](int slot) {
+    double* o = srec(slot);
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[(long long)i * n] = ms[i];
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+      for (int i = 0; i < SC::NP; ++i) o[(long long)(D + f * SC::NP + i) * n] = Ls[f][i];
+    if constexpr (!M::IS_EK1) {
+#pragma unroll
+      for (int a = 0; a < d; ++a) o[(long long)(D + NF * SC::NP + a) * n] = dimscale[a];
+    }
+  };
+  // x_smooth[i] = x_filt[i] as a triangular factor (last state; also used for the un-smoothed first)
+  auto from_filtered = [&](int slot) {
+    typename M::State st;
+    M::load(st, rec(slot) + (long long)(1 + ND) * n, n);
+#pragma unroll
+    for (int i = 0; i < D; ++i) ms[i] = st.m[i];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const Factor<DC, q>* F;
+      if constexpr (M::IS_EK1) F = &st.F; else F = &st.F[f];
+      double Y[SC::R][DCOV], Tt[DCOV][DCOV];
+#pragma unroll
+      for (int c = 0; c < SC::R; ++c)
+#pragma unroll
+        for (int i = 0; i < DCOV; ++i) {
+          if (c < DC)
+            Y[c][i] = F->W[c < DC ? c : 0][i] * dense_cal;
+          else
+            Y[c][i] = (i >= 2 * DC + (c - DC))
+                          ? F->Lz[Factor<DC, q>::lz(c - DC >= 0 ? c - DC : 0, i - 2 * DC >= 0 ? i - 2 * DC : 0)] * dense_cal
+                          : 0.0;
+        }
+#pragma unroll
+      for (int c = 0; c < DCOV; ++c)
+#pragma unroll
+        for (int i = 0; i < DCOV; ++i) Tt[c][i] = 0.0;
+      SC::template triangularize<SC::R>(Y, Tt, Ls[f], status);
+    }
+  };
+
+  from_filtered(ns - 1);
+  write(ns - 1);
+  for (int i = ns - 2; i >= 1; --i) {
+    const double* ri = rec(i);
+    const double* rn = rec(i + 1);
+    const double h = rn[0] - ri[0];
+    if (h == 0.0) {  // src/smoothing.jl:13-16
+      write(i);
+      continue;
+    }
+    double Pk[q + 1], PIk[q + 1];
+    precond_scales<q>(h, Pk, PIk);
+    typename M::State st;
+    M::load(st, ri + (long long)(1 + ND) * n, n);
+    M::scale(st, Pk);  // x[i] = P * x[i]  (src/smoothing.jl:23)
+    // diffusion of the interval t[i] -> t[i+1] is stored with state i+1 (src/integrator_utils.jl:44)
+    double sig[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const double g = sp.calibrate ? (M::IS_EK1 ? gfin[0] : 1.0) : rn[(long long)(1 + (NF > 1 ? f : 0)) * n];
+      sig[f] = sqrt(g);
+    }
+    // delta = P m_next_smoothed - A P m_i ; mean replicas laid out per factor coordinate
+    double mpred[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) mpred[k] = st.m[k];
+    apply_A<d, q>(mpred);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      // scale smoothed factor at i+1 into P(h) coordinates
+#pragma unroll
+      for (int r = 0; r < DCOV; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) Ls[f][SC::tri(r, c)] *= Pk[r / DC];
+    }
+    if constexpr (M::IS_EK1) {
+      st.F.scale_all(dense_cal);
+      double delta[1][D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) delta[0][k] = fma(Pk[k / d], ms[k], -mpred[k]);
+      SC::template step<1>(st.F, sig[0], sp.C, Ls[0], delta, status);
+#pragma unroll
+      for (int k = 0; k < D; ++k) ms[k] = (st.m[k] + delta[0][k]) * PIk[k / d];
+    } else if constexpr (NF == 1) {
+      // Kronecker, shared factor: d mean replicas, replica a holds coordinates (k, a), k = 0..q.
+      // With a static per-dimension calibration the scale cancels in G, so the shared factor is
+      // smoothed uncalibrated and dimscale is applied at output.
+      double delta[d][q + 1];
+#pragma unroll
+      for (int a = 0; a < d; ++a)
+#pragma unroll
+        for (int k = 0; k <= q; ++k) delta[a][k] = fma(Pk[k], ms[k * d + a], -mpred[k * d + a]);
+      const double sg = sp.calibrate ? 1.0 : sig[0];
+      SC::template step<d>(st.F[0], sg, sp.C, Ls[0], delta, status);
+#pragma unroll
+      for (int a = 0; a < d; ++a)
+#pragma unroll
+        for (int k = 0; k <= q; ++k) ms[k * d + a] = (st.m[k * d + a] + delta[a][k]) * PIk[k];
+    } else {
+      // dynamicMV: one factor per dimension, one replica each
+#pragma unroll
+      for (int a = 0; a < d; ++a) {
+        double delta[1][q + 1];
+#pragma unroll
+        for (int k = 0; k <= q; ++k) delta[0][k] = fma(Pk[k], ms[k * d + a], -mpred[k * d + a]);
+        SC::template step<1>(st.F[a < NF ? a : 0], sig[a < NF ? a : 0], sp.C, Ls[a < NF ? a : 0], delta, status);
+#pragma unroll
+        for (int k = 0; k <= q; ++k) ms[k * d + a] = (st.m[k * d + a] + delta[0][k]) * PIk[k];
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+#pragma unroll
+      for (int r = 0; r < DCOV; ++r) {
+#pragma unroll
+        for (int c = 0; c <= r; ++c) Ls[f][SC::tri(r, c)] *= PIk[r / DC];
+        if (!(Ls[f][SC::tri(r, r)] == Ls[f][SC::tri(r, r)])) status |= 1;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      if (!(ms[k] == ms[k])) status |= 1;
+    write(i);
+  }
+  if (ns >= 2) {
+    // the first state is never smoothed (src/smoothing.jl:11: i runs down to 2)
+    from_filtered(0);
+    write(0);
+  }
+  sp.status[tid] = status;
+}
+
+}  // namespace pnde

@@ -1,0 +1,165 @@
+"""GPU parity: the CUDA path (through the C ABI) against the numpy oracle on the same inputs.
+
+Tolerances follow SURVEY.md fact 0.5 / App. C.2: the reference's recursion amplifies rounding
+differences in the high derivatives, so full-state tolerances depend on (q, n_steps); the solution
+block is well conditioned and is held to 1e-10 (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import pnde_oracle as O  # noqa: E402
+
+PROBLEMS = {
+    "fhn_readme": ([-1.0, 1.0], (0.2, 0.2, 3.0)),
+    "fhn_lib": ([1.0, 1.0], (0.7, 0.8, 1 / 12.5, 0.5)),
+    "lotka_volterra": ([1.0, 1.0], (1.5, 1.0, 3.0, 1.0)),
+    "vanderpol": ([0.0, 3.0 ** 0.5], (1e1,)),
+    "logistic": ([0.1], (3.0,)),
+}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def oracle_solve(name, alg, **kw):
+    u0, p = PROBLEMS[name]
+    tspan = kw.pop("tspan", (0.0, 1.0))
+    prob = O.Problem(O.CATALOGUE[name], list(u0), tspan, list(p))
+    return O.solve_ivp(prob, alg, **kw)
+
+
+def gpu_solve(name, alg, **kw):
+    import odefilters_b200 as B
+
+    u0, p = PROBLEMS[name]
+    tspan = kw.pop("tspan", (0.0, 1.0))
+    prob = B.ODEProblem(name, u0, tspan, p)
+    return B.solve(prob, alg, **kw)
+
+
+def cov_tol(q, n):
+    # SURVEY App. C.2 noise floor between two correct FP64 implementations
+    return {1: 1e-10, 2: 1e-7, 3: 1e-5, 4: 1e-3, 5: 1e-2}[q]
+
+
+def mean_tol(q, n):
+    return {1: 1e-11, 2: 1e-10, 3: 1e-7, 4: 1e-5, 5: 1e-3}[q]
+
+
+@pytest.mark.parametrize("name", ["fhn_readme", "lotka_volterra", "fhn_lib"])
+@pytest.mark.parametrize("q", [1, 2, 3, 5])
+@pytest.mark.parametrize("kind", ["EK0", "EK1"])
+def test_fixed_step_filter_history(name, q, kind):
+    import odefilters_b200 as B
+
+    dt = 0.01
+    so = oracle_solve(name, O.Alg(kind, q, "dynamic", False), adaptive=False, dt=dt)
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, smooth=False)
+    sg = gpu_solve(name, alg, adaptive=False, dt=dt)
+    assert len(sg.t) == len(so.t)
+    assert np.array_equal(sg.t, np.asarray(so.t))
+    d = 2
+    uo = np.array([g.mu[:d] for g in so.x_filt])
+    assert rel(sg.x_filt.mu[:, :d], uo) < 1e-10  # solution block: north_star tolerance
+    mo = np.array([g.mu for g in so.x_filt])
+    co = np.array([g.Sigma.mat for g in so.x_filt])
+    n = len(so.t)
+    for k in range(q + 1):  # per derivative block, relative to the block max-norm
+        assert rel(sg.x_filt.mu[:, k * d:(k + 1) * d], mo[:, k * d:(k + 1) * d]) < mean_tol(q, n)
+    assert rel(sg.x_filt.Sigma[:, :d, :d], co[:, :d, :d]) < cov_tol(q, n)
+    assert rel(sg.diffusions, np.asarray(so.diffusions)) < cov_tol(q, n)
+    assert sg.destats["naccept"] == so.naccept and sg.destats["nf"] == so.nf
+    assert sg.x_filt.Sigma[0].max() == 0.0  # exact initial state (test/solution.jl:38-41)
+    assert abs(sg.log_likelihood - so.log_likelihood) < 1e-6 * abs(so.log_likelihood) + cov_tol(q, n) * n
+
+
+@pytest.mark.parametrize("name,kind,q,abstol,reltol,tspan", [
+    ("fhn_readme", "EK0", 1, 1e-1, 1e-2, (0.0, 20.0)),   # BASELINE config 1 (README.md:47)
+    ("fhn_lib", "EK1", 3, 1e-6, 1e-3, (0.0, 1.0)),        # the golden-vector problem
+    ("lotka_volterra", "EK1", 2, 1e-6, 1e-3, (0.0, 2.0)),
+    ("lotka_volterra", "EK0", 3, 1e-5, 1e-3, (0.0, 2.0)),
+    ("vanderpol", "EK1", 3, 1e-6, 1e-3, (0.0, 1.0)),
+    ("logistic", "EK1", 4, 1e-6, 1e-3, (0.0, 2.0)),
+])
+def test_adaptive_grid_identical(name, kind, q, abstol, reltol, tspan):
+    """Adaptive runs: identical accepted/rejected counts, t-grid equal to 1e-12 relative."""
+    import odefilters_b200 as B
+
+    so = oracle_solve(name, O.Alg(kind, q, "dynamic", False), abstol=abstol, reltol=reltol, tspan=tspan)
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, smooth=False)
+    sg = gpu_solve(name, alg, abstol=abstol, reltol=reltol, tspan=tspan)
+    assert (sg.destats["naccept"], sg.destats["nreject"]) == (so.naccept, so.nreject)
+    assert sg.destats["nf"] == so.nf
+    assert sg.retcode == "Success" and sg.t[-1] == tspan[1] and sg.t[0] == tspan[0]
+    assert rel(sg.t, so.t) < 1e-10
+    d = len(PROBLEMS[name][0])
+    assert rel(sg.u, np.array([g.mu[:d] for g in so.x_filt])) < 1e-8
+
+
+@pytest.mark.parametrize("kind", ["EK0", "EK1"])
+@pytest.mark.parametrize("diffusion", ["fixed", "fixedMAP", "dynamic", "fixedMV", "dynamicMV"])
+def test_diffusion_models(kind, diffusion):
+    """test/correctness.jl:15-39: all diffusion models (MV only for EK0), fixed steps."""
+    import odefilters_b200 as B
+
+    if kind == "EK1" and diffusion.endswith("MV"):
+        with pytest.raises(RuntimeError):
+            gpu_solve("lotka_volterra", B.EK1(order=3, diffusionmodel=diffusion, smooth=False), adaptive=False, dt=5e-3)
+        return
+    q = 3
+    so = oracle_solve("lotka_volterra", O.Alg(kind, q, diffusion, False), adaptive=False, dt=5e-3)
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, diffusionmodel=diffusion, smooth=False)
+    sg = gpu_solve("lotka_volterra", alg, adaptive=False, dt=5e-3)
+    d = 2
+    assert rel(sg.x_filt.mu[:, :d], np.array([g.mu[:d] for g in so.x_filt])) < 1e-10
+    co = np.array([g.Sigma.mat for g in so.x_filt])
+    assert rel(sg.x_filt.Sigma[:, :d, :d], co[:, :d, :d]) < 1e-5
+    do = np.array([np.asarray(x)[:d] if np.ndim(x) else x for x in so.diffusions], dtype=float)
+    assert rel(sg.diffusions, do) < 1e-5
+    if diffusion.startswith("fixed"):
+        assert np.isnan(sg.log_likelihood)  # src/integrator_utils.jl:6
+
+
+@pytest.mark.parametrize("name,kind,q,adaptive", [
+    ("lotka_volterra", "EK1", 3, False),   # BASELINE config 5 shape
+    ("lotka_volterra", "EK0", 3, False),
+    ("fhn_readme", "EK1", 2, True),
+    ("fhn_readme", "EK0", 1, True),         # config 1 with smoothing (README default)
+    ("lotka_volterra", "EK0", 2, True),
+])
+def test_smoother(name, kind, q, adaptive):
+    import odefilters_b200 as B
+
+    kw = dict(adaptive=False, dt=0.05, tspan=(0.0, 5.0)) if not adaptive else dict(tspan=(0.0, 5.0))
+    so = oracle_solve(name, O.Alg(kind, q, "dynamic", True), **dict(kw))
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, smooth=True)
+    sg = gpu_solve(name, alg, **dict(kw))
+    assert len(sg.t) == len(so.t)
+    d = 2
+    mo = np.array([g.mu for g in so.x_smooth])
+    co = np.array([g.Sigma.mat for g in so.x_smooth])
+    assert rel(sg.x_smooth.mu[:, :d], mo[:, :d]) < 1e-9
+    assert rel(sg.x_smooth.Sigma[:, :d, :d], co[:, :d, :d]) < cov_tol(q, len(so.t))
+    assert rel(sg.u, np.array(so.u)) < 1e-9                      # sol.u := smoothed means
+    assert np.array_equal(sg.x_smooth.mu[-1], sg.x_filt.mu[-1])  # test/smoothing.jl:39
+    assert np.array_equal(sg.x_smooth.mu[0], sg.x_filt.mu[0])    # first state is never smoothed
+
+
+def test_ensemble_matches_single_solves():
+    import odefilters_b200 as B
+
+    rng = np.random.default_rng(20260118)
+    n = 257  # ragged: not a multiple of the block size
+    P = np.stack([rng.uniform(0.1, 0.3, n), rng.uniform(0.1, 0.3, n), rng.uniform(2, 4, n)], axis=1)
+    prob = B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 1.0), P[0])
+    es = B.solve(B.EnsembleProblem(prob, p=P), B.EK1(order=3, smooth=False), B.EnsembleB200(), adaptive=False, dt=0.01)
+    assert es.converged and len(es) == n
+    for i in (0, 1, 100, 256):
+        pr = O.Problem(O.CATALOGUE["fhn_readme"], [-1.0, 1.0], (0.0, 1.0), list(P[i]))
+        so = O.solve_ivp(pr, O.EK1(order=3, smooth=False), adaptive=False, dt=0.01)
+        assert rel(es.u[i], so.x_filt[-1].mu[:2]) < 1e-10
+        assert es.destats["naccept"][i] == so.naccept
