@@ -1,0 +1,129 @@
+"""CPU tests: host-side logic and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from odefilters_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "pnde.h")).read()
+    declared = set(re.findall(r"\b(pnde_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"pnde_config", "pnde_handle"}
+    lib = _lib.load()
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_config_struct_layout_matches_header():
+    from odefilters_b200 import _lib
+
+    cfg = _lib.PndeConfig()
+    lib = _lib.load()
+    assert lib.pnde_default_config(C.byref(cfg), _lib.ALG_EK1, 3, 0) == 0
+    assert (cfg.abi_version, cfg.alg, cfg.order, cfg.adaptive) == (1, 1, 3, 1)
+    assert (cfg.abstol, cfg.reltol, cfg.qmax, cfg.gamma, cfg.qoldinit) == (1e-6, 1e-3, 10.0, 0.9, 1e-4)
+    assert cfg.maxiters == 100000 and C.sizeof(cfg) == 12 * 4 + 15 * 8 + 2 * 8
+
+
+def test_create_argument_errors_are_reported_without_a_gpu():
+    from odefilters_b200 import _lib
+
+    lib = _lib.load()
+    cfg = _lib.PndeConfig()
+    lib.pnde_default_config(C.byref(cfg), _lib.ALG_EK1, 3, 0)
+    h = C.c_void_p()
+    cfg.diffusion = _lib.DIFFUSIONS["dynamicMV"]  # EK1 + MV: the reference asserts (src/diffusions.jl:97)
+    assert lib.pnde_create(C.byref(cfg), C.byref(h)) == -1 and b"EK0-only" in lib.pnde_last_error(None)
+    cfg.diffusion = 0
+    cfg.adaptive, cfg.dt = 0, 0.0  # test/errors.jl:16-20
+    assert lib.pnde_create(C.byref(cfg), C.byref(h)) == -1 and b"require a choice of dt" in lib.pnde_last_error(None)
+    cfg.adaptive = 1
+    cfg.order = 9
+    assert lib.pnde_create(C.byref(cfg), C.byref(h)) == -3
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import odefilters_b200 as B
+
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        B.solve(B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 1.0), (0.2, 0.2, 3.0)), B.EK1())
+
+
+def test_host_argument_checks():
+    import odefilters_b200 as B
+
+    with pytest.raises(ValueError):  # test/errors.jl:11-14 (non-vector u0)
+        B.ODEProblem("fhn_readme", [[-1.0, 1.0]], (0.0, 1.0), (0.2, 0.2, 3.0))
+    prob = B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 1.0), (0.2, 0.2, 3.0))
+    with pytest.raises(ValueError, match="choice of dt"):
+        B.solve(prob, B.EK0(), adaptive=False)
+    with pytest.raises(ValueError):
+        B.EK1(diffusionmodel="nope")
+    with pytest.raises(ValueError, match="dense"):
+        B.solve(prob, B.EK1(smooth=True), dense=False)
+
+
+def test_shard_range_partitions():
+    import odefilters_b200 as B
+
+    for n in (1, 7, 1000, 10 ** 6 + 3):
+        for w in (1, 2, 4, 8):
+            parts = [B.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+
+
+def test_unpack_lower():
+    from odefilters_b200.api import _unpack_lower
+
+    D = 4
+    A = np.arange(16.0).reshape(4, 4)
+    A = A + A.T
+    il = np.tril_indices(D)
+    assert np.array_equal(_unpack_lower(A[il][None], D)[0], A)
+
+
+def _gloo_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+
+    import odefilters_b200 as B
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = B.shard_range(n, rank, world)
+    import torch
+
+    cnt = torch.tensor([hi - lo], dtype=torch.int64)
+    dist.all_reduce(cnt)
+    mx = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    q.put((rank, int(cnt.item()), float(mx.item()), lo, hi))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_sharding_over_gloo():
+    """The N > 1 path of bench.py: shard by rank, no data-path collective, max-over-ranks timing."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    n = 1001
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(60)
+    assert [r[1] for r in res] == [n, n] and [r[2] for r in res] == [2.0, 2.0]
+    assert res[0][3:] == (0, 500) and res[1][3:] == (500, 1001)
