@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpnde.so")
+LIB_PATH = os.environ.get("PNDE_LIB") or os.path.join(_HERE, "libpnde.so")  # PNDE_LIB: experiment builds
 
 ABI_VERSION = 1
 ALG_EK0, ALG_EK1 = 0, 1

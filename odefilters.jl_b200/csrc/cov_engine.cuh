@@ -39,6 +39,25 @@ __host__ __device__ __forceinline__ constexpr double inv_factorial(int k) {
                 : 1.0 / 5040.0;
 }
 
+// rsqrt / reciprocal with one cubic correction step on top of the 20-bit hardware approximation
+// (MUFU.RSQ64H / MUFU.RCP64H): ~1 ulp, no special-case slow path.  x must be a positive normal
+// number (callers guard zero).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);           // 1 - x y^2
+  const double q = e * fma(0.375, e, 0.5);    // e/2 + 3e^2/8
+  return fma(y, q, y);
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);  // 1 - x y
+  const double q = fma(e, e, e);     // e + e^2
+  return fma(y, q, y);
+}
+
 // x <- A x with A = Atilde (x) I_dc, Atilde[i][j] = 1/(j-i)!  (src/priors.jl:15-27).
 template <int dc, int q>
 __device__ __forceinline__ void apply_A(double (&x)[dc * (q + 1)]) {
@@ -135,12 +154,12 @@ struct Factor {
 
 // One filter step of the covariance: predict (with diffusion sig^2) + exact update, in place.
 //   in : F = factor of Sigma (preconditioned coordinates), Jp = pi0 * J (dc x dc), sig, pi1
-//   out: F = factor of Sigma+;  Rtop = first dc rows of R in primed column order
+//   out: F = factor of Sigma+;  Rinv[a] = 1 / Rtop[a][a];  Rtop = first dc rows of R in primed column order
 //        (cols 0..dc-1: innovation factor, cols dc..2dc-1: x_0 block, cols k*dc..: block k >= 2)
 template <int dc, int q, bool HASJ>
 __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (&Jp)[dc][dc], const double sig,
                                                 const double pi1, const double ipi1, const IwpConsts& C,
-                                                double (&Rtop)[dc][dc * (q + 1)]) {
+                                                double (&Rtop)[dc][dc * (q + 1)], double (&Rinv)[dc]) {
   constexpr int D = dc * (q + 1);
   constexpr int NZ = D - 2 * dc;
   double sL[q + 1][2 > q + 1 ? 2 : q + 1];  // sig * Ltilde[k][k']
@@ -238,13 +257,22 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
       pv = E[c - dc][c];
     else
       pv = sL[kc][kc];
-    double n2 = pv * pv;
+    // squared norm in two interleaved chains (halves the dependent-FMA latency)
+    double n2a = pv * pv, n2b = E[first][c] * E[first][c];
 #pragma unroll
-    for (int i = first; i < D; ++i) n2 = fma(E[i][c], E[i][c], n2);
-    const double nrm = sqrt(n2);
+    for (int i = first + 1; i < D; ++i) {
+      if ((i - first) & 1)
+        n2a = fma(E[i][c], E[i][c], n2a);
+      else
+        n2b = fma(E[i][c], E[i][c], n2b);
+    }
+    const double n2 = n2a + n2b;
+    const bool nzcol = n2 > 0.0;
+    const double rn = nzcol ? fast_rsqrt(n2) : 0.0;  // 1 / ||x||
+    const double nrm = n2 * rn;
     const double snrm = copysign(nrm, pv);
     const double v0 = pv + snrm;
-    const double beta = (n2 > 0.0) ? 1.0 / fma(fabs(pv), nrm, n2) : 0.0;
+    const double beta = nzcol ? fast_rcp(fma(fabs(pv), nrm, n2)) : 0.0;  // 1 / (||x|| (||x|| + |pv|))
     double Rrow[D];
     Rrow[c] = -snrm;
 #pragma unroll
@@ -282,6 +310,7 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
     if (c < dc) {
 #pragma unroll
       for (int j = 0; j < D; ++j) Rtop[c][j] = (j >= c) ? Rrow[j] : 0.0;
+      Rinv[c] = -copysign(rn, pv);  // 1 / R[c][c] (0 for a zero column)
     } else if (c < 2 * dc) {
       const int a = c - dc;
 #pragma unroll

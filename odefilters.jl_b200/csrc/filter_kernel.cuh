@@ -95,9 +95,11 @@ struct DenseEK1 {
   }
 
   // One attempted step in P(h) coordinates.  diffusion in {dynamic, fixed, fixedMAP}.
-  __device__ __forceinline__ static void step(State& s, const double* p, double pi0, double pi1, int diffusion,
-                                              const IwpConsts& C, double (&u_new)[d], double (&err)[d],
-                                              double (&local)[ND], double& loglik) {
+  // quad = z' S^-1 z and detS = sqrt(det S) = |prod diag(R00)| feed the log-likelihood (:66), which the
+  // kernel accumulates without a per-step log.
+  __device__ __forceinline__ static void step(State& s, const double* p, double pi0, double pi1, double ipi1,
+                                              int diffusion, const IwpConsts& C, double (&u_new)[d], double (&err)[d],
+                                              double (&local)[ND], double& quad, double& detS) {
     apply_A<d, q>(s.m);  // predict_mean!  src/filtering.jl:22-25
     double uhat[d], fu[d], J[d][d], Jp[d][d], z[d];
 #pragma unroll
@@ -136,9 +138,8 @@ struct DenseEK1 {
         double djj = B[j][j];
 #pragma unroll
         for (int k = 0; k < j; ++k) djj = fma(-Lb[j][k], Lb[j][k], djj);
-        const double ljj = sqrt(djj);
-        const double il = 1.0 / ljj;
-        Lb[j][j] = ljj;
+        const double il = (djj > 0.0) ? fast_rsqrt(djj) : 0.0;
+        Lb[j][j] = djj * il;
 #pragma unroll
         for (int i = j + 1; i < d; ++i) {
           double v = B[i][j];
@@ -152,26 +153,26 @@ struct DenseEK1 {
         yb[j] = yy * il;
         ss = fma(yb[j], yb[j], ss);
       }
-      local[0] = ss / double(d);
-      sig = sqrt(local[0]);
+      local[0] = ss * (1.0 / double(d));
+      sig = (local[0] > 0.0) ? local[0] * fast_rsqrt(local[0]) : 0.0;
     }
-    double Rtop[d][D];
-    cov_filter_step<d, q, true>(s.F, Jp, sig, pi1, 1.0 / pi1, C, Rtop);  // predict_cov! + update!
+    double Rtop[d][D], Rinv[d];
+    cov_filter_step<d, q, true>(s.F, Jp, sig, pi1, ipi1, C, Rtop, Rinv);  // predict_cov! + update!
     // innovation: S_z = G G', G = Rtop[:, :d]' lower triangular; y = G^-1 z
     double y[d];
-    double yy2 = 0.0, logdet = 0.0;
+    double yy2 = 0.0, dets = 1.0;
 #pragma unroll
     for (int a = 0; a < d; ++a) {
       double acc = z[a];
 #pragma unroll
       for (int b = 0; b < a; ++b) acc = fma(-Rtop[b][a], y[b], acc);
-      const double raa = Rtop[a][a];
-      y[a] = (raa != 0.0) ? acc / raa : 0.0;
+      y[a] = acc * Rinv[a];
       yy2 = fma(y[a], y[a], yy2);
-      logdet += log(fabs(raa));
+      dets *= fabs(Rtop[a][a]);
     }
-    loglik = -0.5 * (yy2 + 2.0 * logdet + double(d) * 1.8378770664093453);  // :66
-    if (diffusion != DIFF_DYNAMIC) local[0] = yy2 / double(d);              // src/diffusions.jl:25,52
+    quad = yy2;
+    detS = dets;
+    if (diffusion != DIFF_DYNAMIC) local[0] = yy2 * (1.0 / double(d));  // src/diffusions.jl:25,52
     // mean update: mu+ = mu- - K z  (src/filtering.jl:87) in primed coordinates
     double m0old[d];
 #pragma unroll
@@ -189,7 +190,6 @@ struct DenseEK1 {
       for (int a = 0; a < d; ++a) acc = fma(-Rtop[a][i], y[a], acc);
       s.m[i] = acc;
     }
-    const double ipi1 = 1.0 / pi1;
 #pragma unroll
     for (int b = 0; b < d; ++b) {
       double acc = fu[b];
@@ -246,9 +246,9 @@ struct KronEK0 {
     for (int f = 0; f < NF; ++f) s.F[f].scale_blocks(sc);
   }
 
-  __device__ __forceinline__ static void step(State& s, const double* p, double pi0, double pi1, int diffusion,
-                                              const IwpConsts& C, double (&u_new)[d], double (&err)[d],
-                                              double (&local)[ND], double& loglik) {
+  __device__ __forceinline__ static void step(State& s, const double* p, double pi0, double pi1, double ipi1,
+                                              int diffusion, const IwpConsts& C, double (&u_new)[d], double (&err)[d],
+                                              double (&local)[ND], double& quad, double& detS) {
     apply_A<d, q>(s.m);
     double uhat[d], fu[d], z[d];
 #pragma unroll
@@ -262,14 +262,14 @@ struct KronEK0 {
     }
     const double B = pi1 * pi1 * C.Qt[1][1];  // H Q H' = B I_d for EK0 (src/diffusions.jl:101-103)
     const double Jp0[1][1] = {{0.0}};
-    const double ipi1 = 1.0 / pi1;
-    double R[NF][1][q + 1];
+    double R[NF][1][q + 1], Ri[NF][1];
     if (MVDYN) {
       // src/diffusions.jl:104-108: Sigma_ii = max(z_i^2 / Q0_11, eps)
 #pragma unroll
       for (int a = 0; a < d; ++a) {
         local[a] = fmax(z[a] * z[a] / B, 2.220446049250313e-16);
-        cov_filter_step<1, q, false>(s.F[a < NF ? a : 0], Jp0, sqrt(local[a]), pi1, ipi1, C, R[a < NF ? a : 0]);
+        cov_filter_step<1, q, false>(s.F[a < NF ? a : 0], Jp0, sqrt(local[a]), pi1, ipi1, C, R[a < NF ? a : 0],
+                                     Ri[a < NF ? a : 0]);
       }
     } else {
       double sig = 1.0;
@@ -277,22 +277,22 @@ struct KronEK0 {
         local[0] = zz / (double(d) * B);
         sig = sqrt(local[0]);
       }
-      cov_filter_step<1, q, false>(s.F[0], Jp0, sig, pi1, ipi1, C, R[0]);
+      cov_filter_step<1, q, false>(s.F[0], Jp0, sig, pi1, ipi1, C, R[0], Ri[0]);
     }
-    double yy2 = 0.0, logdet = 0.0;
+    double yy2 = 0.0, dets = 1.0;
 #pragma unroll
     for (int a = 0; a < d; ++a) {
       const int f = MVDYN ? a : 0;
-      const double r00 = R[f][0][0];
-      const double ya = (r00 != 0.0) ? z[a] / r00 : 0.0;
+      const double ya = z[a] * Ri[f][0];
       yy2 = fma(ya, ya, yy2);
-      logdet += log(fabs(r00));
+      dets *= fabs(R[f][0][0]);
       s.m[a] = fma(-R[f][0][1], ya, s.m[a]);
 #pragma unroll
       for (int k = 2; k <= q; ++k) s.m[k * d + a] = fma(-R[f][0][k], ya, s.m[k * d + a]);
       s.m[d + a] = fu[a] * ipi1;
     }
-    loglik = -0.5 * (yy2 + 2.0 * logdet + double(d) * 1.8378770664093453);
+    quad = yy2;
+    detS = dets;
     if (diffusion == DIFF_FIXED || diffusion == DIFF_FIXED_MAP) local[0] = yy2 / double(d);
     if (diffusion == DIFF_FIXED_MV) {
       const double S11 = R[0][0][0] * R[0][0][0];  // src/diffusions.jl:136-138
@@ -389,8 +389,11 @@ __device__ __forceinline__ double initdt(const double* u0, const double* p, cons
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
+#ifndef PNDE_FILTER_MINB
+#define PNDE_FILTER_MINB 1
+#endif
 template <class M, bool ADAPTIVE>
-__global__ void __launch_bounds__(128) filter_kernel(const FilterParams prm) {
+__global__ void __launch_bounds__(128, PNDE_FILTER_MINB) filter_kernel(const FilterParams prm) {
   using VF = typename M::VF;
   constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,7 +427,11 @@ __global__ void __launch_bounds__(128) filter_kernel(const FilterParams prm) {
   double uprev[d];
 #pragma unroll
   for (int i = 0; i < d; ++i) uprev[i] = u0[i];
-  double ll = 0.0;
+  // log-likelihood (src/perform_step.jl:66,91) = -1/2 sum (quad + 2 log detS + d log 2pi) over committed
+  // steps; the log of the running product of detS is taken lazily (mantissa / exponent split).
+  double ll_quad = 0.0, ll_log = 0.0, ll_mant = 1.0;
+  long long ll_exp = 0;
+  int ll_n = 0;
 
   auto save = [&](const typename M::State& sv, double tt, const double (&g)[ND]) {
     if (nsaved >= prm.max_saved) {
@@ -504,10 +511,10 @@ __global__ void __launch_bounds__(128) filter_kernel(const FilterParams prm) {
       M::scale(st, sc);
       hcur = dt;
     }
-    double unew[d], err[d], local[ND], lls;
+    double unew[d], err[d], local[ND], quad, detS;
 #pragma unroll
     for (int i = 0; i < ND; ++i) local[i] = 1.0;
-    M::step(st, p, PIk[0], PIk[1], diffusion, prm.C, unew, err, local, lls);
+    M::step(st, p, PIk[0], PIk[1], Pk[1], diffusion, prm.C, unew, err, local, quad, detS);
     ++nfe;
     // global diffusion (src/diffusions.jl): success_iter == number of accepted steps so far
     double gcur[ND];
@@ -557,7 +564,21 @@ __global__ void __launch_bounds__(128) filter_kernel(const FilterParams prm) {
         st = old;
       }
     }
-    if (commit) ll += lls;
+    if (commit) {
+      ll_quad += quad;
+      ++ll_n;
+      if (detS > 1e-290 && detS < 1e290) {
+        const long long bits = __double_as_longlong(detS);
+        ll_exp += ((bits >> 52) & 0x7ff) - 1023;
+        ll_mant *= __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL);
+        if (ll_mant > 1e250) {
+          ll_log += log(ll_mant);
+          ll_mant = 1.0;
+        }
+      } else {
+        ll_log += log(detS);
+      }
+    }
     if (!finite) {
       ret = RET_NONFINITE;  // OrdinaryDiffEq check_error!: unstable_check
       break;
@@ -620,6 +641,8 @@ __global__ void __launch_bounds__(128) filter_kernel(const FilterParams prm) {
   double dimscale[d];
 #pragma unroll
   for (int a = 0; a < d; ++a) dimscale[a] = 1.0;
+  double ll = -0.5 * (ll_quad + 2.0 * (ll_log + log(ll_mant) + double(ll_exp) * 0.6931471805599453) +
+                      double(ll_n) * double(d) * 1.8378770664093453);
   if (is_static && nacc > 0) {
 #pragma unroll
     for (int a = 0; a < d; ++a) dimscale[a] = is_mv ? gsaved[a < ND ? a : 0] : gsaved[0];
