@@ -231,7 +231,7 @@ def main():
         ev_ms.append(solver.last_run_ms()[0])
     barrier()
     wall = time.perf_counter() - w0
-    launches = args.steps * solver.launch_count()
+    launches = args.steps * solver.launch_count() * world  # every rank launches the same kernels
     fetch()
     steps_done = int(np.sum(solver.counts()["naccept"]))
     assert steps_done == n * STEPS_PER_TRAJ, steps_done
