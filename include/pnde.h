@@ -167,6 +167,21 @@ int pnde_get_history(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t 
 int pnde_get_marginals(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end,
                        int64_t* offsets, double* t, double* u, double* cov_u);
 
+/* sample_states (src/solution_sampling.jl:24-62): n_samples backward-sampled paths per trajectory of
+ * [traj_begin, traj_end), drawn with an in-kernel counter-based generator (Philox4x32-10 keyed by seed;
+ * reproducible for a given (seed, trajectory, sample, state)).  Needs PNDE_SAVE_EVERY.  Same CSR layout as
+ * pnde_get_history: t [total], samples [total][n_samples][D] (sample() of the reference is the first d
+ * components).  offsets is an output. */
+int pnde_sample(pnde_handle* h, int64_t traj_begin, int64_t traj_end, int32_t n_samples, uint64_t seed,
+                int64_t* offsets, double* t, double* samples);
+
+/* Dense output sol(t) (GaussianODEFilterPosterior, src/solution.jl:165-215) of every trajectory in
+ * [traj_begin, traj_end) at the n_t query times t[]: predict from the left filtered neighbour and, when
+ * which == PNDE_HIST_SMOOTHED, smooth against the right smoothed neighbour.  mean [ntr][n_t][D],
+ * cov [ntr][n_t][D(D+1)/2] packed lower.  Queries before t0 yield NaN (the reference throws). */
+int pnde_eval_dense(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end, int64_t n_t,
+                    const double* t, double* mean, double* cov);
+
 /* Device micro-benchmarks used as roofline denominators by bench.py (not part of the path). */
 int pnde_measure_fp64_peak(int32_t device, double* tflops);
 int pnde_measure_hbm_copy(int32_t device, double* gbs);

@@ -165,9 +165,39 @@ class ProbODESolution:
     retcode: str
     prob: ODEProblem = None
     alg: _EK = None
+    _solver: "FilterSolver" = None
+    _index: int = 0
 
     def __len__(self):
         return len(self.t)
+
+    def __call__(self, t):
+        """Dense output sol(t) = SolProj * posterior(t) (src/solution.jl:211-215); evaluated on the device."""
+        scalar = np.ndim(t) == 0
+        tq = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        which = L.HIST_SMOOTHED if self.x_smooth is not None else L.HIST_FILTERED
+        mean, cov = self._solver.dense(which, self._index, self._index + 1, tq)
+        d = self._solver.d
+        out = _GaussianList(mean[0][:, :d].copy(), cov[0][:, :d, :d].copy())
+        return out[0] if scalar else out
+
+    def posterior(self, t):
+        """Full-state posterior at t (GaussianODEFilterPosterior call, src/solution.jl:165-210)."""
+        tq = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        which = L.HIST_SMOOTHED if self.x_smooth is not None else L.HIST_FILTERED
+        mean, cov = self._solver.dense(which, self._index, self._index + 1, tq)
+        return _GaussianList(mean[0], cov[0])
+
+    def sample_states(self, n: int = 1, seed: int = 0) -> np.ndarray:
+        """sample_states(sol, n) (src/solution_sampling.jl:15-18): [len(sol), D, n]."""
+        if self.x_smooth is None:
+            raise ValueError("sampling not implemented for non-smoothed posteriors")  # :16
+        _, _, smp = self._solver.sample(self._index, self._index + 1, n, seed)
+        return np.ascontiguousarray(np.transpose(smp, (0, 2, 1)))
+
+    def sample(self, n: int = 1, seed: int = 0) -> np.ndarray:
+        """sample(sol, n) (src/solution_sampling.jl:19-23): [len(sol), d, n]."""
+        return self.sample_states(n, seed)[:, : self._solver.d, :]
 
 
 @dataclass
@@ -349,6 +379,27 @@ class FilterSolver:
                                               mean.ctypes.data, cov.ctypes.data, diff.ctypes.data), "pnde_get_history")
         return offsets, t, mean, cov, diff
 
+    def sample(self, lo: int, hi: int, n_samples: int, seed: int = 0):
+        """pnde_sample for trajectories [lo, hi): (offsets, t [total], samples [total, n_samples, D])."""
+        cnt = self.counts()["n_saved"][lo:hi]
+        total = int(cnt.sum())
+        offsets = np.zeros(hi - lo + 1, dtype=np.int64)
+        t = np.empty(total)
+        smp = np.empty((total, n_samples, self.D))
+        self._check(self.lib.pnde_sample(self._h, lo, hi, n_samples, seed, offsets.ctypes.data, t.ctypes.data,
+                                         smp.ctypes.data), "pnde_sample")
+        return offsets, t, smp
+
+    def dense(self, which: int, lo: int, hi: int, tq: np.ndarray):
+        """pnde_eval_dense: (mean [ntr, n_t, D], cov [ntr, n_t, D, D]) of trajectories [lo, hi) at times tq."""
+        tq = np.ascontiguousarray(tq, dtype=np.float64)
+        D = self.D
+        mean = np.empty((hi - lo, len(tq), D))
+        cov = np.empty((hi - lo, len(tq), D * (D + 1) // 2))
+        self._check(self.lib.pnde_eval_dense(self._h, which, lo, hi, len(tq), tq.ctypes.data, mean.ctypes.data,
+                                             cov.ctypes.data), "pnde_eval_dense")
+        return mean, _unpack_lower(cov, D)
+
     def solution(self, i: int, counts: Optional[dict] = None, final=None) -> ProbODESolution:
         """build_solution for trajectory i (src/solution.jl:45-80, src/integrator_utils.jl:20-26)."""
         counts = counts or self.counts()
@@ -377,7 +428,8 @@ class FilterSolver:
             diffusions=diffs if self.is_mv else diffs[:, 0],
             log_likelihood=float(llv),
             destats={k: int(counts[k][i]) for k in ("naccept", "nreject", "nf", "njacs")},
-            retcode=L.RETCODES.get(int(counts["retcode"][i]), "Failure"), prob=self.prob, alg=self.alg)
+            retcode=L.RETCODES.get(int(counts["retcode"][i]), "Failure"), prob=self.prob, alg=self.alg,
+            _solver=self, _index=i)
 
 
 # --------------------------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 // Shared by the inst_*.cu translation units: launchers + the history conversion kernel.
 #pragma once
 #include "model_ops.cuh"
+#include "post_kernels.cuh"
 #include "smoother_kernel.cuh"
 
 namespace pnde {
@@ -95,6 +96,24 @@ cudaError_t launch_smooth_t(const SmoothParams& sp, cudaStream_t s) {
 }
 
 template <class M>
+cudaError_t launch_sample_t(const SampleParams& sp, cudaStream_t s) {
+  const int block = 128;
+  const long long total = (sp.traj_end - sp.traj_begin) * sp.n_samples;
+  if (total <= 0) return cudaSuccess;
+  sample_kernel<M><<<(unsigned)((total + block - 1) / block), block, 0, s>>>(sp);
+  return cudaGetLastError();
+}
+
+template <class M>
+cudaError_t launch_dense_t(const DenseParams& dp, cudaStream_t s) {
+  const int block = 128;
+  const long long total = (dp.traj_end - dp.traj_begin) * dp.n_t;
+  if (total <= 0) return cudaSuccess;
+  dense_kernel<M><<<(unsigned)((total + block - 1) / block), block, 0, s>>>(dp);
+  return cudaGetLastError();
+}
+
+template <class M>
 const ModelOps* make_ops() {
   static const ModelOps ops = {M::d,
                                M::q,
@@ -106,7 +125,9 @@ const ModelOps* make_ops() {
                                M::IS_EK1,
                                &launch_filter_t<M>,
                                &launch_convert_t<M>,
-                               &launch_smooth_t<M>};
+                               &launch_smooth_t<M>,
+                               &launch_sample_t<M>,
+                               &launch_dense_t<M>};
   return &ops;
 }
 

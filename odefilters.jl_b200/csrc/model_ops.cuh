@@ -40,12 +40,17 @@ struct SmoothParams {
   IwpConsts C;
 };
 
+struct SampleParams;
+struct DenseParams;
+
 struct ModelOps {
   int d, q, D, nd, rec, srec, np;
   bool ek1;
   cudaError_t (*launch_filter)(const FilterParams&, bool adaptive, cudaStream_t);
   cudaError_t (*launch_convert)(const ConvertParams&, cudaStream_t);
   cudaError_t (*launch_smooth)(const SmoothParams&, cudaStream_t);
+  cudaError_t (*launch_sample)(const SampleParams&, cudaStream_t);
+  cudaError_t (*launch_dense)(const DenseParams&, cudaStream_t);
 };
 
 // defined in inst_*.cu

@@ -10,6 +10,7 @@
 
 #include "../../include/pnde.h"
 #include "model_ops.cuh"
+#include "post_kernels.cuh"
 
 using namespace pnde;
 
@@ -574,6 +575,112 @@ int pnde_get_history(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t 
 int pnde_get_marginals(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end, int64_t* offsets, double* t,
                        double* u, double* cov_u) {
   return get_history_impl(h, which, traj_begin, traj_end, offsets, t, u, cov_u, nullptr, true);
+}
+
+int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint64_t seed, int64_t* offsets, double* t,
+                double* samples) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  if (h->cfg.save_mode != PNDE_SAVE_EVERY) return h->fail(PNDE_ERR_STATE, "pnde_sample needs save_mode = PNDE_SAVE_EVERY");
+  if (tb < 0 || te > h->n || tb >= te || !offsets || n_samples < 1) return h->fail(PNDE_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const ModelOps* o = h->ops;
+  std::vector<int> ns;
+  int rc = fetch_i32(h, h->n_saved, ns);
+  if (rc != PNDE_OK) return rc;
+  const long long ntr = te - tb;
+  std::vector<long long> off((size_t)ntr + 1);
+  off[0] = 0;
+  for (long long i = 0; i < ntr; ++i) off[(size_t)i + 1] = off[(size_t)i] + ns[(size_t)(tb + i)];
+  const long long total = off[(size_t)ntr];
+  for (long long i = 0; i <= ntr; ++i) offsets[i] = off[(size_t)i];
+  const size_t nout = (size_t)total * n_samples * o->D;
+  CK(h->scratch_off.ensure(((size_t)ntr + 1) * 8), "alloc offsets");
+  CK(h->scratch_out.ensure(((size_t)total + nout) * 8 + 64), "alloc sample staging");
+  CK(cudaMemcpyAsync(h->scratch_off.p, off.data(), ((size_t)ntr + 1) * 8, cudaMemcpyHostToDevice, h->stream), "H2D offsets");
+  const int df = h->cfg.diffusion;
+  double* dt_ = h->scratch_out.as<double>();
+  double* dout = dt_ + total;
+  // time stamps through the converter (marginals mode with null outputs writes only t)
+  ConvertParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.n = h->n;
+  cp.traj_begin = tb;
+  cp.traj_end = te;
+  cp.max_saved = h->max_saved;
+  cp.n_saved = h->n_saved.as<int>();
+  cp.offsets = h->scratch_off.as<long long>();
+  cp.hist = h->hist.as<double>();
+  cp.final_diff = h->final_diff.as<double>();
+  cp.which = 0;
+  cp.marginals = 1;
+  cp.t = dt_;
+  cp.nd_out = 1;
+  CK(o->launch_convert(cp, h->stream), "convert kernel launch");
+  SampleParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.n = h->n;
+  sp.traj_begin = tb;
+  sp.traj_end = te;
+  sp.max_saved = h->max_saved;
+  sp.n_saved = h->n_saved.as<int>();
+  sp.offsets = h->scratch_off.as<long long>();
+  sp.hist = h->hist.as<double>();
+  sp.final_diff = h->final_diff.as<double>();
+  sp.calibrate = (df == PNDE_DIFF_FIXED || df == PNDE_DIFF_FIXED_MAP || df == PNDE_DIFF_FIXED_MV);
+  sp.is_mv = (df == PNDE_DIFF_DYNAMIC_MV || df == PNDE_DIFF_FIXED_MV);
+  sp.n_samples = n_samples;
+  sp.seed = seed;
+  sp.out = dout;
+  sp.C = h->C;
+  CK(o->launch_sample(sp, h->stream), "sample kernel launch");
+  if (t) CK(cudaMemcpyAsync(t, dt_, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
+  if (samples) CK(cudaMemcpyAsync(samples, dout, nout * 8, cudaMemcpyDeviceToHost, h->stream), "D2H samples");
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  return PNDE_OK;
+}
+
+int pnde_eval_dense(pnde_handle* h, int32_t which, int64_t tb, int64_t te, int64_t n_t, const double* t, double* mean,
+                    double* cov) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  if (h->cfg.save_mode != PNDE_SAVE_EVERY) return h->fail(PNDE_ERR_STATE, "dense output needs save_mode = PNDE_SAVE_EVERY");
+  if (which == PNDE_HIST_SMOOTHED && !h->smoothed) return h->fail(PNDE_ERR_STATE, "history has not been smoothed");
+  if (which != PNDE_HIST_FILTERED && which != PNDE_HIST_SMOOTHED) return h->fail(PNDE_ERR_ARG, "bad 'which'");
+  if (tb < 0 || te > h->n || tb >= te || n_t < 1 || !t) return h->fail(PNDE_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const ModelOps* o = h->ops;
+  const size_t ntr = (size_t)(te - tb), NC = (size_t)(o->D * (o->D + 1) / 2);
+  const size_t nm = ntr * (size_t)n_t * o->D, nc = ntr * (size_t)n_t * NC;
+  CK(h->scratch_out.ensure(((size_t)n_t + nm + nc) * 8 + 64), "alloc dense staging");
+  double* dtq = h->scratch_out.as<double>();
+  double* dmean = dtq + n_t;
+  double* dcov = dmean + nm;
+  CK(cudaMemcpyAsync(dtq, t, (size_t)n_t * 8, cudaMemcpyHostToDevice, h->stream), "H2D query times");
+  const int df = h->cfg.diffusion;
+  DenseParams dp;
+  memset(&dp, 0, sizeof(dp));
+  dp.n = h->n;
+  dp.traj_begin = tb;
+  dp.traj_end = te;
+  dp.max_saved = h->max_saved;
+  dp.n_t = n_t;
+  dp.n_saved = h->n_saved.as<int>();
+  dp.hist = h->hist.as<double>();
+  dp.smooth = h->smooth.as<double>();
+  dp.final_diff = h->final_diff.as<double>();
+  dp.calibrate = (df == PNDE_DIFF_FIXED || df == PNDE_DIFF_FIXED_MAP || df == PNDE_DIFF_FIXED_MV);
+  dp.is_mv = (df == PNDE_DIFF_DYNAMIC_MV || df == PNDE_DIFF_FIXED_MV);
+  dp.smoothed = (which == PNDE_HIST_SMOOTHED);
+  dp.tq = dtq;
+  dp.mean = dmean;
+  dp.cov = dcov;
+  dp.C = h->C;
+  CK(o->launch_dense(dp, h->stream), "dense kernel launch");
+  if (mean) CK(cudaMemcpyAsync(mean, dmean, nm * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
+  if (cov) CK(cudaMemcpyAsync(cov, dcov, nc * 8, cudaMemcpyDeviceToHost, h->stream), "D2H cov");
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  return PNDE_OK;
 }
 
 }  // extern "C"

@@ -38,10 +38,12 @@ struct SmoothCov {
         n2 = fma(v, v, n2);
       }
       const double pv = (c < NR1) ? Y[c < NR1 ? c : 0][c] : Tt[c - NR1 >= 0 ? c - NR1 : 0][c];
-      const double nrm = sqrt(n2);
+      const bool nz = n2 > 0.0;
+      const double rn = nz ? fast_rsqrt(n2) : 0.0;
+      const double nrm = n2 * rn;
       const double snrm = copysign(nrm, pv);
       const double v0 = pv + snrm;
-      const double beta = (n2 > 0.0) ? 1.0 / fma(fabs(pv), nrm, n2) : 0.0;
+      const double beta = nz ? fast_rcp(fma(fabs(pv), nrm, n2)) : 0.0;
       L[tri(c, c)] = -snrm;
 #pragma unroll
       for (int j = c + 1; j < D; ++j) {
@@ -69,79 +71,94 @@ struct SmoothCov {
     }
   }
 
-  // One RTS step of the covariance.
-  //   F   : filtered factor at i in P(h) coordinates (already scaled by the caller)
-  //   Ls  : smoothed factor at i+1 in P(h) coordinates, packed lower; overwritten by the smoothed
-  //         factor at i (still P(h) coordinates)
-  //   delta: in  m_next_smoothed - A m  ->  out  G * delta          (ND_M mean replicas)
-  template <int NREP>
-  __device__ __forceinline__ static void step(const Factor<dc, q>& F, const double sig, const IwpConsts& C,
-                                              double (&Ls)[NP], double (&delta)[NREP][D], int& status) {
+  // columns of the reduced-rank filtered factor as dense D-vectors
+  __device__ __forceinline__ static void cols_from_factor(const Factor<dc, q>& F, double (&cols)[R][D]) {
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        if (c < dc)
+          cols[c][i] = F.W[c < dc ? c : 0][i];
+        else
+          cols[c][i] = (i >= 2 * dc + (c - dc))
+                           ? F.Lz[Factor<dc, q>::lz(c - dc >= 0 ? c - dc : 0, i - 2 * dc >= 0 ? i - 2 * dc : 0)]
+                           : 0.0;
+      }
+    }
+  }
+  // columns of a packed lower-triangular D x D factor
+  __device__ __forceinline__ static void cols_from_lower(const double (&L)[NP], double (&cols)[D][D]) {
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+      for (int i = 0; i < D; ++i) cols[c][i] = (i >= c) ? L[tri(i, c)] : 0.0;
+  }
+
+  // stage 1: Householder sweep over [sig Q_L' | 0 ; (A cols)' | cols'] in natural coordinate order.
+  //   in : Er = the NR factor columns (P(h) coordinates)
+  //   out: Rm = R-' packed lower (Rm[tri(j,c)] = R-[c][j]), rinv[c] = 1/R-[c][c], X = top-right block,
+  //        Er = Y (backward-kernel noise factor: Y'Y = Sigma - G Sigma- G')
+  template <int NR>
+  __device__ __forceinline__ static void stage1(double (&Er)[NR][D], const double sig, const IwpConsts& C,
+                                                double (&Rm)[NP], double (&rinv)[D], double (&X)[D][D]) {
     double sL[q + 1][q + 1];
 #pragma unroll
     for (int k = 0; k <= q; ++k)
 #pragma unroll
       for (int kk = 0; kk <= k; ++kk) sL[k][kk] = sig * C.Lt[k][kk];
-    // bottom rows: left = (A s)', right = s'
-    double El[R][D], Er[R][D];
+    double El[NR][D];
 #pragma unroll
-    for (int c = 0; c < R; ++c) {
+    for (int c = 0; c < NR; ++c) {
       double w[D];
-      if (c < dc) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) w[i] = F.W[c < dc ? c : 0][i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-          w[i] = (i >= 2 * dc + (c - dc)) ? F.Lz[Factor<dc, q>::lz(c - dc >= 0 ? c - dc : 0, i - 2 * dc >= 0 ? i - 2 * dc : 0)] : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) Er[c][i] = w[i];
+      for (int i = 0; i < D; ++i) w[i] = Er[c][i];
       apply_A<dc, q>(w);
 #pragma unroll
       for (int i = 0; i < D; ++i) El[c][i] = w[i];
     }
-    // stage 1: Householder sweep, natural coordinate order; prior rows are sparse pivots
-    double Rm[NP];    // R- stored as its transpose (lower packed): Rm[tri(j,c)] = R-[c][j]
-    double X[D][D];   // top-right block
 #pragma unroll
     for (int c = 0; c < D; ++c) {
       const int kc = c / dc, ac = c % dc;
       const double pv = sL[kc][kc];
       double n2 = pv * pv;
 #pragma unroll
-      for (int i = 0; i < R; ++i) n2 = fma(El[i][c], El[i][c], n2);
-      const double nrm = sqrt(n2);
+      for (int i = 0; i < NR; ++i) n2 = fma(El[i][c], El[i][c], n2);
+      const bool nz = n2 > 0.0;
+      const double rn = nz ? fast_rsqrt(n2) : 0.0;
+      const double nrm = n2 * rn;
       const double v0 = pv + nrm;
-      const double beta = (n2 > 0.0) ? 1.0 / fma(pv, nrm, n2) : 0.0;
+      const double beta = nz ? fast_rcp(fma(pv, nrm, n2)) : 0.0;
       Rm[tri(c, c)] = -nrm;
+      rinv[c] = -rn;
 #pragma unroll
       for (int j = c + 1; j < D; ++j) {
         const bool pnz = (j % dc == ac);
         const double prj = pnz ? sL[j / dc][kc] : 0.0;
         double w = pnz ? v0 * prj : 0.0;
 #pragma unroll
-        for (int i = 0; i < R; ++i) w = (i == 0 && !pnz) ? El[i][c] * El[i][j] : fma(El[i][c], El[i][j], w);
+        for (int i = 0; i < NR; ++i) w = (i == 0 && !pnz) ? El[i][c] * El[i][j] : fma(El[i][c], El[i][j], w);
         const double s = beta * w;
         Rm[tri(j, c)] = pnz ? fma(-s, v0, prj) : -s * v0;
 #pragma unroll
-        for (int i = 0; i < R; ++i) El[i][j] = fma(-s, El[i][c], El[i][j]);
+        for (int i = 0; i < NR; ++i) El[i][j] = fma(-s, El[i][c], El[i][j]);
       }
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         double w = El[0][c] * Er[0][j];
 #pragma unroll
-        for (int i = 1; i < R; ++i) w = fma(El[i][c], Er[i][j], w);
+        for (int i = 1; i < NR; ++i) w = fma(El[i][c], Er[i][j], w);
         const double s = beta * w;
         X[c][j] = -s * v0;
 #pragma unroll
-        for (int i = 0; i < R; ++i) Er[i][j] = fma(-s, El[i][c], Er[i][j]);
+        for (int i = 0; i < NR; ++i) Er[i][j] = fma(-s, El[i][c], Er[i][j]);
       }
     }
-    // stage 2a: mean  G delta = X' (R-^-T delta);  R-^T is lower triangular = Rm as stored
-    double rinv[D];
-#pragma unroll
-    for (int c = 0; c < D; ++c) rinv[c] = (Rm[tri(c, c)] != 0.0) ? 1.0 / Rm[tri(c, c)] : 0.0;
+  }
+
+  // delta <- G delta = X' (R-^-T delta)
+  template <int NREP>
+  __device__ __forceinline__ static void apply_gain(const double (&Rm)[NP], const double (&rinv)[D],
+                                                    const double (&X)[D][D], double (&delta)[NREP][D]) {
 #pragma unroll
     for (int r = 0; r < NREP; ++r) {
       double y[D];
@@ -160,7 +177,12 @@ struct SmoothCov {
         delta[r][i] = acc;
       }
     }
-    // stage 2b: Z = R-^-T Ls (lower triangular), column by column (forward substitution)
+  }
+
+  // Tt[c][i] = (G Ls)[i][c]:  Z = R-^-T Ls (lower triangular, forward substitution), T = X' Z
+  __device__ __forceinline__ static void gain_times_lower(const double (&Rm)[NP], const double (&rinv)[D],
+                                                          const double (&X)[D][D], const double (&Ls)[NP],
+                                                          double (&Tt)[D][D]) {
     double Z[NP];
 #pragma unroll
     for (int c = 0; c < D; ++c) {
@@ -172,8 +194,6 @@ struct SmoothCov {
         Z[tri(i, c)] = acc * rinv[i];
       }
     }
-    // T = X' Z  (D x D), stored transposed: Tt[c][i] = T[i][c] = sum_{k>=c} X[k][i] Z[k][c]
-    double Tt[D][D];
 #pragma unroll
     for (int c = 0; c < D; ++c) {
 #pragma unroll
@@ -184,8 +204,29 @@ struct SmoothCov {
         Tt[c][i] = acc;
       }
     }
-    // stage 3: smoothed factor = triangularisation of [Y ; T']
-    triangularize<R>(Er, Tt, Ls, status);
+  }
+
+  // One RTS step of the covariance.
+  //   cols : the NR columns of the current (filtered / predicted) factor in P(h) coordinates; destroyed
+  //   Ls   : smoothed factor at i+1 in P(h) coordinates, packed lower; overwritten by the smoothed
+  //          factor at i (still P(h) coordinates)
+  //   delta: in  m_next_smoothed - A m  ->  out  G * delta          (NREP mean replicas)
+  template <int NR, int NREP>
+  __device__ __forceinline__ static void step_cols(double (&cols)[NR][D], const double sig, const IwpConsts& C,
+                                                   double (&Ls)[NP], double (&delta)[NREP][D], int& status) {
+    double Rm[NP], rinv[D], X[D][D];
+    stage1<NR>(cols, sig, C, Rm, rinv, X);
+    apply_gain<NREP>(Rm, rinv, X, delta);
+    double Tt[D][D];
+    gain_times_lower(Rm, rinv, X, Ls, Tt);
+    triangularize<NR>(cols, Tt, Ls, status);
+  }
+  template <int NREP>
+  __device__ __forceinline__ static void step(const Factor<dc, q>& F, const double sig, const IwpConsts& C,
+                                              double (&Ls)[NP], double (&delta)[NREP][D], int& status) {
+    double cols[R][D];
+    cols_from_factor(F, cols);
+    step_cols<R, NREP>(cols, sig, C, Ls, delta, status);
   }
 };
 
@@ -261,7 +302,7 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
   using SC = typename SM::SC;
   constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, SREC = SM::SREC, NF = SM::NF, DC = SM::DC;
   constexpr int DCOV = DC * (q + 1);  // dimension of one covariance factor
-  constexpr int NREP = D / DCOV;      // mean replicas per factor group (1 dense, d Kronecker)
+
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= sp.n) return;
   const long long n = sp.n;

@@ -165,3 +165,68 @@ def test_ensemble_matches_single_solves():
         so = O.solve_ivp(pr, O.EK1(order=3, smooth=False), adaptive=False, dt=0.01)
         assert rel(es.u[i], so.x_filt[-1].mu[:2]) < 1e-10
         assert es.destats["naccept"][i] == so.naccept
+
+
+# ---- dense output and sampling ----------------------------------------
+@pytest.mark.parametrize("name,kind,q,smooth", [
+    ("lotka_volterra", "EK1", 3, True), ("lotka_volterra", "EK1", 2, False), ("fhn_readme", "EK0", 2, True),
+    ("lotka_volterra", "EK0", 3, False),
+])
+def test_dense_output_matches_oracle(name, kind, q, smooth):
+    """sol(t): GaussianODEFilterPosterior (src/solution.jl:165-215) against the oracle's posterior_at."""
+    import odefilters_b200 as B
+
+    so = oracle_solve(name, O.Alg(kind, q, "dynamic", smooth), tspan=(0.0, 2.0))
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, smooth=smooth)
+    sg = gpu_solve(name, alg, tspan=(0.0, 2.0))
+    assert len(sg.t) == len(so.t)
+    # exact hits are taken from the GPU's own grid (adaptive grids agree to ~1e-10, not bitwise)
+    tq = np.concatenate([np.linspace(0.013, 1.987, 23), np.asarray(sg.t)[[0, 3, -1]], [2.5]])
+    post = sg.posterior(tq)
+    d = 2
+    for i, t in enumerate(tq):
+        if t in sg.t:  # exact hits return the stored state (src/solution.jl:172-176)
+            k = list(sg.t).index(t)
+            src = sg.x_smooth if smooth else sg.x_filt
+            assert np.array_equal(post.mu[i], src.mu[k])
+            continue
+        ref = O.posterior_at(so, float(t))
+        assert rel(post.mu[i][:d], ref.mu[:d]) < 1e-8
+        assert rel(post.Sigma[i][:d, :d], ref.Sigma.mat[:d, :d]) < cov_tol(q, 0) * 10
+    u = sg(tq[:5])  # sol(t) is the projection onto the solution block
+    assert np.array_equal(u.mu, post.mu[:5, :d])
+    # test/solution.jl:44-55: variance grows away from a grid point (filtering posterior)
+    if not smooth:
+        t0 = sg.t[0]
+        v1, v2 = sg(t0 + 1e-3).Sigma.mat, sg(t0 + 2e-3).Sigma.mat
+        assert np.all(np.diag(v1) < np.diag(v2))
+
+
+@pytest.mark.parametrize("kind,q", [("EK1", 3), ("EK0", 2)])
+def test_sampling_statistics(kind, q):
+    """sample_states (src/solution_sampling.jl:24-62): the draws differ from the reference's (other factor,
+    other generator) but the distribution is the smoothing posterior: moments and test/solution.jl:58-104."""
+    import odefilters_b200 as B
+
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, smooth=True)
+    sol = gpu_solve("lotka_volterra", alg, tspan=(0.0, 3.0), abstol=1e-3, reltol=1e-2)
+    n = 4000
+    S = sol.sample_states(n, seed=7)
+    D = 2 * (q + 1)
+    assert S.shape == (len(sol), D, n)
+    assert np.array_equal(S, sol.sample_states(n, seed=7))          # reproducible
+    assert not np.array_equal(S, sol.sample_states(n, seed=8))
+    assert np.allclose(S[0, :2, :], 1.0, rtol=1e-14, atol=0)         # initial state has zero covariance (P, PI round trip only)
+    mu, Sig = sol.x_smooth.mu, sol.x_smooth.Sigma
+    std = np.sqrt(np.maximum(np.diagonal(Sig, axis1=1, axis2=2), 0))
+    m_emp, s_emp = S.mean(axis=2), S.std(axis=2)
+    ok = std > 1e-14 * np.abs(mu).max()
+    assert np.all(np.abs(m_emp - mu)[ok] < 6 * std[ok] / np.sqrt(n))  # sample mean = smoothed mean
+    assert np.all(np.abs(s_emp[ok] / std[ok] - 1) < 0.12)             # sample std = smoothed std
+    smp = sol.sample(10, seed=3)
+    assert smp.shape == (len(sol), 2, 10)
+    outliers = np.sum(np.abs(smp - sol.u[:, :, None]) > 3 * std[:, :2, None])
+    assert outliers < 0.05 * smp.size                                  # test/solution.jl:70-72
+    # cross-time structure: lag-1 sample covariance of u matches G-propagated smoothing covariance sign
+    c = np.mean((S[-2, 0] - m_emp[-2, 0]) * (S[-1, 0] - m_emp[-1, 0]))
+    assert c > 0
