@@ -68,11 +68,27 @@ def config5(n):
             "all_success": bool((c["retcode"] == 0).all())}
 
 
+def config4(d=1024):
+    rng = np.random.default_rng(SEED)
+    u0 = 8.0 + 0.01 * rng.standard_normal(d)
+    prob = B.ODEProblem("lorenz96", u0, (0.0, 1.0), (8.0,))
+    s = B.FilterSolver(prob, B.EK0(order=3, smooth=False), adaptive=False, dt=1e-3, save_everystep=False)
+    s.upload(u0[None, :], np.array([[8.0]]))
+    for _ in range(3):
+        s.run()
+    ms = s.last_run_ms()[0]
+    c = s.counts()
+    steps = int(c["naccept"].sum())
+    return {"config": 4, "what": f"Lorenz-96 d={d}, EK0(order=3) Kronecker covariance, fixed dt=1e-3, one CTA",
+            "steps": steps, "ms": ms, "us_per_step": 1e3 * ms / steps, "all_success": bool((c["retcode"] == 0).all()),
+            "note": "latency bound (one sequential chain, 3 block syncs per step); EK1 dense D=4096 path not built"}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--n3", type=int, default=100000)
     ap.add_argument("--n5", type=int, default=250000)
     a = ap.parse_args()
-    for fn, arg in ((config1, None), (config3, a.n3), (config5, a.n5)):
+    for fn, arg in ((config1, None), (config3, a.n3), (config4, 1024), (config5, a.n5)):
         out = fn() if arg is None else fn(arg)
         print(json.dumps(out), flush=True)

@@ -63,7 +63,8 @@ extern "C" {
 #define PNDE_VF_VANDERPOL 3      /* prob_ode_vanstiff ordering u=(y,x), p = (mu) */
 #define PNDE_VF_LINEAR2 4        /* du_i = p_i u_i, d = 2 (test/state_init.jl:15) */
 #define PNDE_VF_LOGISTIC 5       /* du = p u (1-u), d = 1 (test/specific_problems.jl:62) */
-#define PNDE_VF_LORENZ96 6       /* d given in the config, p = (F) */
+#define PNDE_VF_LORENZ96 6       /* d given in the config (4..2048), p = (F); EK0 only: one CTA per trajectory,
+                                    Kronecker-factored covariance, final state only (BASELINE config 4) */
 #define PNDE_VF_LINEAR1 7        /* du = p u, d = 1 (test/convergence.jl:10) */
 
 /* what is written to the device-side history */
@@ -121,6 +122,8 @@ const char* pnde_last_error(const pnde_handle* h); /* h may be NULL: last create
 int64_t pnde_state_dim(const pnde_handle* h);    /* D = d (q+1) */
 int64_t pnde_n_params(const pnde_handle* h);     /* parameters per trajectory */
 int64_t pnde_record_len(const pnde_handle* h);   /* doubles per saved state in the device history */
+int64_t pnde_cov_len(const pnde_handle* h);      /* rows of pnde_get_final's cov: D(D+1)/2, or (q+1)(q+2)/2 for
+                                                    the Lorenz-96 Kronecker path (Sigma = Ctilde (x) I_d) */
 
 /* One call = one EnsembleProblem solve: host buffers in, results kept on the device.
  * u0: [d][n_traj], p: [n_params][n_traj].  Equivalent to pnde_upload + pnde_run (+ pnde_smooth). */

@@ -34,7 +34,7 @@ class PndeConfig(C.Structure):
 
 EXPORTS = [
     "pnde_default_config", "pnde_create", "pnde_destroy", "pnde_last_error", "pnde_state_dim", "pnde_n_params",
-    "pnde_record_len", "pnde_solve_ensemble", "pnde_upload", "pnde_run", "pnde_synchronize", "pnde_last_run_ms",
+    "pnde_record_len", "pnde_cov_len", "pnde_solve_ensemble", "pnde_upload", "pnde_run", "pnde_synchronize", "pnde_last_run_ms",
     "pnde_last_launch_count", "pnde_smooth", "pnde_query_sizes", "pnde_get_counts", "pnde_get_final",
     "pnde_get_history", "pnde_get_marginals", "pnde_sample", "pnde_eval_dense", "pnde_measure_fp64_peak",
     "pnde_measure_hbm_copy",
@@ -59,7 +59,7 @@ def load():
     lib.pnde_destroy.argtypes = [vp]
     lib.pnde_last_error.argtypes = [vp]
     lib.pnde_last_error.restype = C.c_char_p
-    for f in ("pnde_state_dim", "pnde_n_params", "pnde_record_len", "pnde_last_launch_count"):
+    for f in ("pnde_state_dim", "pnde_n_params", "pnde_record_len", "pnde_cov_len", "pnde_last_launch_count"):
         getattr(lib, f).argtypes = [vp]
         getattr(lib, f).restype = C.c_int64
     lib.pnde_solve_ensemble.argtypes = [vp, C.c_int64, vp, vp]

@@ -54,14 +54,14 @@ class ODEProblem:
     p: Sequence[float] = ()
 
     def __post_init__(self):
-        if self.f not in L.VF_DIMS:
-            raise ValueError(f"unknown vector field {self.f!r}; catalogue: {sorted(L.VF_DIMS)}")
+        if self.f not in L.VF_KINDS:
+            raise ValueError(f"unknown vector field {self.f!r}; catalogue: {sorted(L.VF_KINDS)}")
         u0 = np.asarray(self.u0, dtype=np.float64)
         if u0.ndim != 1:
             # src/caches.jl:46-49
             raise ValueError("Problems which are not scalar- or vector-valued (e.g. u0 is a scalar or a matrix) "
                              "are currently not supported")
-        d, npar = L.VF_DIMS[self.f]
+        d, npar = L.VF_DIMS.get(self.f, (u0.shape[0], 1))  # lorenz96: d = len(u0), p = (F,)
         if u0.shape[0] != d:
             raise ValueError(f"{self.f} has dimension {d}")
         p = np.atleast_1d(np.asarray(self.p, dtype=np.float64))
@@ -255,6 +255,7 @@ class FilterSolver:
         cfg.maxiters = int(maxiters)
         cfg.max_saved = int(max_saved)
         cfg.dtmin = float(dtmin)
+        cfg.d = len(prob.u0)
         for name, val in (("dtmax", dtmax), ("qmin", qmin), ("qmax", qmax), ("gamma", gamma), ("beta1", beta1),
                           ("beta2", beta2)):
             if val is not None:
@@ -264,8 +265,10 @@ class FilterSolver:
         rc = self.lib.pnde_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             raise RuntimeError(f"pnde_create failed ({rc}): {self.lib.pnde_last_error(None).decode()}")
-        self.d, self.npar = L.VF_DIMS[prob.f]
+        self.d, self.npar = L.VF_DIMS.get(prob.f, (len(prob.u0), 1))
         self.D = int(self.lib.pnde_state_dim(self._h))
+        self.ncov = int(self.lib.pnde_cov_len(self._h))
+        self.kron = prob.f == "lorenz96"  # covariance returned as the Kronecker factor Ctilde
         self.n = 0
         self.is_mv = alg.diffusionmodel in ("dynamicMV", "fixedMV")
 
@@ -343,7 +346,7 @@ class FilterSolver:
         """(mean [N, D], cov packed [N, D(D+1)/2], t_final [N], loglik [N])."""
         n, D = self.n, self.D
         mean = np.empty((D, n))
-        cov = np.empty((D * (D + 1) // 2, n))
+        cov = np.empty((self.ncov, n))
         tf = np.empty(n)
         ll = np.empty(n)
         self._check(self.lib.pnde_get_final(self._h, mean.ctypes.data, cov.ctypes.data, tf.ctypes.data,
@@ -407,6 +410,16 @@ class FilterSolver:
         smoothed = bool(self.cfg.smooth)
         if self.cfg.save_mode == L.SAVE_FINAL:
             mean, cov, tf, ll = final or self.final()
+            if self.kron:
+                # Sigma = Ctilde (x) I_d: the full D x D matrix is never formed; marginals use Ctilde[0, 0]
+                ct = _unpack_lower(cov[i:i + 1], self.alg.order + 1)
+                pu = _GaussianList(mean[i:i + 1, :d].copy(), ct[:, 0, 0][:, None, None] * np.eye(d)[None])
+                return ProbODESolution(
+                    t=tf[i:i + 1], u=pu.mu, pu=pu, x_filt=_GaussianList(mean[i:i + 1], ct), x_smooth=None,
+                    diffusions=np.zeros(0), log_likelihood=float(ll[i]),
+                    destats={k: int(counts[k][i]) for k in ("naccept", "nreject", "nf", "njacs")},
+                    retcode=L.RETCODES.get(int(counts["retcode"][i]), "Failure"), prob=self.prob, alg=self.alg,
+                    _solver=self, _index=i)
             xf = _GaussianList(mean[i:i + 1], _unpack_lower(cov[i:i + 1], D))
             t = tf[i:i + 1]
             diffs = np.zeros((0, 1))

@@ -10,6 +10,7 @@
 
 #include "../../include/pnde.h"
 #include "model_ops.cuh"
+#include "lorenz96_kernel.cuh"
 #include "post_kernels.cuh"
 
 using namespace pnde;
@@ -81,7 +82,9 @@ const ModelOps* find_ops(int vf, int alg, int q, bool mvdyn) {
 
 struct pnde_handle {
   pnde_config cfg;
-  const ModelOps* ops = nullptr;
+  const ModelOps* ops = nullptr;  // nullptr for the CTA-per-trajectory Lorenz-96 path
+  bool lorenz = false;
+  int d = 0, D = 0, np = 0, nd = 1, ncov = 0;  // dimensions (from ops, or from cfg for Lorenz-96)
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -191,14 +194,35 @@ int pnde_create(const pnde_config* cfg, pnde_handle** out) {
     g_create_error = "save_stride must be >= 1";
     return PNDE_ERR_ARG;
   }
-  const ModelOps* ops = find_ops(cfg->vf_kind, cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV);
-  if (!ops) {
-    g_create_error = "no built-in kernel for this (vf_kind, alg, order)";
-    return PNDE_ERR_UNSUPPORTED;
-  }
-  if (cfg->d != 0 && cfg->d != ops->d) {
-    g_create_error = "d does not match the vector field";
-    return PNDE_ERR_ARG;
+  const bool lorenz = (cfg->vf_kind == PNDE_VF_LORENZ96);
+  const ModelOps* ops = nullptr;
+  if (lorenz) {
+    if (cfg->alg != PNDE_ALG_EK0) {
+      g_create_error = "Lorenz-96: only the EK0 Kronecker path is built; the EK1 dense path (D >= 64, DMMA QR) is not";
+      return PNDE_ERR_UNSUPPORTED;
+    }
+    if (cfg->d < 4 || cfg->d > 8 * LORENZ_THREADS) {
+      g_create_error = "Lorenz-96: d must be in 4..2048";
+      return PNDE_ERR_ARG;
+    }
+    if (mv) {
+      g_create_error = "Lorenz-96: MV diffusion models are not built for the large-d path";
+      return PNDE_ERR_UNSUPPORTED;
+    }
+    if (cfg->save_mode != PNDE_SAVE_FINAL || cfg->smooth) {
+      g_create_error = "Lorenz-96: only save_mode = PNDE_SAVE_FINAL (no smoothing) is built for the large-d path";
+      return PNDE_ERR_UNSUPPORTED;
+    }
+  } else {
+    ops = find_ops(cfg->vf_kind, cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV);
+    if (!ops) {
+      g_create_error = "no built-in kernel for this (vf_kind, alg, order)";
+      return PNDE_ERR_UNSUPPORTED;
+    }
+    if (cfg->d != 0 && cfg->d != ops->d) {
+      g_create_error = "d does not match the vector field";
+      return PNDE_ERR_ARG;
+    }
   }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -220,8 +244,22 @@ int pnde_create(const pnde_config* cfg, pnde_handle** out) {
   }
   pnde_handle* h = new pnde_handle();
   h->cfg = *cfg;
-  h->cfg.d = ops->d;
   h->ops = ops;
+  h->lorenz = lorenz;
+  if (lorenz) {
+    h->d = cfg->d;
+    h->D = cfg->d * (cfg->order + 1);
+    h->np = 1;
+    h->nd = 1;
+    h->ncov = (cfg->order + 1) * (cfg->order + 2) / 2;  // Kronecker factor Ctilde
+  } else {
+    h->d = ops->d;
+    h->D = ops->D;
+    h->np = ops->np;
+    h->nd = ops->nd;
+    h->ncov = ops->D * (ops->D + 1) / 2;
+  }
+  h->cfg.d = h->d;
   h->device = dev;
   if (!build_iwp(cfg->order, h->C)) {
     delete h;
@@ -262,9 +300,10 @@ int pnde_destroy(pnde_handle* h) {
 
 const char* pnde_last_error(const pnde_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int64_t pnde_state_dim(const pnde_handle* h) { return h ? h->ops->D : 0; }
-int64_t pnde_n_params(const pnde_handle* h) { return h ? h->ops->np : 0; }
-int64_t pnde_record_len(const pnde_handle* h) { return h ? h->ops->rec : 0; }
+int64_t pnde_state_dim(const pnde_handle* h) { return h ? h->D : 0; }
+int64_t pnde_n_params(const pnde_handle* h) { return h ? h->np : 0; }
+int64_t pnde_record_len(const pnde_handle* h) { return (h && h->ops) ? h->ops->rec : 0; }
+int64_t pnde_cov_len(const pnde_handle* h) { return h ? h->ncov : 0; }
 
 static long long derive_max_saved(const pnde_handle* h) {
   const pnde_config& c = h->cfg;
@@ -279,9 +318,10 @@ static long long derive_max_saved(const pnde_handle* h) {
 
 int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* p) {
   if (!h) return PNDE_ERR_ARG;
-  if (n_traj <= 0 || !u0 || (!p && h->ops->np > 0)) return h->fail(PNDE_ERR_ARG, "pnde_upload: bad arguments");
+  if (n_traj <= 0 || !u0 || (!p && h->np > 0)) return h->fail(PNDE_ERR_ARG, "pnde_upload: bad arguments");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
-  const ModelOps* o = h->ops;
+  struct { int d, np, D, nd, rec; } dims = {h->d, h->np, h->D, h->nd, h->ops ? h->ops->rec : 0};
+  const auto* o = &dims;
   const size_t n = (size_t)n_traj;
   const long long ms = derive_max_saved(h);
   if (h->cfg.save_mode != PNDE_SAVE_FINAL && ms <= 0)
@@ -290,7 +330,7 @@ int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* 
   CK(h->u0.ensure(n * o->d * 8), "alloc u0");
   CK(h->p.ensure(n * (o->np > 0 ? o->np : 1) * 8), "alloc p");
   CK(h->mean.ensure(n * o->D * 8), "alloc mean");
-  CK(h->cov.ensure(n * (size_t)(o->D * (o->D + 1) / 2) * 8), "alloc cov");
+  CK(h->cov.ensure(n * (size_t)h->ncov * 8), "alloc cov");
   CK(h->t_final.ensure(n * 8), "alloc t_final");
   CK(h->loglik.ensure(n * 8), "alloc loglik");
   CK(h->final_diff.ensure(n * o->nd * 8), "alloc final_diff");
@@ -361,7 +401,36 @@ int pnde_run(pnde_handle* h) {
   fp.K.dtmax = c.dtmax;
   fp.K.maxiters = c.maxiters;
   CK(cudaEventRecord(h->ev[0], h->stream), "event record");
-  CK(h->ops->launch_filter(fp, c.adaptive != 0, h->stream), "filter kernel launch");
+  if (h->lorenz) {
+    LorenzParams lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.n = fp.n;
+    lp.d = h->d;
+    lp.u0 = fp.u0;
+    lp.p = fp.p;
+    lp.mean = fp.mean;
+    lp.cov = fp.cov;
+    lp.t_final = fp.t_final;
+    lp.loglik = fp.loglik;
+    lp.final_diff = fp.final_diff;
+    lp.retcode = fp.retcode;
+    lp.naccept = fp.naccept;
+    lp.nreject = fp.nreject;
+    lp.nf = fp.nf;
+    lp.n_saved = fp.n_saved;
+    lp.hist = nullptr;
+    lp.max_saved = 0;
+    lp.save_mode = PNDE_SAVE_FINAL;
+    lp.save_stride = 1;
+    lp.diffusion = fp.diffusion;
+    lp.adaptive = c.adaptive;
+    lp.C = fp.C;
+    lp.K = fp.K;
+    CK(cudaMemsetAsync(h->njacs.p, 0, (size_t)h->n * 4, h->stream), "memset njacs");
+    CK(launch_lorenz(c.order, lp, h->stream), "lorenz96 kernel launch");
+  } else {
+    CK(h->ops->launch_filter(fp, c.adaptive != 0, h->stream), "filter kernel launch");
+  }
   CK(cudaEventRecord(h->ev[1], h->stream), "event record");
   h->launches = 1;
   h->ran = true;
@@ -496,11 +565,8 @@ int pnde_get_final(pnde_handle* h, double* mean, double* cov, double* t_final, d
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   const size_t n = (size_t)h->n;
-  const ModelOps* o = h->ops;
-  if (mean) CK(cudaMemcpyAsync(mean, h->mean.p, n * o->D * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
-  if (cov)
-    CK(cudaMemcpyAsync(cov, h->cov.p, n * (size_t)(o->D * (o->D + 1) / 2) * 8, cudaMemcpyDeviceToHost, h->stream),
-       "D2H cov");
+  if (mean) CK(cudaMemcpyAsync(mean, h->mean.p, n * h->D * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
+  if (cov) CK(cudaMemcpyAsync(cov, h->cov.p, n * (size_t)h->ncov * 8, cudaMemcpyDeviceToHost, h->stream), "D2H cov");
   if (t_final) CK(cudaMemcpyAsync(t_final, h->t_final.p, n * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
   if (loglik) CK(cudaMemcpyAsync(loglik, h->loglik.p, n * 8, cudaMemcpyDeviceToHost, h->stream), "D2H loglik");
   CK(cudaStreamSynchronize(h->stream), "stream synchronize");

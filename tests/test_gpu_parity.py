@@ -230,3 +230,46 @@ def test_sampling_statistics(kind, q):
     # cross-time structure: lag-1 sample covariance of u matches G-propagated smoothing covariance sign
     c = np.mean((S[-2, 0] - m_emp[-2, 0]) * (S[-1, 0] - m_emp[-1, 0]))
     assert c > 0
+
+
+# ---- BASELINE config 4: Lorenz-96, EK0 with the Kronecker-factored covariance -------------------
+def _lorenz_inputs(d, seed=20260118):
+    rng = np.random.default_rng(seed)
+    return 8.0 + 0.01 * rng.standard_normal(d)
+
+
+@pytest.mark.parametrize("d", [8, 40])
+@pytest.mark.parametrize("diffusion", ["dynamic", "fixed"])
+def test_lorenz96_small_d_against_dense_oracle(d, diffusion):
+    import odefilters_b200 as B
+
+    u0 = _lorenz_inputs(d)
+    so = O.solve_ivp(O.Problem(O.lorenz96(d), list(u0), (0.0, 0.3), [8.0]), O.Alg("EK0", 3, diffusion, False),
+                     adaptive=False, dt=0.01)
+    sg = B.solve(B.ODEProblem("lorenz96", u0, (0.0, 0.3), (8.0,)), B.EK0(order=3, diffusionmodel=diffusion, smooth=False),
+                 adaptive=False, dt=0.01, save_everystep=False)
+    ref = so.x_filt[-1]
+    assert rel(sg.x_filt.mu[0], ref.mu) < 1e-9
+    Cfull = np.kron(sg.x_filt.Sigma[0], np.eye(d))
+    assert rel(Cfull, ref.Sigma.mat) < 1e-6
+    assert sg.destats["naccept"] == so.naccept and sg.retcode == "Success"
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_lorenz96_d1024(adaptive):
+    """d = 1024 (config 4): against the numpy Kronecker model, itself checked against the dense oracle."""
+    import kron_model as KM
+    import odefilters_b200 as B
+
+    d, q, F = 1024, 3, 8.0
+    u0 = _lorenz_inputs(d)
+    kw = dict(adaptive=False, dt=1e-3) if not adaptive else dict()
+    km = KM.solve_ek0_kron(lambda u: KM.lorenz96_f(u, F), KM.lorenz96_jets(u0, F, q), (0.0, 0.2), q, **kw)
+    sg = B.solve(B.ODEProblem("lorenz96", u0, (0.0, 0.2), (F,)), B.EK0(order=q, smooth=False), save_everystep=False, **kw)
+    assert (sg.destats["naccept"], sg.destats["nreject"], sg.destats["nf"]) == (km["naccept"], km["nreject"], km["nf"])
+    M = sg.x_filt.mu[0].reshape(q + 1, d)
+    assert rel(M[0], km["M"][0]) < 1e-10
+    for k in range(1, q + 1):
+        assert rel(M[k], km["M"][k]) < 1e-6
+    assert rel(sg.x_filt.Sigma[0], km["C"]) < 1e-5
+    assert sg.t[-1] == 0.2

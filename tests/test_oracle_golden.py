@@ -202,3 +202,21 @@ def test_c_restatement_adaptive_counts():
     r = R.solve_ensemble("fhn_lib", "EK1", 3, [[1.0, 1.0]], [[0.7, 0.8, 1 / 12.5, 0.5]], (0.0, 1.0))
     assert (r["naccept"][0], r["nreject"][0], r["nf"][0]) == (so.naccept, so.nreject, so.nf) == (7, 0, 9)
     assert np.allclose(r["mean"][0][:2], so.x_filt[-1].mu[:2], rtol=1e-9)
+
+
+# ---- the Kronecker EK0 model (checker of the large-d GPU path) against the dense oracle ---------
+@pytest.mark.parametrize("adaptive", [False, True])
+@pytest.mark.parametrize("diffusion", ["dynamic", "fixed"])
+def test_kronecker_model_equals_dense_oracle(adaptive, diffusion):
+    import kron_model as KM
+
+    d, F, q = 8, 8.0, 3
+    u0 = F + 0.01 * np.random.default_rng(0).standard_normal(d)
+    kw = dict(adaptive=False, dt=0.01) if not adaptive else dict()
+    so = O.solve_ivp(O.Problem(O.lorenz96(d), list(u0), (0.0, 0.5), [F]), O.Alg("EK0", q, diffusion, False), **kw)
+    km = KM.solve_ek0_kron(lambda u: KM.lorenz96_f(u, F), KM.lorenz96_jets(u0, F, q), (0.0, 0.5), q,
+                           diffusion=diffusion, **kw)
+    assert (so.naccept, so.nreject, so.nf) == (km["naccept"], km["nreject"], km["nf"])
+    ref = so.x_filt[-1]
+    assert np.max(np.abs(km["M"].ravel() - ref.mu)) / np.max(np.abs(ref.mu)) < 1e-10
+    assert np.max(np.abs(np.kron(km["C"], np.eye(d)) - ref.Sigma.mat)) / np.max(np.abs(ref.Sigma.mat)) < 1e-9
