@@ -268,7 +268,8 @@ class FilterSolver:
         self.d, self.npar = L.VF_DIMS.get(prob.f, (len(prob.u0), 1))
         self.D = int(self.lib.pnde_state_dim(self._h))
         self.ncov = int(self.lib.pnde_cov_len(self._h))
-        self.kron = prob.f == "lorenz96"  # covariance returned as the Kronecker factor Ctilde
+        # Lorenz-96 EK0: covariance returned as the Kronecker factor Ctilde (EK1 returns the full matrix)
+        self.kron = prob.f == "lorenz96" and alg.kind == L.ALG_EK0
         self.n = 0
         self.is_mv = alg.diffusionmodel in ("dynamicMV", "fixedMV")
 

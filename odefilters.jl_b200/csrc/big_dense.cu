@@ -1,0 +1,459 @@
+// Host orchestration + element-wise kernels of the large-D EK1 path (see big_dense.cuh).
+// Lorenz-96 only (the one catalogue entry with large d); fixed steps; one trajectory at a time.
+#include "big_dense.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "big_dense_api.h"
+#include "filter_kernel.cuh"
+
+namespace pnde {
+namespace big {
+
+namespace {
+
+struct StepCtx {
+  int d, q, D;
+  double F;
+  double* m;      // [D] mean, natural coordinates
+  double* mp;     // [D] predicted mean, P(h) coordinates
+  double* Jp;     // [d][4] pi0 * J, columns (i-2, i-1, i, i+1)
+  double* fu;     // [d]
+  double* z;      // [d]
+  double* y;      // [d]
+  double* S;      // [D-d][D] posterior factor columns (natural coordinates), row c = column c
+  double* E;      // [D][D]
+  double* R;      // [D][D]
+  Scalars* sc;
+  int diffusion;
+  IwpConsts C;
+};
+
+__device__ __forceinline__ int wrapi(int i, int d) { return i < 0 ? i + d : (i >= d ? i - d : i); }
+
+// per step scalars: pi_k for this h (also resets the per-step accumulators)
+__global__ void set_step_kernel(Scalars* sc, double h, int q) {
+  double v = sqrt(h);
+  for (int k = q; k > 1; --k) v *= h;  // h^(q-1/2) = pi_1
+  sc->pi1 = v;
+  sc->pi0 = v * h;
+  sc->ipi1 = 1.0 / v;
+  sc->h = h;
+}
+
+// mean predict (P(h) coordinates), u-hat, f, sparse J, z
+__global__ void measure_kernel(StepCtx c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.d) return;
+  const int d = c.d, q = c.q;
+  const double h = c.sc->h, pi0 = c.sc->pi0, pi1 = c.sc->pi1;
+  // P_k = h^(k-q-1/2): P_0 = 1/pi0, P_k = P_{k-1} * h
+  auto pred0 = [&](int j) {  // block 0 of A P m at dimension j
+    double Pk = 1.0 / pi0, acc = 0.0;
+    for (int k = 0; k <= q; ++k) {
+      acc = fma(inv_factorial(k) * Pk, c.m[k * d + j], acc);
+      Pk *= h;
+    }
+    return acc;
+  };
+  double Pk = 1.0 / pi0;
+  double Pks[QMAX + 1];
+  for (int k = 0; k <= q; ++k) {
+    Pks[k] = Pk;
+    Pk *= h;
+  }
+  for (int k = 0; k <= q; ++k) {
+    double acc = 0.0;
+    for (int kk = k; kk <= q; ++kk) acc = fma(inv_factorial(kk - k) * Pks[kk], c.m[kk * d + i], acc);
+    c.mp[k * d + i] = acc;
+  }
+  const double up = pi0 * pred0(wrapi(i + 1, d)), um1 = pi0 * pred0(wrapi(i - 1, d)), um2 = pi0 * pred0(wrapi(i - 2, d));
+  const double ui = pi0 * c.mp[i];
+  const double f = (up - um2) * um1 - ui + c.F;
+  c.fu[i] = f;
+  c.z[i] = fma(pi1, c.mp[d + i], -f);
+  // J row i: d f_i / d u_{i-2} = -u_{i-1}; / d u_{i-1} = u_{i+1} - u_{i-2}; / d u_i = -1; / d u_{i+1} = u_{i-1}
+  c.Jp[i * 4 + 0] = pi0 * (-um1);
+  c.Jp[i * 4 + 1] = pi0 * (up - um2);
+  c.Jp[i * 4 + 2] = pi0 * (-1.0);
+  c.Jp[i * 4 + 3] = pi0 * um1;
+}
+
+// Jp[b][a] for the sparse Lorenz-96 Jacobian (0 outside the 4 stored columns)
+__device__ __forceinline__ double jp_entry(const double* Jp, int b, int a, int d) {
+  int off = a - b;
+  if (off > d / 2) off -= d;
+  if (off < -d / 2) off += d;
+  if (off < -2 || off > 1) return 0.0;
+  return Jp[b * 4 + off + 2];
+}
+
+// Cmat (2d x d) with B = H Q H' = Cmat' Cmat (src/diffusions.jl:77): rows (0,a): pi1 L10 delta - L00 Jp[b][a];
+// rows (1,a): pi1 L11 delta.  Written into E (ld = D).
+__global__ void build_c_kernel(StepCtx c) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = c.d;
+  if (idx >= 2LL * d * d) return;
+  const int row = (int)(idx / d), b = (int)(idx % d);
+  const int blk = row / d, a = row % d;
+  const double pi1 = c.sc->pi1;
+  double v;
+  if (blk == 0)
+    v = ((a == b) ? pi1 * c.C.Lt[1][0] : 0.0) - c.C.Lt[0][0] * jp_entry(c.Jp, b, a, d);
+  else
+    v = (a == b) ? pi1 * c.C.Lt[1][1] : 0.0;
+  c.E[(size_t)row * c.D + b] = v;
+}
+
+// Solve R(0:n,0:n)' y = z (R upper triangular): blocked forward substitution in one CTA.
+__global__ void __launch_bounds__(1024) trsv_t_kernel(const double* R, int ld, int n, const double* z, double* y,
+                                                      double* quad_out, double* logdet_out) {
+  extern __shared__ double sy[];  // [n] running right-hand side / solution
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sy[i] = z[i];
+  __syncthreads();
+  for (int b0 = 0; b0 < n; b0 += 32) {
+    const int bn = min(32, n - b0);
+    if (threadIdx.x < 32) {
+      // warp-sequential solve of the diagonal block
+      for (int k = 0; k < bn; ++k) {
+        const double rkk = R[(size_t)(b0 + k) * ld + b0 + k];
+        const double yk = (rkk != 0.0) ? sy[b0 + k] / rkk : 0.0;
+        __syncwarp();
+        if (threadIdx.x == 0) sy[b0 + k] = yk;
+        const int i = k + 1 + threadIdx.x;
+        if (i < bn) sy[b0 + i] -= R[(size_t)(b0 + k) * ld + b0 + i] * yk;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = b0 + bn + threadIdx.x; i < n; i += blockDim.x) {
+      double acc = sy[i];
+      for (int k = 0; k < bn; ++k) acc = fma(-R[(size_t)(b0 + k) * ld + i], sy[b0 + k], acc);
+      sy[i] = acc;
+    }
+    __syncthreads();
+  }
+  __shared__ double red[64];
+  double q2 = 0.0, ld2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    y[i] = sy[i];
+    q2 = fma(sy[i], sy[i], q2);
+    ld2 += log(fabs(R[(size_t)i * ld + i]));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+    ld2 += __shfl_xor_sync(0xffffffffu, ld2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = q2;
+    red[32 + (threadIdx.x >> 5)] = ld2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      a += red[w];
+      b += red[32 + w];
+    }
+    *quad_out = a;
+    *logdet_out = b;
+  }
+}
+
+// sigma from the diffusion solve: sigma^2 = quad / d (dynamic); static models predict with sigma = 1
+__global__ void set_sigma_kernel(Scalars* sc, int d, int dynamic) {
+  if (dynamic) {
+    sc->local = sc->quad / double(d);
+    sc->sigma = sqrt(sc->local);
+  } else {
+    sc->sigma = 1.0;
+  }
+}
+
+// E rows 0..d-1: the prior rows of block 0; rows d..D-1: (T A P s)' for every factor column s
+__global__ void build_e_kernel(StepCtx c) {
+  const int d = c.d, q = c.q, D = c.D;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)D * d) return;
+  const int row = (int)(idx / d), b = (int)(idx % d);
+  const double sigma = c.sc->sigma, pi1 = c.sc->pi1, pi0 = c.sc->pi0, h = c.sc->h;
+  double* e = c.E + (size_t)row * D;
+  if (row < d) {
+    const int a = row;
+    e[b] = sigma * (((a == b) ? pi1 * c.C.Lt[1][0] : 0.0) - c.C.Lt[0][0] * jp_entry(c.Jp, b, a, d));
+    e[d + b] = (a == b) ? sigma * c.C.Lt[0][0] : 0.0;
+    for (int k = 2; k <= q; ++k) e[k * d + b] = (a == b) ? sigma * c.C.Lt[k][0] : 0.0;
+    return;
+  }
+  const double* s = c.S + (size_t)(row - d) * D;
+  double Pks[QMAX + 1];
+  double Pk = 1.0 / pi0;
+  for (int k = 0; k <= q; ++k) {
+    Pks[k] = Pk;
+    Pk *= h;
+  }
+  auto w_blk = [&](int k, int j) {  // block k of A P s at dimension j
+    double acc = 0.0;
+    for (int kk = k; kk <= q; ++kk) acc = fma(inv_factorial(kk - k) * Pks[kk], s[kk * d + j], acc);
+    return acc;
+  };
+  double yv = pi1 * w_blk(1, b);
+  for (int off = -2; off <= 1; ++off) yv = fma(-c.Jp[b * 4 + off + 2], w_blk(0, wrapi(b + off, d)), yv);
+  e[b] = yv;
+  e[d + b] = w_blk(0, b);
+  for (int k = 2; k <= q; ++k) e[k * d + b] = w_blk(k, b);
+}
+
+// mean update in primed coordinates + back to natural coordinates
+__global__ void mean_update_kernel(StepCtx c) {
+  const int d = c.d, q = c.q, D = c.D;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d) return;
+  const double pi0 = c.sc->pi0, h = c.sc->h, ipi1 = c.sc->ipi1;
+  // m'+[j] = m'-[j] - sum_a R[a][j] y[a] for the x0 block (j = d + b) and blocks k >= 2
+  double acc0 = c.mp[b];
+  for (int a = 0; a < d; ++a) acc0 = fma(-c.R[(size_t)a * D + d + b], c.y[a], acc0);
+  double PIk = pi0;  // PI_k = pi0 / h^k
+  c.m[b] = acc0 * PIk;
+  // block 1 needs m0+ of the neighbours: recompute them (cheap relative to the QR)
+  double accs[4];
+  for (int off = -2; off <= 1; ++off) {
+    const int j = wrapi(b + off, d);
+    double a0 = c.mp[j];
+    for (int a = 0; a < d; ++a) a0 = fma(-c.R[(size_t)a * D + d + j], c.y[a], a0);
+    accs[off + 2] = a0 - c.mp[j];
+  }
+  double m1 = c.fu[b];
+  for (int off = -2; off <= 1; ++off) m1 = fma(c.Jp[b * 4 + off + 2], accs[off + 2], m1);
+  PIk /= h;
+  c.m[d + b] = m1 * ipi1 * PIk;
+  for (int k = 2; k <= q; ++k) {
+    PIk /= h;
+    double ak = c.mp[k * d + b];
+    for (int a = 0; a < d; ++a) ak = fma(-c.R[(size_t)a * D + k * d + b], c.y[a], ak);
+    c.m[k * d + b] = ak * PIk;
+  }
+  if (!(fabs(c.m[b]) <= 1.79769313486231570e308)) c.sc->nonfinite = 1;
+}
+
+// posterior factor columns in natural coordinates from rows d.. of R (upper triangular: entries left of
+// the diagonal are stale storage and read as zero)
+__global__ void build_s_kernel(StepCtx c) {
+  const int d = c.d, q = c.q, D = c.D;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)(D - d) * d) return;
+  const int cc = (int)(idx / d), b = (int)(idx % d);
+  const int row = d + cc;
+  const double pi0 = c.sc->pi0, h = c.sc->h, ipi1 = c.sc->ipi1;
+  const double* r = c.R + (size_t)row * D;
+  auto x0 = [&](int j) { return (d + j >= row) ? r[d + j] : 0.0; };
+  double* s = c.S + (size_t)cc * D;
+  double PIk = pi0;
+  s[b] = x0(b) * PIk;
+  double x1 = 0.0;
+  for (int off = -2; off <= 1; ++off) x1 = fma(c.Jp[b * 4 + off + 2], x0(wrapi(b + off, d)), x1);
+  PIk /= h;
+  s[d + b] = x1 * ipi1 * PIk;
+  for (int k = 2; k <= q; ++k) {
+    PIk /= h;
+    s[k * d + b] = ((k * d + b >= row) ? r[k * d + b] : 0.0) * PIk;
+  }
+}
+
+// end of step: diffusion bookkeeping (src/diffusions.jl) and log-likelihood accumulation
+__global__ void finish_step_kernel(Scalars* sc, int d, int diffusion) {
+  if (diffusion != DIFF_DYNAMIC) sc->local = sc->quad / double(d);
+  const int nacc = sc->nacc;
+  double g;
+  if (diffusion == DIFF_DYNAMIC) {
+    g = sc->local;
+  } else if (diffusion == DIFF_FIXED) {
+    g = (nacc == 0) ? sc->local : sc->global_saved + (sc->local - sc->global_saved) / double(nacc);
+  } else {
+    const double Nn = double(nacc + 1), al = 0.5, be = 0.5;
+    g = (nacc == 0) ? (be + 0.5 * sc->local) / (al + Nn * d / 2.0 + 1.0)
+                    : (be + 0.5 * ((sc->global_saved * (al + (Nn - 1.0) * d / 2.0 + 1.0) - be) * 2.0 + sc->local)) /
+                          (al + Nn * d / 2.0 + 1.0);
+  }
+  sc->global_saved = g;
+  sc->nacc = nacc + 1;
+  sc->ll_quad += sc->quad;
+  sc->ll_logdet += sc->logdet;
+  sc->ll_n += 1;
+}
+
+__global__ void init_mean_kernel(StepCtx c, const double* u0, long long n, long long tr, double* jets /* [(q+1)][d] */) {
+  // Taylor-mode jets of Lorenz-96 (same recursion as lorenz96_kernel.cuh); single CTA
+  const int d = c.d, q = c.q;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) jets[i] = u0[(long long)i * n + tr];
+  __syncthreads();
+  for (int k = 0; k < q; ++k) {
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      double acc = 0.0;
+      for (int a = 0; a <= k; ++a)
+        acc = fma(jets[a * d + wrapi(i + 1, d)] - jets[a * d + wrapi(i - 2, d)], jets[(k - a) * d + wrapi(i - 1, d)], acc);
+      acc -= jets[k * d + i];
+      if (k == 0) acc += c.F;
+      jets[(k + 1) * d + i] = acc / double(k + 1);
+    }
+    __syncthreads();
+  }
+  double fact = 1.0;
+  for (int k = 0; k <= q; ++k) {
+    if (k > 0) fact *= double(k);
+    for (int i = threadIdx.x; i < d; i += blockDim.x) c.m[k * d + i] = fact * jets[k * d + i];
+  }
+}
+
+// packed lower triangle of cal * S' S (Sigma = sum over factor columns) from the full D x D product
+__global__ void pack_cov_kernel(const double* full, int D, double cal, double* out, long long n, long long tr) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)D * D) return;
+  const int i = (int)(idx / D), j = (int)(idx % D);
+  if (j > i) return;
+  out[((long long)i * (i + 1) / 2 + j) * n + tr] = cal * full[(size_t)i * D + j];
+}
+
+__global__ void write_outputs_kernel(StepCtx c, double* mean, double* t_final, double* loglik, double* final_diff,
+                                     int* retcode, int* naccept, int* nreject, int* nf, int* njacs, int* n_saved,
+                                     long long n, long long tr, double t, int is_static) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c.D) mean[(long long)i * n + tr] = c.m[i];
+  if (i == 0) {
+    const Scalars* sc = c.sc;
+    double ll = -0.5 * (sc->ll_quad + 2.0 * sc->ll_logdet + double(sc->ll_n) * double(c.d) * 1.8378770664093453);
+    if (is_static && sc->nacc > 0) ll = nan("");
+    t_final[tr] = t;
+    loglik[tr] = ll;
+    final_diff[tr] = sc->global_saved;
+    retcode[tr] = sc->nonfinite ? RET_NONFINITE : RET_SUCCESS;
+    naccept[tr] = sc->nacc;
+    nreject[tr] = 0;
+    nf[tr] = sc->nacc;
+    njacs[tr] = sc->nacc;
+    n_saved[tr] = 0;
+  }
+}
+
+double ulp_host(double x) {
+  x = fabs(x);
+  if (x == 0.0) return 4.9406564584124654e-324;
+  return nextafter(x, INFINITY) - x;
+}
+
+}  // namespace
+
+size_t big_work_bytes(int d, int q) {
+  const size_t D = (size_t)d * (q + 1);
+  // m, mp, Jp, fu, z, y, jets | S | E | R | W | v0, T | scalars
+  return (D * 2 + (size_t)d * 4 + (size_t)d * 3 + D) * 8 + (D - d) * D * 8 + D * D * 8 * 2 + (size_t)NB * D * 8 +
+         (NB + NB * NB) * 8 + sizeof(Scalars) + 4096;
+}
+
+#define BCK(call)                      \
+  do {                                 \
+    cudaError_t e__ = (call);          \
+    if (e__ != cudaSuccess) return e__; \
+  } while (0)
+
+cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
+  const int d = A.d, q = A.q, D = d * (q + 1);
+  char* base = reinterpret_cast<char*>(A.work);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base + off;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  };
+  StepCtx c;
+  memset(&c, 0, sizeof(c));
+  c.d = d;
+  c.q = q;
+  c.D = D;
+  c.m = (double*)take((size_t)D * 8);
+  c.mp = (double*)take((size_t)D * 8);
+  c.Jp = (double*)take((size_t)d * 4 * 8);
+  c.fu = (double*)take((size_t)d * 8);
+  c.z = (double*)take((size_t)d * 8);
+  c.y = (double*)take((size_t)d * 8);
+  double* jets = (double*)take((size_t)D * 8);
+  c.S = (double*)take((size_t)(D - d) * D * 8);
+  c.E = (double*)take((size_t)D * D * 8);
+  c.R = (double*)take((size_t)D * D * 8);
+  QrWork wk;
+  wk.W = (double*)take((size_t)NB * D * 8);
+  wk.v0 = (double*)take(NB * 8);
+  wk.T = (double*)take(NB * NB * 8);
+  c.sc = (Scalars*)take(sizeof(Scalars));
+  c.diffusion = A.diffusion;
+  c.C = A.C;
+  const bool dynamic = (A.diffusion == DIFF_DYNAMIC);
+  const bool is_static = !dynamic;
+  const int TB = 256;
+  for (long long tr = 0; tr < A.n; ++tr) {
+    double Fh = 0.0;
+    BCK(cudaMemcpyAsync(&Fh, A.p + tr, 8, cudaMemcpyDeviceToHost, s));
+    BCK(cudaStreamSynchronize(s));
+    c.F = Fh;
+    BCK(cudaMemsetAsync(c.sc, 0, sizeof(Scalars), s));
+    BCK(cudaMemsetAsync(c.S, 0, (size_t)(D - d) * D * 8, s));  // Sigma_0 = 0 exactly
+    init_mean_kernel<<<1, 1024, 0, s>>>(c, A.u0, A.n, tr, jets);
+    ++*launches;
+    double t = A.K.t0;
+    long long iter = 0;
+    const int trsv_smem = d * 8;
+    BCK(cudaFuncSetAttribute(trsv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsv_smem));
+    while (t < A.K.t1) {
+      if (++iter > A.K.maxiters) break;
+      const double h = fmin(A.K.dt, A.K.t1 - t);
+      set_step_kernel<<<1, 1, 0, s>>>(c.sc, h, q);
+      measure_kernel<<<(d + TB - 1) / TB, TB, 0, s>>>(c);
+      *launches += 2;
+      if (dynamic) {
+        // sigma^2 = z' (H Q H')^-1 z / d via the QR of the 2d x d factor of H Q H'
+        build_c_kernel<<<(unsigned)((2LL * d * d + TB - 1) / TB), TB, 0, s>>>(c);
+        ++*launches;
+        BCK(blocked_qr(c.E, c.R, D, 2 * d, d, d, 0, c.sc, c.C, wk, s, launches));
+        trsv_t_kernel<<<1, 1024, trsv_smem, s>>>(c.R, D, d, c.z, c.y, &c.sc->quad, &c.sc->logdet);
+        ++*launches;
+      }
+      set_sigma_kernel<<<1, 1, 0, s>>>(c.sc, d, dynamic ? 1 : 0);
+      build_e_kernel<<<(unsigned)(((long long)D * d + TB - 1) / TB), TB, 0, s>>>(c);
+      *launches += 2;
+      BCK(blocked_qr(c.E, c.R, D, D, D, d, 1, c.sc, c.C, wk, s, launches));
+      trsv_t_kernel<<<1, 1024, trsv_smem, s>>>(c.R, D, d, c.z, c.y, &c.sc->quad, &c.sc->logdet);
+      mean_update_kernel<<<(d + TB - 1) / TB, TB, 0, s>>>(c);
+      build_s_kernel<<<(unsigned)(((long long)(D - d) * d + TB - 1) / TB), TB, 0, s>>>(c);
+      finish_step_kernel<<<1, 1, 0, s>>>(c.sc, d, A.diffusion);
+      *launches += 4;
+      const double ttmp = t + h;
+      t = (fabs(ttmp - A.K.t1) < 10.0 * ulp_host(fmax(t, A.K.t1))) ? A.K.t1 : ttmp;
+    }
+    write_outputs_kernel<<<(D + TB - 1) / TB, TB, 0, s>>>(c, A.mean, A.t_final, A.loglik, A.final_diff, A.retcode,
+                                                          A.naccept, A.nreject, A.nf, A.njacs, A.n_saved, A.n, tr, t,
+                                                          is_static ? 1 : 0);
+    ++*launches;
+    if (A.cov) {
+      // Sigma = S' S over the factor columns (rows of S): full D x D by the same DMMA kernel, then packed
+      BCK(cudaMemsetAsync(c.E, 0, (size_t)D * D * 8, s));
+      const int kchunk = 512;
+      dim3 g((D + 63) / 64, D / 32, (D - d + kchunk - 1) / kchunk);
+      atb_kernel<<<g, 128, 0, s>>>(c.S, D, c.S, D, c.E, D, D, D - d, kchunk);
+      double cal = 1.0;
+      if (is_static) {
+        Scalars hs;
+        BCK(cudaMemcpyAsync(&hs, c.sc, sizeof(hs), cudaMemcpyDeviceToHost, s));
+        BCK(cudaStreamSynchronize(s));
+        if (hs.nacc > 0) cal = hs.global_saved;
+      }
+      pack_cov_kernel<<<(unsigned)(((long long)D * D + TB - 1) / TB), TB, 0, s>>>(c.E, D, cal, A.cov, A.n, tr);
+      *launches += 2;
+    }
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace big
+}  // namespace pnde

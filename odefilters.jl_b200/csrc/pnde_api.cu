@@ -10,6 +10,7 @@
 
 #include "../../include/pnde.h"
 #include "model_ops.cuh"
+#include "big_dense_api.h"
 #include "lorenz96_kernel.cuh"
 #include "post_kernels.cuh"
 
@@ -95,7 +96,7 @@ struct pnde_handle {
   double filter_ms = 0.0, smooth_ms = 0.0;
   long long launches = 0;
   DevBuf u0, p, mean, cov, t_final, loglik, final_diff, retcode, naccept, nreject, nf, njacs, n_saved, hist, smooth,
-      sstatus, scratch_off, scratch_out;
+      sstatus, scratch_off, scratch_out, bigwork;
   std::string err;
 
   int fail(int code, const std::string& msg) {
@@ -197,11 +198,17 @@ int pnde_create(const pnde_config* cfg, pnde_handle** out) {
   const bool lorenz = (cfg->vf_kind == PNDE_VF_LORENZ96);
   const ModelOps* ops = nullptr;
   if (lorenz) {
-    if (cfg->alg != PNDE_ALG_EK0) {
-      g_create_error = "Lorenz-96: only the EK0 Kronecker path is built; the EK1 dense path (D >= 64, DMMA QR) is not";
-      return PNDE_ERR_UNSUPPORTED;
-    }
-    if (cfg->d < 4 || cfg->d > 8 * LORENZ_THREADS) {
+    if (cfg->alg == PNDE_ALG_EK1) {
+      // large-D dense path (blocked Householder QR with FP64 tensor-core updates, big_dense.cu)
+      if (cfg->d < 32 || cfg->d % 32 != 0 || cfg->d * (cfg->order + 1) > 6144) {
+        g_create_error = "Lorenz-96 EK1 (dense, D >= 64): d must be a multiple of 32 with d (q+1) <= 6144";
+        return PNDE_ERR_UNSUPPORTED;
+      }
+      if (cfg->adaptive) {
+        g_create_error = "Lorenz-96 EK1 (dense): only fixed steps are built";
+        return PNDE_ERR_UNSUPPORTED;
+      }
+    } else if (cfg->d < 4 || cfg->d > 8 * LORENZ_THREADS) {
       g_create_error = "Lorenz-96: d must be in 4..2048";
       return PNDE_ERR_ARG;
     }
@@ -252,6 +259,7 @@ int pnde_create(const pnde_config* cfg, pnde_handle** out) {
     h->np = 1;
     h->nd = 1;
     h->ncov = (cfg->order + 1) * (cfg->order + 2) / 2;  // Kronecker factor Ctilde
+    if (cfg->alg == PNDE_ALG_EK1) h->ncov = h->D * (h->D + 1) / 2;
   } else {
     h->d = ops->d;
     h->D = ops->D;
@@ -289,7 +297,8 @@ int pnde_destroy(pnde_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->u0,      &h->p,      &h->mean,  &h->cov,     &h->t_final, &h->loglik,
                     &h->final_diff, &h->retcode, &h->naccept, &h->nreject, &h->nf,      &h->njacs,
-                    &h->n_saved, &h->hist,   &h->smooth, &h->sstatus, &h->scratch_off, &h->scratch_out};
+                    &h->n_saved, &h->hist,   &h->smooth, &h->sstatus, &h->scratch_off, &h->scratch_out,
+                    &h->bigwork};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -401,7 +410,44 @@ int pnde_run(pnde_handle* h) {
   fp.K.dtmax = c.dtmax;
   fp.K.maxiters = c.maxiters;
   CK(cudaEventRecord(h->ev[0], h->stream), "event record");
-  if (h->lorenz) {
+  if (h->lorenz && c.alg == PNDE_ALG_EK1) {
+    cudaError_t e = h->bigwork.ensure(big::big_work_bytes(h->d, c.order));
+    if (e != cudaSuccess) {
+      h->err = std::string("work-space allocation for the dense large-D path: ") + cudaGetErrorString(e);
+      cudaGetLastError();
+      return PNDE_ERR_ALLOC;
+    }
+    big::BigRunArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.n = fp.n;
+    ba.d = h->d;
+    ba.q = c.order;
+    ba.diffusion = c.diffusion;
+    ba.u0 = fp.u0;
+    ba.p = fp.p;
+    ba.mean = fp.mean;
+    ba.cov = fp.cov;
+    ba.t_final = fp.t_final;
+    ba.loglik = fp.loglik;
+    ba.final_diff = fp.final_diff;
+    ba.retcode = fp.retcode;
+    ba.naccept = fp.naccept;
+    ba.nreject = fp.nreject;
+    ba.nf = fp.nf;
+    ba.njacs = fp.njacs;
+    ba.n_saved = fp.n_saved;
+    ba.work = h->bigwork.p;
+    ba.C = fp.C;
+    ba.K = fp.K;
+    long long nl = 0;
+    CK(big::big_run(ba, h->stream, &nl), "dense large-D EK1 run");
+    CK(cudaEventRecord(h->ev[1], h->stream), "event record");
+    h->launches = nl;
+    h->ran = true;
+    h->smoothed = false;
+    h->smooth_ms = 0.0;
+    return PNDE_OK;
+  } else if (h->lorenz) {
     LorenzParams lp;
     memset(&lp, 0, sizeof(lp));
     lp.n = fp.n;
