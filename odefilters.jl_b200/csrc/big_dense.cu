@@ -111,19 +111,25 @@ __global__ void build_c_kernel(StepCtx c) {
 __global__ void __launch_bounds__(1024) trsv_t_kernel(const double* R, int ld, int n, const double* z, double* y,
                                                       double* quad_out, double* logdet_out) {
   extern __shared__ double sy[];  // [n] running right-hand side / solution
+  __shared__ double sd[32][33];   // diagonal block
   for (int i = threadIdx.x; i < n; i += blockDim.x) sy[i] = z[i];
   __syncthreads();
   for (int b0 = 0; b0 < n; b0 += 32) {
     const int bn = min(32, n - b0);
+    {
+      const int r = threadIdx.x / 32, cc = threadIdx.x % 32;
+      if (r < bn && cc < bn) sd[r][cc] = R[(size_t)(b0 + r) * ld + b0 + cc];
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
-      // warp-sequential solve of the diagonal block
+      // warp-sequential solve of the diagonal block (from shared memory)
       for (int k = 0; k < bn; ++k) {
-        const double rkk = R[(size_t)(b0 + k) * ld + b0 + k];
+        const double rkk = sd[k][k];
         const double yk = (rkk != 0.0) ? sy[b0 + k] / rkk : 0.0;
         __syncwarp();
         if (threadIdx.x == 0) sy[b0 + k] = yk;
         const int i = k + 1 + threadIdx.x;
-        if (i < bn) sy[b0 + i] -= R[(size_t)(b0 + k) * ld + b0 + i] * yk;
+        if (i < bn) sy[b0 + i] -= sd[k][i] * yk;
         __syncwarp();
       }
     }
@@ -206,34 +212,32 @@ __global__ void build_e_kernel(StepCtx c) {
   for (int k = 2; k <= q; ++k) e[k * d + b] = w_blk(k, b);
 }
 
-// mean update in primed coordinates + back to natural coordinates
-__global__ void mean_update_kernel(StepCtx c) {
-  const int d = c.d, q = c.q, D = c.D;
+// delta[j] = sum_a R[a][j] y[a] for j in [d, D): rows split over blockIdx.y, FP64 atomics
+__global__ void gain_gemv_kernel(StepCtx c, double* delta) {
+  const int d = c.d, D = c.D;
+  const int j = d + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  const int a0 = blockIdx.y * 64, a1 = min(d, a0 + 64);
+  double acc = 0.0;
+  for (int a = a0; a < a1; ++a) acc = fma(c.R[(size_t)a * D + j], c.y[a], acc);
+  atomicAdd(&delta[j], acc);
+}
+
+// mean update in primed coordinates + back to natural coordinates (delta from gain_gemv_kernel)
+__global__ void mean_update2_kernel(StepCtx c, const double* delta) {
+  const int d = c.d, q = c.q;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= d) return;
   const double pi0 = c.sc->pi0, h = c.sc->h, ipi1 = c.sc->ipi1;
-  // m'+[j] = m'-[j] - sum_a R[a][j] y[a] for the x0 block (j = d + b) and blocks k >= 2
-  double acc0 = c.mp[b];
-  for (int a = 0; a < d; ++a) acc0 = fma(-c.R[(size_t)a * D + d + b], c.y[a], acc0);
-  double PIk = pi0;  // PI_k = pi0 / h^k
-  c.m[b] = acc0 * PIk;
-  // block 1 needs m0+ of the neighbours: recompute them (cheap relative to the QR)
-  double accs[4];
-  for (int off = -2; off <= 1; ++off) {
-    const int j = wrapi(b + off, d);
-    double a0 = c.mp[j];
-    for (int a = 0; a < d; ++a) a0 = fma(-c.R[(size_t)a * D + d + j], c.y[a], a0);
-    accs[off + 2] = a0 - c.mp[j];
-  }
+  double PIk = pi0;
+  c.m[b] = (c.mp[b] - delta[d + b]) * PIk;
   double m1 = c.fu[b];
-  for (int off = -2; off <= 1; ++off) m1 = fma(c.Jp[b * 4 + off + 2], accs[off + 2], m1);
+  for (int off = -2; off <= 1; ++off) m1 = fma(c.Jp[b * 4 + off + 2], -delta[d + wrapi(b + off, d)], m1);
   PIk /= h;
   c.m[d + b] = m1 * ipi1 * PIk;
   for (int k = 2; k <= q; ++k) {
     PIk /= h;
-    double ak = c.mp[k * d + b];
-    for (int a = 0; a < d; ++a) ak = fma(-c.R[(size_t)a * D + k * d + b], c.y[a], ak);
-    c.m[k * d + b] = ak * PIk;
+    c.m[k * d + b] = (c.mp[k * d + b] - delta[k * d + b]) * PIk;
   }
   if (!(fabs(c.m[b]) <= 1.79769313486231570e308)) c.sc->nonfinite = 1;
 }
@@ -424,7 +428,10 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
       *launches += 2;
       BCK(blocked_qr(c.E, c.R, D, D, D, d, 1, c.sc, c.C, wk, s, launches));
       trsv_t_kernel<<<1, 1024, trsv_smem, s>>>(c.R, D, d, c.z, c.y, &c.sc->quad, &c.sc->logdet);
-      mean_update_kernel<<<(d + TB - 1) / TB, TB, 0, s>>>(c);
+      BCK(cudaMemsetAsync(jets, 0, (size_t)D * 8, s));  // jets is free after the initialisation: reuse as delta
+      gain_gemv_kernel<<<dim3((D - d + TB - 1) / TB, (d + 63) / 64), TB, 0, s>>>(c, jets);
+      mean_update2_kernel<<<(d + TB - 1) / TB, TB, 0, s>>>(c, jets);
+      ++*launches;
       build_s_kernel<<<(unsigned)(((long long)(D - d) * d + TB - 1) / TB), TB, 0, s>>>(c);
       finish_step_kernel<<<1, 1, 0, s>>>(c.sc, d, A.diffusion);
       *launches += 4;

@@ -30,7 +30,7 @@ namespace cg = cooperative_groups;
 
 constexpr int NB = 32;        // panel width
 constexpr int NCLUSTER = 8;   // CTAs per panel cluster
-constexpr int PANEL_THREADS = 256;
+constexpr int PANEL_THREADS = 1024;
 
 struct Geometry {
   int d, q, D;
@@ -88,9 +88,8 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
   const int row0 = rank * rows_per;
   constexpr int LDS = NB + 1;
   double* slab = smem;                         // [rows_per][LDS]
-  double* part = slab + (size_t)rows_per * LDS;  // [8][NB] partial sums over row stripes
-  double* gl = part + 8 * NB;                  // [2][NB] this CTA's column sums (double buffered)
-  double* gram = gl + 2 * NB;                  // [NB][NB] Gram of Vb (local, then total in rank 0)
+  double* part = slab + (size_t)rows_per * LDS;      // [NSTRIPE][NB] partial sums + [2][NB] column sums
+  double* gram = part + (PANEL_THREADS / NB + 2) * NB;  // [NB][NB] Gram of Vb (local, then total in rank 0)
   __shared__ double s_v0[NB], s_beta[NB], s_T[NB][NB];
   const int tid = threadIdx.x;
   const double sigma = (a.mode == 0) ? 1.0 : a.sc->sigma;
@@ -101,54 +100,61 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
     slab[r * LDS + k] = a.E[(size_t)(row0 + r) * a.ld + a.c0 + k];
   }
   __syncthreads();
-  const int col = tid % NB, stripe = tid / NB;  // 8 stripes of rows
+  // Thread (col, stripe): lanes of a warp are the NB panel columns, warp w owns row stripe w.  Per column:
+  // partial inner products -> block reduction -> one value per column published to the cluster ->
+  // warp 0 gathers the 8 ranks through DSMEM, computes the reflector scalars and broadcasts s_j.
+  const int col = tid % NB, stripe = tid / NB;
+  constexpr int NSTRIPE = PANEL_THREADS / NB;
+  double* gl = part + NSTRIPE * NB;  // [2][NB]
+  __shared__ double s_coef[NB];
   for (int k = 0; k < NB; ++k) {
-    // g[j] = sum_r slab[r][k] * slab[r][j], j >= k  (j == k: squared norm)
     double acc = 0.0;
     if (col >= k)
-      for (int r = stripe; r < rows_per; r += PANEL_THREADS / NB) acc = fma(slab[r * LDS + k], slab[r * LDS + col], acc);
+      for (int r = stripe; r < rows_per; r += NSTRIPE) acc = fma(slab[r * LDS + k], slab[r * LDS + col], acc);
     part[stripe * NB + col] = acc;
     __syncthreads();
     double* glk = gl + (k & 1) * NB;
     if (tid < NB) {
-      double s = 0.0;
+      double sm_ = 0.0;
 #pragma unroll
-      for (int st = 0; st < PANEL_THREADS / NB; ++st) s += part[st * NB + tid];
-      glk[tid] = s;
+      for (int st = 0; st < NSTRIPE; ++st) sm_ += part[st * NB + tid];
+      glk[tid] = sm_;
     }
     cluster.sync();
-    double g = 0.0;
     if (tid < NB) {
+      double g = 0.0;
 #pragma unroll
       for (int rk = 0; rk < NCLUSTER; ++rk) g += cluster.map_shared_rank(glk, rk)[tid];
+      const double gk = __shfl_sync(0xffffffffu, g, k);
+      const int c = a.c0 + k;
+      const double pv = sigma * prior_pivot(c, c, a.d, pi1, a.C, a.mode);
+      const double n2 = fma(pv, pv, gk);
+      const bool nz = n2 > 0.0;
+      const double rn = nz ? fast_rsqrt(n2) : 0.0;
+      const double nrm = n2 * rn;
+      const double v0 = pv + nrm;
+      const double beta = nz ? fast_rcp(fma(pv, nrm, n2)) : 0.0;
+      double sj = 0.0;
+      if (tid > k) {
+        const double prj = sigma * prior_pivot(c, a.c0 + tid, a.d, pi1, a.C, a.mode);
+        sj = beta * fma(v0, prj, g);
+        if (rank == 0) a.R[(size_t)c * a.ld + a.c0 + tid] = fma(-sj, v0, prj);
+      }
+      s_coef[tid] = sj;
+      if (tid == 0) {
+        s_v0[k] = v0;
+        s_beta[k] = beta;
+        if (rank == 0) a.R[(size_t)c * a.ld + c] = -nrm;
+      }
     }
-    // broadcast g[k] and g[col] inside the CTA through shared memory
-    __shared__ double s_g[NB];
-    if (tid < NB) s_g[tid] = g;
     __syncthreads();
-    const int c = a.c0 + k;
-    const double pv = sigma * prior_pivot(c, c, a.d, pi1, a.C, a.mode);
-    const double n2 = fma(pv, pv, s_g[k]);
-    const bool nz = n2 > 0.0;
-    const double rn = nz ? fast_rsqrt(n2) : 0.0;
-    const double nrm = n2 * rn;
-    const double v0 = pv + nrm;
-    const double beta = nz ? fast_rcp(fma(pv, nrm, n2)) : 0.0;
-    double sj = 0.0;
     if (col > k) {
-      const double prj = sigma * prior_pivot(c, a.c0 + col, a.d, pi1, a.C, a.mode);
-      const double w = fma(v0, prj, s_g[col]);
-      sj = beta * w;
-      if (rank == 0 && stripe == 0) a.R[(size_t)c * a.ld + a.c0 + col] = fma(-sj, v0, prj);
-      for (int r = stripe; r < rows_per; r += PANEL_THREADS / NB) slab[r * LDS + col] = fma(-sj, slab[r * LDS + k], slab[r * LDS + col]);
+      const double sj = s_coef[col];
+      for (int r = stripe; r < rows_per; r += NSTRIPE) slab[r * LDS + col] = fma(-sj, slab[r * LDS + k], slab[r * LDS + col]);
     }
-    if (tid == 0) {
-      s_v0[k] = v0;
-      s_beta[k] = beta;
-      if (rank == 0) a.R[(size_t)c * a.ld + c] = -nrm;
-    }
-    __syncthreads();
+    __syncwarp();
   }
+  __syncthreads();
   // write Vb back, local Gram of Vb
   for (int idx = tid; idx < rows_per * NB; idx += PANEL_THREADS) {
     const int r = idx / NB, k = idx % NB;
@@ -342,7 +348,7 @@ struct QrWork {
 inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols, int d, int mode, const Scalars* sc,
                               const IwpConsts& C, const QrWork& wk, cudaStream_t s, long long* launches) {
   const int rows_per = nrows / NCLUSTER;
-  const size_t smem = ((size_t)rows_per * (NB + 1) + 8 * NB + 2 * NB + NB * NB) * sizeof(double);
+  const size_t smem = ((size_t)rows_per * (NB + 1) + (PANEL_THREADS / NB + 2) * NB + NB * NB) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   for (int c0 = 0; c0 < ncols; c0 += NB) {
@@ -364,7 +370,7 @@ inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols
     if (ntrail <= 0) break;
     e = cudaMemsetAsync(wk.W, 0, (size_t)NB * ld * sizeof(double), s);
     if (e != cudaSuccess) return e;
-    const int kchunk = 512;
+    const int kchunk = 128;
     dim3 g1((ntrail + 63) / 64, 1, (nrows + kchunk - 1) / kchunk);
     atb_kernel<<<g1, 128, 0, s>>>(E + c0, ld, E + c0 + NB, ld, wk.W, ld, ntrail, nrows, kchunk);
     W2Args wa;
