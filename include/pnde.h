@@ -66,6 +66,7 @@ extern "C" {
 #define PNDE_VF_LORENZ96 6       /* d given in the config (4..2048), p = (F); EK0 only: one CTA per trajectory,
                                     Kronecker-factored covariance, final state only (BASELINE config 4) */
 #define PNDE_VF_LINEAR1 7        /* du = p u, d = 1 (test/convergence.jl:10) */
+#define PNDE_VF_CUSTOM 100       /* user source, compiled at run time: pnde_create_custom */
 
 /* what is written to the device-side history */
 #define PNDE_SAVE_FINAL 0  /* final state only */
@@ -115,6 +116,19 @@ int pnde_default_config(pnde_config* cfg, int32_t alg, int32_t order, int32_t vf
 /* alg_cache (src/caches.jl:42-114): validates the configuration, builds the IWP constants
  * (src/priors.jl:7-59), binds the device. */
 int pnde_create(const pnde_config* cfg, pnde_handle** out);
+/* Any autonomous user ODE (d <= 8): the vector field and its Jacobian are given as CUDA C++ statement lists and
+ * compiled at run time (NVRTC) into the same kernels as the catalogue.  f_body assigns du[i] from u[] and p[]
+ * and must be generic in the scalar type T (it is also evaluated on truncated Taylor series for the exact
+ * initial state, src/state_initialization.jl:15-42): + - * / exp log sin cos sqrt are available.  jac_body
+ * assigns J[i][j] = d f_i / d u_j in doubles (what src/jacobian.jl:6-22 obtains from ModelingToolkit); it may
+ * be NULL for EK0.  cfg->vf_kind must be PNDE_VF_CUSTOM.  Example (Lotka-Volterra):
+ *   f_body   "du[0] = p[0]*u[0] - p[1]*u[0]*u[1]; du[1] = -p[2]*u[1] + p[3]*u[0]*u[1];"
+ *   jac_body "J[0][0] = p[0]-p[1]*u[1]; J[0][1] = -p[1]*u[0]; J[1][0] = p[3]*u[1]; J[1][1] = -p[2]+p[3]*u[0];" */
+int pnde_create_custom(const pnde_config* cfg, int32_t d, int32_t n_params, const char* f_body,
+                       const char* jac_body, pnde_handle** out);
+/* Compile-only validation of such a source (needs libnvrtc but no GPU); the compiler log goes to `log`. */
+int pnde_check_custom(int32_t alg, int32_t order, int32_t diffusion, int32_t d, int32_t n_params,
+                      const char* f_body, const char* jac_body, char* log, int64_t log_len);
 int pnde_destroy(pnde_handle* h);
 const char* pnde_last_error(const pnde_handle* h); /* h may be NULL: last create error */
 

@@ -10,6 +10,7 @@ Names follow the reference: ``EK0``/``EK1`` (src/algorithms.jl:23-51), ``solve``
 ``EnsembleProblem``, ``SRMatrix`` (src/squarerootmatrix.jl), ``Gaussian``.
 """
 from .api import (  # noqa: F401
+    CustomVectorField,
     EK0,
     EK1,
     EnsembleB200,
@@ -25,5 +26,5 @@ from .api import (  # noqa: F401
 )
 from . import _lib  # noqa: F401
 
-__all__ = ["EK0", "EK1", "EnsembleB200", "EnsembleProblem", "EnsembleSolution", "FilterSolver", "Gaussian",
+__all__ = ["CustomVectorField", "EK0", "EK1", "EnsembleB200", "EnsembleProblem", "EnsembleSolution", "FilterSolver", "Gaussian",
            "ODEProblem", "ProbODESolution", "SRMatrix", "shard_range", "solve"]

@@ -12,7 +12,7 @@ ABI_VERSION = 1
 ALG_EK0, ALG_EK1 = 0, 1
 DIFFUSIONS = {"dynamic": 0, "fixed": 1, "fixedMAP": 2, "dynamicMV": 3, "fixedMV": 4}
 VF_KINDS = {"fhn_readme": 0, "fhn_lib": 1, "lotka_volterra": 2, "vanderpol": 3, "linear2": 4, "logistic": 5,
-            "lorenz96": 6, "linear1": 7}
+            "lorenz96": 6, "linear1": 7, "custom": 100}
 VF_DIMS = {"fhn_readme": (2, 3), "fhn_lib": (2, 4), "lotka_volterra": (2, 4), "vanderpol": (2, 1), "linear2": (2, 2),
            "logistic": (1, 1), "linear1": (1, 1)}
 SAVE_FINAL, SAVE_EVERY, SAVE_STRIDE = 0, 1, 2
@@ -33,7 +33,7 @@ class PndeConfig(C.Structure):
 
 
 EXPORTS = [
-    "pnde_default_config", "pnde_create", "pnde_destroy", "pnde_last_error", "pnde_state_dim", "pnde_n_params",
+    "pnde_default_config", "pnde_create", "pnde_create_custom", "pnde_check_custom", "pnde_destroy", "pnde_last_error", "pnde_state_dim", "pnde_n_params",
     "pnde_record_len", "pnde_cov_len", "pnde_solve_ensemble", "pnde_upload", "pnde_run", "pnde_synchronize", "pnde_last_run_ms",
     "pnde_last_launch_count", "pnde_smooth", "pnde_query_sizes", "pnde_get_counts", "pnde_get_final",
     "pnde_get_history", "pnde_get_marginals", "pnde_sample", "pnde_eval_dense", "pnde_measure_fp64_peak",
@@ -56,6 +56,10 @@ def load():
     vp, dp, ip64, ip32 = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int32)
     lib.pnde_default_config.argtypes = [C.POINTER(PndeConfig), C.c_int32, C.c_int32, C.c_int32]
     lib.pnde_create.argtypes = [C.POINTER(PndeConfig), C.POINTER(vp)]
+    lib.pnde_create_custom.argtypes = [C.POINTER(PndeConfig), C.c_int32, C.c_int32, C.c_char_p, C.c_char_p,
+                                       C.POINTER(vp)]
+    lib.pnde_check_custom.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p,
+                                      C.c_char_p, C.c_int64]
     lib.pnde_destroy.argtypes = [vp]
     lib.pnde_last_error.argtypes = [vp]
     lib.pnde_last_error.restype = C.c_char_p

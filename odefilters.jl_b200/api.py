@@ -44,16 +44,46 @@ def EK1(order: int = 3, diffusionmodel: str = "dynamic", smooth: bool = True, pr
     return _EK(order, diffusionmodel, smooth, prior, L.ALG_EK1)
 
 
+@dataclass(frozen=True)
+class CustomVectorField:
+    """A user ODE for the run-time compiled path (pnde_create_custom): CUDA C++ statement lists for f and its
+    Jacobian, the role ModelingToolkit-generated code plays on the Julia side (src/jacobian.jl:6-22).
+
+        lv = CustomVectorField(d=2, n_params=4,
+                               f="du[0] = p[0]*u[0] - p[1]*u[0]*u[1]; du[1] = -p[2]*u[1] + p[3]*u[0]*u[1];",
+                               jac="J[0][0] = p[0]-p[1]*u[1]; J[0][1] = -p[1]*u[0]; J[1][0] = p[3]*u[1]; J[1][1] = -p[2]+p[3]*u[0];")
+    """
+
+    d: int
+    n_params: int
+    f: str
+    jac: Optional[str] = None
+
+    def check(self, alg: "_EK") -> str:
+        """Compile-only validation (no GPU needed); returns the compiler log, raises on errors."""
+        lib = L.load()
+        log = C.create_string_buffer(1 << 16)
+        rc = lib.pnde_check_custom(alg.kind, alg.order, L.DIFFUSIONS[alg.diffusionmodel], self.d, self.n_params,
+                                   self.f.encode(), self.jac.encode() if self.jac else None, log, len(log))
+        if rc != 0:
+            raise ValueError(log.value.decode())
+        return log.value.decode()
+
+
 @dataclass
 class ODEProblem:
-    """ODEProblem(f, u0, tspan, p) with ``f`` a name from the built-in catalogue (include/pnde.h)."""
+    """ODEProblem(f, u0, tspan, p) with ``f`` a name from the built-in catalogue (include/pnde.h) or a
+    CustomVectorField."""
 
-    f: str
+    f: object
     u0: Sequence[float]
     tspan: Sequence[float]
     p: Sequence[float] = ()
 
     def __post_init__(self):
+        self.custom = self.f if isinstance(self.f, CustomVectorField) else None
+        if self.custom is not None:
+            self.f = "custom"
         if self.f not in L.VF_KINDS:
             raise ValueError(f"unknown vector field {self.f!r}; catalogue: {sorted(L.VF_KINDS)}")
         u0 = np.asarray(self.u0, dtype=np.float64)
@@ -62,9 +92,13 @@ class ODEProblem:
             raise ValueError("Problems which are not scalar- or vector-valued (e.g. u0 is a scalar or a matrix) "
                              "are currently not supported")
         d, npar = L.VF_DIMS.get(self.f, (u0.shape[0], 1))  # lorenz96: d = len(u0), p = (F,)
+        if self.custom is not None:
+            d, npar = self.custom.d, self.custom.n_params
         if u0.shape[0] != d:
             raise ValueError(f"{self.f} has dimension {d}")
         p = np.atleast_1d(np.asarray(self.p, dtype=np.float64))
+        if npar == 0 and p.size == 0:
+            p = np.zeros(0)
         if p.shape[0] != npar:
             raise ValueError(f"{self.f} takes {npar} parameters")
         self.u0, self.p = u0, p
@@ -262,10 +296,17 @@ class FilterSolver:
                 setattr(cfg, name, float(val))
         self.cfg = cfg
         self._h = C.c_void_p()
-        rc = self.lib.pnde_create(C.byref(cfg), C.byref(self._h))
+        if prob.custom is not None:
+            cv = prob.custom
+            rc = self.lib.pnde_create_custom(C.byref(cfg), cv.d, cv.n_params, cv.f.encode(),
+                                             cv.jac.encode() if cv.jac else None, C.byref(self._h))
+        else:
+            rc = self.lib.pnde_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             raise RuntimeError(f"pnde_create failed ({rc}): {self.lib.pnde_last_error(None).decode()}")
         self.d, self.npar = L.VF_DIMS.get(prob.f, (len(prob.u0), 1))
+        if prob.custom is not None:
+            self.d, self.npar = prob.custom.d, prob.custom.n_params
         self.D = int(self.lib.pnde_state_dim(self._h))
         self.ncov = int(self.lib.pnde_cov_len(self._h))
         # Lorenz-96 EK0: covariance returned as the Kronecker factor Ctilde (EK1 returns the full matrix)

@@ -18,7 +18,9 @@
 // posterior factor.  sig Q_L' is already triangular in these coordinates up to a dc x dc block, so
 // every Householder vector has length <= D+1.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 
 namespace pnde {
 

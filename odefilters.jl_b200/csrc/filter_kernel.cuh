@@ -10,8 +10,12 @@
 //   savevalues!      src/integrator_utils.jl:33-48
 //   controller       src/alg_utils.jl:13-24 + OrdinaryDiffEq (external)
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
+#ifndef __CUDACC_RTC__
 #include <math.h>
+#endif
 
 #include "cov_engine.cuh"
 #include "vector_fields.cuh"

@@ -1,7 +1,9 @@
 // Per-model dispatch table: every (vector field, order, algorithm) combination is a separate
 // template instantiation; the C-ABI layer (pnde_api.cu) looks its launchers up at pnde_create time.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 
 #include "filter_kernel.cuh"
 
@@ -43,14 +45,16 @@ struct SmoothParams {
 struct SampleParams;
 struct DenseParams;
 
+#ifndef __CUDACC_RTC__
+// `self` lets run-time compiled models (rtc_model.cu) carry their CUfunction handles
 struct ModelOps {
   int d, q, D, nd, rec, srec, np;
   bool ek1;
-  cudaError_t (*launch_filter)(const FilterParams&, bool adaptive, cudaStream_t);
-  cudaError_t (*launch_convert)(const ConvertParams&, cudaStream_t);
-  cudaError_t (*launch_smooth)(const SmoothParams&, cudaStream_t);
-  cudaError_t (*launch_sample)(const SampleParams&, cudaStream_t);
-  cudaError_t (*launch_dense)(const DenseParams&, cudaStream_t);
+  cudaError_t (*launch_filter)(const ModelOps* self, const FilterParams&, bool adaptive, cudaStream_t);
+  cudaError_t (*launch_convert)(const ModelOps* self, const ConvertParams&, cudaStream_t);
+  cudaError_t (*launch_smooth)(const ModelOps* self, const SmoothParams&, cudaStream_t);
+  cudaError_t (*launch_sample)(const ModelOps* self, const SampleParams&, cudaStream_t);
+  cudaError_t (*launch_dense)(const ModelOps* self, const DenseParams&, cudaStream_t);
 };
 
 // defined in inst_*.cu
@@ -61,5 +65,6 @@ const ModelOps* ops_vanderpol(int alg, int q, bool mvdyn);
 const ModelOps* ops_linear2(int alg, int q, bool mvdyn);
 const ModelOps* ops_logistic(int alg, int q, bool mvdyn);
 const ModelOps* ops_linear1(int alg, int q, bool mvdyn);
+#endif  // !__CUDACC_RTC__
 
 }  // namespace pnde

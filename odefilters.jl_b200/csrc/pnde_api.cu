@@ -13,6 +13,7 @@
 #include "big_dense_api.h"
 #include "lorenz96_kernel.cuh"
 #include "post_kernels.cuh"
+#include "rtc_model.h"
 
 using namespace pnde;
 
@@ -84,6 +85,7 @@ const ModelOps* find_ops(int vf, int alg, int q, bool mvdyn) {
 struct pnde_handle {
   pnde_config cfg;
   const ModelOps* ops = nullptr;  // nullptr for the CTA-per-trajectory Lorenz-96 path
+  bool owns_ops = false;           // run-time compiled model (pnde_create_custom)
   bool lorenz = false;
   int d = 0, D = 0, np = 0, nd = 1, ncov = 0;  // dimensions (from ops, or from cfg for Lorenz-96)
   int device = 0;
@@ -151,7 +153,13 @@ int pnde_default_config(pnde_config* cfg, int32_t alg, int32_t order, int32_t vf
   return PNDE_OK;
 }
 
-int pnde_create(const pnde_config* cfg, pnde_handle** out) {
+struct CustomVf {
+  int d, np;
+  const char* f_body;
+  const char* jac_body;
+};
+
+static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf* custom) {
   if (!cfg || !out) {
     g_create_error = "null argument";
     return PNDE_ERR_ARG;
@@ -220,6 +228,11 @@ int pnde_create(const pnde_config* cfg, pnde_handle** out) {
       g_create_error = "Lorenz-96: only save_mode = PNDE_SAVE_FINAL (no smoothing) is built for the large-d path";
       return PNDE_ERR_UNSUPPORTED;
     }
+  } else if (custom) {
+    if (custom->d < 1 || custom->d > 8 || custom->np < 0 || custom->np > 64) {
+      g_create_error = "custom vector field: d must be in 1..8 and n_params in 0..64";
+      return PNDE_ERR_ARG;
+    }
   } else {
     ops = find_ops(cfg->vf_kind, cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV);
     if (!ops) {
@@ -249,9 +262,25 @@ int pnde_create(const pnde_config* cfg, pnde_handle** out) {
     g_create_error = "device ordinal out of range";
     return PNDE_ERR_ARG;
   }
+  bool owns = false;
+  if (custom) {
+    if (cudaSetDevice(dev) != cudaSuccess) {
+      g_create_error = "cudaSetDevice failed";
+      return PNDE_ERR_CUDA;
+    }
+    std::string rerr;
+    ops = rtc_build(cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV, custom->d, custom->np, custom->f_body,
+                    custom->jac_body, rerr);
+    if (!ops) {
+      g_create_error = rerr;
+      return PNDE_ERR_ARG;
+    }
+    owns = true;
+  }
   pnde_handle* h = new pnde_handle();
   h->cfg = *cfg;
   h->ops = ops;
+  h->owns_ops = owns;
   h->lorenz = lorenz;
   if (lorenz) {
     h->d = cfg->d;
@@ -291,6 +320,29 @@ int pnde_create(const pnde_config* cfg, pnde_handle** out) {
   return PNDE_OK;
 }
 
+int pnde_create(const pnde_config* cfg, pnde_handle** out) { return create_impl(cfg, out, nullptr); }
+
+int pnde_create_custom(const pnde_config* cfg, int32_t d, int32_t n_params, const char* f_body, const char* jac_body,
+                       pnde_handle** out) {
+  CustomVf c = {d, n_params, f_body, jac_body};
+  if (cfg && cfg->vf_kind != PNDE_VF_CUSTOM) {
+    g_create_error = "pnde_create_custom: cfg.vf_kind must be PNDE_VF_CUSTOM";
+    return PNDE_ERR_ARG;
+  }
+  return create_impl(cfg, out, &c);
+}
+
+int pnde_check_custom(int32_t alg, int32_t order, int32_t diffusion, int32_t d, int32_t n_params, const char* f_body,
+                      const char* jac_body, char* log, int64_t log_len) {
+  std::string err;
+  const bool ok = rtc_check(alg, order, diffusion == PNDE_DIFF_DYNAMIC_MV, d, n_params, f_body, jac_body, err);
+  if (log && log_len > 0) {
+    strncpy(log, err.c_str(), (size_t)log_len - 1);
+    log[log_len - 1] = 0;
+  }
+  return ok ? PNDE_OK : PNDE_ERR_ARG;
+}
+
 int pnde_destroy(pnde_handle* h) {
   if (!h) return PNDE_OK;
   cudaSetDevice(h->device);
@@ -303,6 +355,7 @@ int pnde_destroy(pnde_handle* h) {
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->owns_ops) rtc_destroy(h->ops);
   delete h;
   return PNDE_OK;
 }
@@ -475,7 +528,7 @@ int pnde_run(pnde_handle* h) {
     CK(cudaMemsetAsync(h->njacs.p, 0, (size_t)h->n * 4, h->stream), "memset njacs");
     CK(launch_lorenz(c.order, lp, h->stream), "lorenz96 kernel launch");
   } else {
-    CK(h->ops->launch_filter(fp, c.adaptive != 0, h->stream), "filter kernel launch");
+    CK(h->ops->launch_filter(h->ops, fp, c.adaptive != 0, h->stream), "filter kernel launch");
   }
   CK(cudaEventRecord(h->ev[1], h->stream), "event record");
   h->launches = 1;
@@ -513,7 +566,7 @@ int pnde_smooth(pnde_handle* h) {
   sp.status = h->sstatus.as<int>();
   sp.C = h->C;
   CK(cudaEventRecord(h->ev[2], h->stream), "event record");
-  CK(o->launch_smooth(sp, h->stream), "smoother kernel launch");
+  CK(o->launch_smooth(o, sp, h->stream), "smoother kernel launch");
   CK(cudaEventRecord(h->ev[3], h->stream), "event record");
   h->launches += 1;
   h->smoothed = true;
@@ -670,7 +723,7 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   cp.cov = dcov;
   cp.diffusion = ddif;
   cp.nd_out = nd_out;
-  CK(o->launch_convert(cp, h->stream), "convert kernel launch");
+  CK(o->launch_convert(o, cp, h->stream), "convert kernel launch");
   if (t) CK(cudaMemcpyAsync(t, dt_, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
   if (mean) CK(cudaMemcpyAsync(mean, dmean, nm * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
   if (cov) CK(cudaMemcpyAsync(cov, dcov, nc * 8, cudaMemcpyDeviceToHost, h->stream), "D2H cov");
@@ -728,7 +781,7 @@ int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint6
   cp.marginals = 1;
   cp.t = dt_;
   cp.nd_out = 1;
-  CK(o->launch_convert(cp, h->stream), "convert kernel launch");
+  CK(o->launch_convert(o, cp, h->stream), "convert kernel launch");
   SampleParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.n = h->n;
@@ -745,7 +798,7 @@ int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint6
   sp.seed = seed;
   sp.out = dout;
   sp.C = h->C;
-  CK(o->launch_sample(sp, h->stream), "sample kernel launch");
+  CK(o->launch_sample(o, sp, h->stream), "sample kernel launch");
   if (t) CK(cudaMemcpyAsync(t, dt_, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
   if (samples) CK(cudaMemcpyAsync(samples, dout, nout * 8, cudaMemcpyDeviceToHost, h->stream), "D2H samples");
   CK(cudaStreamSynchronize(h->stream), "stream synchronize");
@@ -788,7 +841,7 @@ int pnde_eval_dense(pnde_handle* h, int32_t which, int64_t tb, int64_t te, int64
   dp.mean = dmean;
   dp.cov = dcov;
   dp.C = h->C;
-  CK(o->launch_dense(dp, h->stream), "dense kernel launch");
+  CK(o->launch_dense(o, dp, h->stream), "dense kernel launch");
   if (mean) CK(cudaMemcpyAsync(mean, dmean, nm * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
   if (cov) CK(cudaMemcpyAsync(cov, dcov, nc * 8, cudaMemcpyDeviceToHost, h->stream), "D2H cov");
   CK(cudaStreamSynchronize(h->stream), "stream synchronize");

@@ -7,7 +7,12 @@
 // runs a full `smooth` against a zero-covariance "next state" per sample and per interval
 // (src/solution_sampling.jl:49-58), which is the same distribution.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#else
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+#endif
 
 #include "smoother_kernel.cuh"
 

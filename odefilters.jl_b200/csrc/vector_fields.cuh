@@ -3,7 +3,9 @@
 // src/jacobian.jl:6-22 builds symbolic Jacobians with ModelingToolkit -- here f and J are
 // device code selected by the PNDE_VF_* enum of include/pnde.h).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 
 namespace pnde {
 
@@ -85,6 +87,108 @@ __device__ __forceinline__ Jet<N> operator*(const Jet<N>& a, const Jet<N>& b) { 
 #pragma unroll
     for (int i = 1; i <= k; ++i) s = fma(a.c[i], b.c[k - i], s);
     r.c[k] = s;
+  }
+  return r;
+}
+
+
+// keep the double versions visible next to the Jet overloads declared in this namespace
+using ::cos;
+using ::exp;
+using ::log;
+using ::sin;
+using ::sqrt;
+
+// Quotients and elementary functions of jets (standard power-series recurrences), so that run-time
+// compiled user vector fields (rtc_model.cu) can use / exp log sin cos sqrt and still get the exact
+// Taylor-mode initialisation.  The double overloads are CUDA's own.
+template <int N>
+__device__ __forceinline__ Jet<N> operator/(const Jet<N>& a, const Jet<N>& b) {
+  Jet<N> r;
+  const double ib = 1.0 / b.c[0];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double s = a.c[k];
+#pragma unroll
+    for (int i = 1; i <= k; ++i) s = fma(-b.c[i], r.c[k - i], s);
+    r.c[k] = s * ib;
+  }
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Jet<N> operator/(double a, const Jet<N>& b) {
+  Jet<N> x;
+#pragma unroll
+  for (int i = 0; i < N; ++i) x.c[i] = 0.0;
+  x.c[0] = a;
+  return x / b;
+}
+template <int N>
+__device__ __forceinline__ Jet<N> exp(const Jet<N>& a) {
+  Jet<N> r;
+  r.c[0] = ::exp(a.c[0]);
+#pragma unroll
+  for (int k = 1; k < N; ++k) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 1; i <= k; ++i) s = fma(double(i) * a.c[i], r.c[k - i], s);
+    r.c[k] = s / double(k);
+  }
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Jet<N> log(const Jet<N>& a) {
+  Jet<N> r;
+  r.c[0] = ::log(a.c[0]);
+  const double ia = 1.0 / a.c[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 1; i < k; ++i) s = fma(double(i) * r.c[i], a.c[k - i], s);
+    r.c[k] = (a.c[k] - s / double(k)) * ia;
+  }
+  return r;
+}
+template <int N>
+__device__ __forceinline__ void sincos_jet(const Jet<N>& a, Jet<N>& sn, Jet<N>& cs) {
+  sn.c[0] = ::sin(a.c[0]);
+  cs.c[0] = ::cos(a.c[0]);
+#pragma unroll
+  for (int k = 1; k < N; ++k) {
+    double ss = 0.0, cc = 0.0;
+#pragma unroll
+    for (int i = 1; i <= k; ++i) {
+      ss = fma(double(i) * a.c[i], cs.c[k - i], ss);
+      cc = fma(double(i) * a.c[i], sn.c[k - i], cc);
+    }
+    sn.c[k] = ss / double(k);
+    cs.c[k] = -cc / double(k);
+  }
+}
+template <int N>
+__device__ __forceinline__ Jet<N> sin(const Jet<N>& a) {
+  Jet<N> s, c;
+  sincos_jet(a, s, c);
+  return s;
+}
+template <int N>
+__device__ __forceinline__ Jet<N> cos(const Jet<N>& a) {
+  Jet<N> s, c;
+  sincos_jet(a, s, c);
+  return c;
+}
+template <int N>
+__device__ __forceinline__ Jet<N> sqrt(const Jet<N>& a) {
+  Jet<N> r;
+  r.c[0] = ::sqrt(a.c[0]);
+  const double ih = 0.5 / r.c[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) {
+    double s = a.c[k];
+#pragma unroll
+    for (int i = 1; i < k; ++i) s = fma(-r.c[i], r.c[k - i], s);
+    r.c[k] = s * ih;
   }
   return r;
 }

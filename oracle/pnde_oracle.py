@@ -679,6 +679,35 @@ class Jet:
         return Jet([a / o for a in self.c])
 
 
+def _jet_sincos(a: "Jet"):
+    n = len(a.c)
+    s, c = [math.sin(_value(a.c[0])) + 0 * a.c[0]], [math.cos(_value(a.c[0])) + 0 * a.c[0]]
+    for k in range(1, n):
+        ss = sum(i * a.c[i] * c[k - i] for i in range(1, k + 1))
+        cc = sum(i * a.c[i] * s[k - i] for i in range(1, k + 1))
+        s.append(ss / k)
+        c.append(-cc / k)
+    return Jet(s), Jet(c)
+
+
+def gsin(x):
+    """sin for floats and jets (vector fields of the run-time compiled path use elementary functions)."""
+    return _jet_sincos(x)[0] if isinstance(x, Jet) else math.sin(x)
+
+
+def gcos(x):
+    return _jet_sincos(x)[1] if isinstance(x, Jet) else math.cos(x)
+
+
+def gexp(x):
+    if not isinstance(x, Jet):
+        return math.exp(x)
+    r = [math.exp(x.c[0])]
+    for k in range(1, len(x.c)):
+        r.append(sum(i * x.c[i] * r[k - i] for i in range(1, k + 1)) / k)
+    return Jet(r)
+
+
 def get_derivatives(u0, vf: VectorField, p, t0, q: int):
     """[u'(t0), ..., u^(q)(t0)] by Taylor-mode AD (src/state_initialization.jl:15-42).
 

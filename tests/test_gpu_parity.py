@@ -338,3 +338,43 @@ def test_large_dense_ek1_d1024_properties():
     S11 = H @ Sig @ H.T
     scale = np.abs(Sig[d:2 * d, d:2 * d]).max()
     assert np.abs(S11).max() < 1e-4 * scale  # J is evaluated at the prediction in the filter, at the posterior here
+
+
+# ---- run-time compiled user vector fields ------------------------------------
+LV_SRC = dict(d=2, n_params=4,
+              f="du[0] = p[0]*u[0] - p[1]*u[0]*u[1]; du[1] = -p[2]*u[1] + p[3]*u[0]*u[1];",
+              jac="J[0][0] = p[0]-p[1]*u[1]; J[0][1] = -p[1]*u[0]; J[1][0] = p[3]*u[1]; J[1][1] = -p[2]+p[3]*u[0];")
+
+
+@pytest.mark.parametrize("kind,smooth", [("EK1", True), ("EK0", False)])
+def test_custom_vector_field_equals_catalogue(kind, smooth):
+    """The same ODE through NVRTC and through the built-in catalogue runs the same kernel template."""
+    import odefilters_b200 as B
+
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=3, smooth=smooth)
+    u0, p = PROBLEMS["lotka_volterra"]
+    a = B.solve(B.ODEProblem("lotka_volterra", u0, (0.0, 2.0), p), alg)
+    b = B.solve(B.ODEProblem(B.CustomVectorField(**LV_SRC), u0, (0.0, 2.0), p), alg)
+    assert a.destats == b.destats and np.array_equal(a.t, b.t)
+    assert rel(b.x_filt.mu, a.x_filt.mu) < 1e-13 and rel(b.x_filt.Sigma, a.x_filt.Sigma) < 1e-10
+    if smooth:
+        assert rel(b.x_smooth.mu, a.x_smooth.mu) < 1e-12
+        assert b(0.77).mu.shape == (2,) and rel(b(0.77).mu, a(0.77).mu) < 1e-12   # dense output kernel via NVRTC
+        assert b.sample(3, seed=1).shape == (len(b), 2, 3)
+
+
+def test_custom_vector_field_with_elementary_functions():
+    """A field outside the catalogue (pendulum, uses sin/cos): Taylor-mode initialisation through the jet
+    versions of sin/cos and the whole adaptive solve against the oracle."""
+    import odefilters_b200 as B
+
+    pend = B.CustomVectorField(d=2, n_params=1, f="du[0] = u[1]; du[1] = -p[0]*sin(u[0]);",
+                               jac="J[0][0] = 0.0; J[0][1] = 1.0; J[1][0] = -p[0]*cos(u[0]); J[1][1] = 0.0;")
+    vf = O.VectorField("pendulum", 2, 1, lambda u, p, t: [u[1] + 0 * u[0], -p[0] * O.gsin(u[0])],
+                       lambda u, p, t: [[0.0, 1.0], [-p[0] * O.gcos(u[0]), 0.0]])
+    u0, p = [1.2, -0.3], [9.81]
+    so = O.solve_ivp(O.Problem(vf, u0, (0.0, 1.5), p), O.EK1(order=4, smooth=False), abstol=1e-7, reltol=1e-5)
+    sg = B.solve(B.ODEProblem(pend, u0, (0.0, 1.5), p), B.EK1(order=4, smooth=False), abstol=1e-7, reltol=1e-5)
+    assert rel(sg.x_filt.mu[0], so.x_filt[0].mu) < 1e-14                      # exact initial derivatives
+    assert (sg.destats["naccept"], sg.destats["nreject"]) == (so.naccept, so.nreject)
+    assert rel(sg.u, np.array([g.mu[:2] for g in so.x_filt])) < 1e-8

@@ -127,3 +127,16 @@ def test_world_size_2_sharding_over_gloo():
         p.join(60)
     assert [r[1] for r in res] == [n, n] and [r[2] for r in res] == [2.0, 2.0]
     assert res[0][3:] == (0, 500) and res[1][3:] == (500, 1001)
+
+
+def test_custom_vector_field_source_is_validated_without_gpu():
+    """pnde_check_custom: NVRTC compile-only validation (needs libnvrtc, no device)."""
+    import odefilters_b200 as B
+
+    ok = B.CustomVectorField(2, 1, "du[0] = u[1]; du[1] = -p[0]*sin(u[0]);",
+                             "J[0][0] = 0.0; J[0][1] = 1.0; J[1][0] = -p[0]*cos(u[0]); J[1][1] = 0.0;")
+    assert ok.check(B.EK1(order=2)) == ""
+    assert ok.check(B.EK0(order=3, diffusionmodel="dynamicMV")) == ""
+    bad = B.CustomVectorField(2, 1, "du[0] = u[1] du[1] = 0.0;")
+    with pytest.raises(ValueError, match="expected a"):
+        bad.check(B.EK0(order=2))
