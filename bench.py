@@ -272,7 +272,11 @@ def main():
             "peak_source": "DFMA micro-benchmark measured in this run (pnde_measure_fp64_peak); MEASURED_PEAKS.json "
                            "has no FP64 entry" if fp64_peak else "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz",
             "nominal_peak": nominal, "flop_per_unit": FLOP_PER_STEP, "units_per_launch": steps_per_launch,
-            "launch_ms": k_ms, "traffic": None,
+            "launch_ms": k_ms,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel for this workload, one ncu --set full
+            # capture (profiles/r1_filter_kernel_ncu_summary.csv): 51.6 MB + 349.5 MB; algorithmic bytes 408 MB
+            "traffic": 401.0e6 if n == N_TRAJ_PER_GPU else None, "traffic_unit": "bytes per launch",
+            "algorithmic_bytes": (BYTES_IN_PER_TRAJ + BYTES_OUT_PER_TRAJ) * n,
             "hbm": {"achieved": (BYTES_IN_PER_TRAJ + BYTES_OUT_PER_TRAJ) * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "peak_source": hbm_src,
                     "note": "state lives in registers across the time loop: HBM is touched once per trajectory"},

@@ -396,8 +396,11 @@ __device__ __forceinline__ double initdt(const double* u0, const double* p, cons
 #ifndef PNDE_FILTER_MINB
 #define PNDE_FILTER_MINB 1
 #endif
+#ifndef PNDE_FILTER_BLOCK
+#define PNDE_FILTER_BLOCK 128
+#endif
 template <class M, bool ADAPTIVE>
-__global__ void __launch_bounds__(128, PNDE_FILTER_MINB) filter_kernel(const FilterParams prm) {
+__global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_kernel(const FilterParams prm) {
   using VF = typename M::VF;
   constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;

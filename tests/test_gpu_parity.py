@@ -378,3 +378,72 @@ def test_custom_vector_field_with_elementary_functions():
     assert rel(sg.x_filt.mu[0], so.x_filt[0].mu) < 1e-14                      # exact initial derivatives
     assert (sg.destats["naccept"], sg.destats["nreject"]) == (so.naccept, so.nreject)
     assert rel(sg.u, np.array([g.mu[:2] for g in so.x_filt])) < 1e-8
+
+
+# ---- edge cases ----------------------------------------------------------------------------------
+def test_fixed_step_grid_with_sliver_last_step():
+    """t += dt accumulation gives (0,10), dt=0.01 -> 1001 steps, the last one h ~ 1.7e-13
+    (P(h) ~ 1e45).  The GPU must walk the same grid and stay finite."""
+    import odefilters_b200 as B
+
+    so = oracle_solve("lotka_volterra", O.Alg("EK1", 2, "dynamic", False), adaptive=False, dt=0.01, tspan=(0.0, 10.0))
+    sg = gpu_solve("lotka_volterra", B.EK1(order=2, smooth=False), adaptive=False, dt=0.01, tspan=(0.0, 10.0))
+    assert so.naccept == 1001 and sg.destats["naccept"] == 1001
+    assert np.array_equal(sg.t, np.asarray(so.t))
+    assert np.all(np.isfinite(sg.x_filt.mu)) and np.all(np.isfinite(sg.x_filt.Sigma))
+    assert rel(sg.u[:-1], np.array([g.mu[:2] for g in so.x_filt[:-1]])) < 1e-9
+
+
+def test_small_dt_smoothing_stays_finite():
+    """test/smoothing.jl:13-21 and test/specific_problems.jl:16-22: q=4, tiny fixed steps, with smoothing."""
+    import odefilters_b200 as B
+
+    for alg in (B.EK0(order=4, smooth=True), B.EK1(order=4, diffusionmodel="fixed", smooth=True)):
+        sg = gpu_solve("lotka_volterra", alg, adaptive=False, dt=1e-3, tspan=(0.0, 0.5))
+        assert sg.retcode == "Success"
+        assert np.all(np.isfinite(sg.x_smooth.mu)) and np.all(np.isfinite(sg.x_smooth.Sigma))
+        assert np.all(np.diagonal(sg.x_smooth.Sigma, axis1=1, axis2=2) >= 0)
+
+
+@pytest.mark.parametrize("kind,diffusion", [("EK1", "fixed"), ("EK0", "fixedMV"), ("EK0", "dynamicMV"), ("EK1", "fixedMAP")])
+def test_smoother_with_all_diffusion_families(kind, diffusion):
+    """postamble!: static calibration then smoothing (src/integrator_utils.jl:4-26); MV models through the
+    Kronecker smoother."""
+    import odefilters_b200 as B
+
+    so = oracle_solve("lotka_volterra", O.Alg(kind, 2, diffusion, True), adaptive=False, dt=0.02, tspan=(0.0, 1.0))
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=2, diffusionmodel=diffusion, smooth=True)
+    sg = gpu_solve("lotka_volterra", alg, adaptive=False, dt=0.02, tspan=(0.0, 1.0))
+    mo = np.array([g.mu for g in so.x_smooth])
+    co = np.array([g.Sigma.mat for g in so.x_smooth])
+    assert rel(sg.x_smooth.mu[:, :2], mo[:, :2]) < 1e-9
+    assert rel(sg.x_smooth.Sigma[:, :2, :2], co[:, :2, :2]) < 1e-6
+    cf = np.array([g.Sigma.mat for g in so.x_filt])
+    assert rel(sg.x_filt.Sigma[:, :2, :2], cf[:, :2, :2]) < 1e-6  # calibrated filtering covariances
+
+
+def test_retcodes_and_history_growth():
+    import odefilters_b200 as B
+
+    prob = B.ODEProblem("vanderpol", [0.0, 3.0 ** 0.5], (0.0, 1.0), (1e3,))
+    sol = B.solve(prob, B.EK1(order=3, smooth=False), maxiters=50)
+    assert sol.retcode == "MaxIters" and sol.destats["naccept"] + sol.destats["nreject"] == 50
+    # history capacity is grown automatically (retcode 4 internally) until the run fits
+    sol = B.solve(prob, B.EK1(order=3, smooth=False), max_saved=0)
+    assert sol.retcode == "Success" and len(sol.t) == sol.destats["naccept"] + 1 and sol.t[-1] == 1.0
+    with pytest.raises(RuntimeError):
+        s = B.FilterSolver(prob, B.EK1(order=3), save_everystep=False)
+        s.upload(np.zeros((0, 2)), np.zeros((0, 1)))  # empty ensemble is an argument error, not a crash
+
+
+def test_save_stride_and_final_only_agree_with_every_step():
+    import odefilters_b200 as B
+
+    prob = B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 2.0), (0.2, 0.2, 3.0))
+    full = B.solve(prob, B.EK1(order=3, smooth=False), adaptive=False, dt=0.01)
+    s = B.FilterSolver(prob, B.EK1(order=3, smooth=False), adaptive=False, dt=0.01, save_everystep=False, save_stride=50)
+    s.solve_ensemble(prob.u0[None], prob.p[None])
+    _, t, mean, cov, _ = s.history(0, 0, 1)
+    assert np.array_equal(t, full.t[::50]) and np.array_equal(mean, full.x_filt.mu[::50])
+    fin = B.solve(prob, B.EK1(order=3, smooth=False), adaptive=False, dt=0.01, save_everystep=False)
+    assert np.array_equal(fin.x_filt.mu[0], full.x_filt.mu[-1]) and fin.t[0] == 2.0
