@@ -1111,6 +1111,8 @@ def solve_ivp(prob: Problem, alg: Alg, *, adaptive=True, dt=None, abstol=1e-6, r
             sol.retcode = "DtNaN"
             break
         EEst, u_filt = perform_step(cache, prob, alg, sol, t, cur_dt, adaptive, abstol, reltol, u, success_iter)
+        if EEst is not None and not isinstance(EEst, float):
+            EEst = float(EEst)  # mpmath arbiter runs: the controller itself stays in Float64 like dt and t
         u = u_filt  # src/perform_step.jl:86
         if record_attempts is not None:
             record_attempts.append((t, cur_dt, EEst))

@@ -220,3 +220,22 @@ def test_kronecker_model_equals_dense_oracle(adaptive, diffusion):
     ref = so.x_filt[-1]
     assert np.max(np.abs(km["M"].ravel() - ref.mu)) / np.max(np.abs(ref.mu)) < 1e-10
     assert np.max(np.abs(np.kron(km["C"], np.eye(d)) - ref.Sigma.mat)) / np.max(np.abs(ref.Sigma.mat)) < 1e-9
+
+
+# ---- committed fixtures (tests/golden/): the oracle must keep reproducing them ------------------------
+def test_oracle_reproduces_committed_fixtures():
+    import json
+    import os
+
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    lit = json.load(open(os.path.join(gdir, "reference_literals.json")))
+    A, Q = O.ibm(1, 2)
+    assert np.allclose(A, lit["test/priors.jl:50-59"]["A"]) and np.allclose(Q.mat, lit["test/priors.jl:50-59"]["Q"])
+    g = np.load(os.path.join(gdir, "oracle_config1_fhn_readme_ek0q1.npz"))
+    s = O.solve_ivp(O.Problem(O.CATALOGUE["fhn_readme"], [-1.0, 1.0], (0.0, 20.0), [0.2, 0.2, 3.0]), O.EK0(order=1),
+                    abstol=1e-1, reltol=1e-2)
+    assert [s.naccept, s.nreject, s.nf] == list(g["counts"]) and np.allclose(np.array(s.t), g["t"], rtol=1e-12)
+    g = np.load(os.path.join(gdir, "oracle_config5_lv_ek1q3_smooth.npz"))
+    s = O.solve_ivp(O.Problem(O.CATALOGUE["lotka_volterra"], [1.0, 1.0], (0.0, 10.0), [1.5, 1.0, 3.0, 1.0]),
+                    O.EK1(order=3, smooth=True), adaptive=False, dt=0.05)
+    assert np.allclose(np.array([x.mu for x in s.x_smooth]), g["smooth_mean"], rtol=1e-9, atol=1e-12)
