@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams sp) {
 #pragma unroll
             for (int k = 0; k < DCOV; ++k) cols[c][k] *= cs;
         }
-        double Rm[SC::NP], rinv[DCOV], X[DCOV][DCOV];
+        double Rm[SC::NP], rinv[DCOV];
+        RegMat<DCOV> X;
         SC::template stage1<R>(cols, sig, sp.C, Rm, rinv, X);  // cols now holds Y
         constexpr int NR_ = (NF > 1) ? 1 : PT::NREP;           // replicas served by this factor
 #pragma unroll

@@ -14,6 +14,22 @@
 
 namespace pnde {
 
+// D x D matrix either in registers or in shared memory (one column of shared memory per thread, stride =
+// block size, so consecutive threads hit consecutive banks)
+template <int D>
+struct RegMat {
+  double v[D][D];
+  __device__ __forceinline__ double get(int i, int j) const { return v[i][j]; }
+  __device__ __forceinline__ void set(int i, int j, double x) { v[i][j] = x; }
+};
+template <int D>
+struct SmemMat {
+  double* p;
+  int st;
+  __device__ __forceinline__ double get(int i, int j) const { return p[(i * D + j) * st]; }
+  __device__ __forceinline__ void set(int i, int j, double x) { p[(i * D + j) * st] = x; }
+};
+
 template <int dc, int q>
 struct SmoothCov {
   static constexpr int D = dc * (q + 1);
@@ -98,9 +114,9 @@ struct SmoothCov {
   //   in : Er = the NR factor columns (P(h) coordinates)
   //   out: Rm = R-' packed lower (Rm[tri(j,c)] = R-[c][j]), rinv[c] = 1/R-[c][c], X = top-right block,
   //        Er = Y (backward-kernel noise factor: Y'Y = Sigma - G Sigma- G')
-  template <int NR>
+  template <int NR, class XV>
   __device__ __forceinline__ static void stage1(double (&Er)[NR][D], const double sig, const IwpConsts& C,
-                                                double (&Rm)[NP], double (&rinv)[D], double (&X)[D][D]) {
+                                                double (&Rm)[NP], double (&rinv)[D], XV& X) {
     double sL[q + 1][q + 1];
 #pragma unroll
     for (int k = 0; k <= q; ++k)
@@ -148,7 +164,7 @@ struct SmoothCov {
 #pragma unroll
         for (int i = 1; i < NR; ++i) w = fma(El[i][c], Er[i][j], w);
         const double s = beta * w;
-        X[c][j] = -s * v0;
+        X.set(c, j, -s * v0);
 #pragma unroll
         for (int i = 0; i < NR; ++i) Er[i][j] = fma(-s, El[i][c], Er[i][j]);
       }
@@ -156,9 +172,9 @@ struct SmoothCov {
   }
 
   // delta <- G delta = X' (R-^-T delta)
-  template <int NREP>
-  __device__ __forceinline__ static void apply_gain(const double (&Rm)[NP], const double (&rinv)[D],
-                                                    const double (&X)[D][D], double (&delta)[NREP][D]) {
+  template <int NREP, class XV>
+  __device__ __forceinline__ static void apply_gain(const double (&Rm)[NP], const double (&rinv)[D], const XV& X,
+                                                    double (&delta)[NREP][D]) {
 #pragma unroll
     for (int r = 0; r < NREP; ++r) {
       double y[D];
@@ -173,7 +189,7 @@ struct SmoothCov {
       for (int i = 0; i < D; ++i) {
         double acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < D; ++k) acc = fma(X[k][i], y[k], acc);
+        for (int k = 0; k < D; ++k) acc = fma(X.get(k, i), y[k], acc);
         delta[r][i] = acc;
       }
     }
@@ -181,7 +197,7 @@ struct SmoothCov {
 
   // Tt[c][i] = (G Ls)[i][c]:  Z = R-^-T Ls (lower triangular, forward substitution), T = X' Z
   __device__ __forceinline__ static void gain_times_lower(const double (&Rm)[NP], const double (&rinv)[D],
-                                                          const double (&X)[D][D], const double (&Ls)[NP],
+                                                          const RegMat<D>& X, const double (&Ls)[NP],
                                                           double (&Tt)[D][D]) {
     double Z[NP];
 #pragma unroll
@@ -198,9 +214,9 @@ struct SmoothCov {
     for (int c = 0; c < D; ++c) {
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        double acc = X[c][i] * Z[tri(c, c)];
+        double acc = X.get(c, i) * Z[tri(c, c)];
 #pragma unroll
-        for (int k = c + 1; k < D; ++k) acc = fma(X[k][i], Z[tri(k, c)], acc);
+        for (int k = c + 1; k < D; ++k) acc = fma(X.get(k, i), Z[tri(k, c)], acc);
         Tt[c][i] = acc;
       }
     }
@@ -214,13 +230,106 @@ struct SmoothCov {
   template <int NR, int NREP>
   __device__ __forceinline__ static void step_cols(double (&cols)[NR][D], const double sig, const IwpConsts& C,
                                                    double (&Ls)[NP], double (&delta)[NREP][D], int& status) {
-    double Rm[NP], rinv[D], X[D][D];
+    double Rm[NP], rinv[D];
+    RegMat<D> X;
     stage1<NR>(cols, sig, C, Rm, rinv, X);
     apply_gain<NREP>(Rm, rinv, X, delta);
     double Tt[D][D];
     gain_times_lower(Rm, rinv, X, Ls, Tt);
     triangularize<NR>(cols, Tt, Ls, status);
   }
+  // Row-block Householder update: R_acc (upper triangular, stored as its transpose: Racc[tri(j,c)] = R[c][j])
+  // <- triangular factor of [R_acc ; rows].  Reflector c = [R_acc[c][c] ; rows[:, c]] (length NCH + 1).
+  template <int NCH>
+  __device__ __forceinline__ static void qr_update_rows(double (&Racc)[NP], double (&rows)[NCH][D], int& status) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const double pv = Racc[tri(c, c)];
+      double n2 = pv * pv;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) n2 = fma(rows[i][c], rows[i][c], n2);
+      const bool nz = n2 > 0.0;
+      const double rn = nz ? fast_rsqrt(n2) : 0.0;
+      const double nrm = n2 * rn;
+      const double snrm = copysign(nrm, pv);
+      const double v0 = pv + snrm;
+      const double beta = nz ? fast_rcp(fma(fabs(pv), nrm, n2)) : 0.0;
+      Racc[tri(c, c)] = -snrm;
+      if (!(n2 == n2)) status |= 1;
+#pragma unroll
+      for (int j = c + 1; j < D; ++j) {
+        const double prj = Racc[tri(j, c)];
+        double w = v0 * prj;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) w = fma(rows[i][c], rows[i][j], w);
+        const double s = beta * w;
+        Racc[tri(j, c)] = fma(-s, v0, prj);
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) rows[i][j] = fma(-s, rows[i][c], rows[i][j]);
+      }
+    }
+  }
+
+  // Same RTS step as step_cols, laid out for one thread per trajectory WITHOUT register spills: X (and then
+  // T' in its place) and the smoothed factor L^s live in shared memory, the final triangularisation is a
+  // sequence of row-block updates (Y, then T' four rows at a time) so that at most ~85 doubles are live.
+  //   Xs : D x D scratch in shared memory;  Lsv: packed lower L^s_{i+1} in shared memory, natural coordinates;
+  //   Pk / PIk: block scales of this interval (L^s is re-preconditioned on the fly)
+  template <int NR>
+  __device__ __forceinline__ static void step_cols_smem(double (&cols)[NR][D], const double sig, const IwpConsts& C,
+                                                        SmemMat<D>& Xs, double* Lsv, int lst, const double (&Pk)[q + 1],
+                                                        const double (&PIk)[q + 1], double (&delta)[1][D], int& status) {
+    double Rm[NP], rinv[D];
+    stage1<NR>(cols, sig, C, Rm, rinv, Xs);
+    apply_gain<1>(Rm, rinv, Xs, delta);
+    // Z = R-^-T (P L^s): forward substitution row by row
+    double Z[NP];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int c = 0; c <= i; ++c) {
+        double acc = Lsv[tri(i, c) * lst] * Pk[i / dc];
+#pragma unroll
+        for (int k = c; k < i; ++k) acc = fma(-Rm[tri(i, k)], Z[tri(k, c)], acc);
+        Z[tri(i, c)] = acc * rinv[i];
+      }
+    }
+    // T' in place of X: Tt[c][i] = sum_{k >= c} X[k][i] Z[k][c], one column i of X at a time
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double xc[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) xc[k] = Xs.get(k, i);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double acc = xc[c] * Z[tri(c, c)];
+#pragma unroll
+        for (int k = c + 1; k < D; ++k) acc = fma(xc[k], Z[tri(k, c)], acc);
+        Xs.set(c, i, acc);
+      }
+    }
+    // triangularise [Y ; T'] by row blocks
+    double Racc[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) Racc[i] = 0.0;
+    qr_update_rows<NR>(Racc, cols, status);
+    constexpr int CH = 4;
+#pragma unroll
+    for (int r0 = 0; r0 < D; r0 += CH) {
+      double rows[CH][D];
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) rows[i][j] = (r0 + i < D) ? Xs.get(r0 + i < D ? r0 + i : 0, j) : 0.0;
+      qr_update_rows<CH>(Racc, rows, status);
+    }
+    // L^s_i = R', back to natural coordinates
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+      for (int c = 0; c <= j; ++c) Lsv[tri(j, c) * lst] = Racc[tri(j, c)] * PIk[j / dc];
+  }
+
   template <int NREP>
   __device__ __forceinline__ static void step(const Factor<dc, q>& F, const double sig, const IwpConsts& C,
                                               double (&Ls)[NP], double (&delta)[NREP][D], int& status) {
@@ -296,6 +405,12 @@ struct SmoothModel<KronEK0<VF, q_, MVDYN>> {
   }
 };
 
+#ifndef PNDE_PREFETCH_OP
+#define PNDE_PREFETCH_OP "prefetch.global.L2"
+#endif
+#ifndef PNDE_PREFETCH_AHEAD
+#define PNDE_PREFETCH_AHEAD 1
+#endif
 template <class M>
 __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
   using SM = SmoothModel<M>;
@@ -327,7 +442,12 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
   auto srec = [&](int slot) { return sp.smooth + ((long long)slot * SREC) * n + tid; };
 
   double ms[D];          // smoothed mean at i+1 (natural coordinates)
-  double Ls[NF][SC::NP]; // smoothed factor(s) at i+1 (natural coordinates), packed lower
+  double Ls[NF][SC::NP]; // smoothed factor(s) at i+1 (natural coordinates), packed lower (Kronecker models)
+  // dense EK1: the D x D scratch X / T' and the smoothed factor live in shared memory (no register spills)
+  extern __shared__ double sm_dyn[];
+  const int lst = blockDim.x;
+  SmemMat<DCOV> Xs{sm_dyn + threadIdx.x, lst};
+  double* Lsv = sm_dyn + (size_t)DCOV * DCOV * lst + threadIdx.x;
   auto write = [&](int slot) {
     double* o = srec(slot);
 #pragma unroll
@@ -335,7 +455,8 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
 #pragma unroll
     for (int f = 0; f < NF; ++f)
 #pragma unroll
-      for (int i = 0; i < SC::NP; ++i) o[(long long)(D + f * SC::NP + i) * n] = Ls[f][i];
+      for (int i = 0; i < SC::NP; ++i)
+        o[(long long)(D + f * SC::NP + i) * n] = M::IS_EK1 ? Lsv[i * lst] : Ls[f][i];
     if constexpr (!M::IS_EK1) {
 #pragma unroll
       for (int a = 0; a < d; ++a) o[(long long)(D + NF * SC::NP + a) * n] = dimscale[a];
@@ -368,6 +489,10 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
 #pragma unroll
         for (int i = 0; i < DCOV; ++i) Tt[c][i] = 0.0;
       SC::template triangularize<SC::R>(Y, Tt, Ls[f], status);
+      if constexpr (M::IS_EK1) {
+#pragma unroll
+        for (int i = 0; i < SC::NP; ++i) Lsv[i * lst] = Ls[0][i];
+      }
     }
   };
 
@@ -376,6 +501,12 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
   for (int i = ns - 2; i >= 1; --i) {
     const double* ri = rec(i);
     const double* rn = rec(i + 1);
+    // the records are streamed once, backwards: pull the next one (i-1) towards L1/L2 while this step computes
+    if (i > PNDE_PREFETCH_AHEAD) {
+      const double* rp = rec(i - PNDE_PREFETCH_AHEAD);
+#pragma unroll
+      for (int k = 0; k < REC; ++k) asm volatile(PNDE_PREFETCH_OP " [%0];" ::"l"(rp + (long long)k * n));
+    }
     const double h = rn[0] - ri[0];
     if (h == 0.0) {  // src/smoothing.jl:13-16
       write(i);
@@ -398,20 +529,24 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
 #pragma unroll
     for (int k = 0; k < D; ++k) mpred[k] = st.m[k];
     apply_A<d, q>(mpred);
+    if constexpr (!M::IS_EK1) {
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      // scale smoothed factor at i+1 into P(h) coordinates
+      for (int f = 0; f < NF; ++f) {
+        // scale smoothed factor at i+1 into P(h) coordinates
 #pragma unroll
-      for (int r = 0; r < DCOV; ++r)
+        for (int r = 0; r < DCOV; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) Ls[f][SC::tri(r, c)] *= Pk[r / DC];
+          for (int c = 0; c <= r; ++c) Ls[f][SC::tri(r, c)] *= Pk[r / DC];
+      }
     }
     if constexpr (M::IS_EK1) {
       st.F.scale_all(dense_cal);
       double delta[1][D];
 #pragma unroll
       for (int k = 0; k < D; ++k) delta[0][k] = fma(Pk[k / d], ms[k], -mpred[k]);
-      SC::template step<1>(st.F, sig[0], sp.C, Ls[0], delta, status);
+      double cols[SC::R][D];
+      SC::cols_from_factor(st.F, cols);
+      SC::template step_cols_smem<SC::R>(cols, sig[0], sp.C, Xs, Lsv, lst, Pk, PIk, delta, status);
 #pragma unroll
       for (int k = 0; k < D; ++k) ms[k] = (st.m[k] + delta[0][k]) * PIk[k / d];
     } else if constexpr (NF == 1) {
@@ -441,13 +576,15 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
         for (int k = 0; k <= q; ++k) ms[k * d + a] = (st.m[k * d + a] + delta[0][k]) * PIk[k];
       }
     }
+    if constexpr (!M::IS_EK1) {
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
+      for (int f = 0; f < NF; ++f) {
 #pragma unroll
-      for (int r = 0; r < DCOV; ++r) {
+        for (int r = 0; r < DCOV; ++r) {
 #pragma unroll
-        for (int c = 0; c <= r; ++c) Ls[f][SC::tri(r, c)] *= PIk[r / DC];
-        if (!(Ls[f][SC::tri(r, r)] == Ls[f][SC::tri(r, r)])) status |= 1;
+          for (int c = 0; c <= r; ++c) Ls[f][SC::tri(r, c)] *= PIk[r / DC];
+          if (!(Ls[f][SC::tri(r, r)] == Ls[f][SC::tri(r, r)])) status |= 1;
+        }
       }
     }
 #pragma unroll
