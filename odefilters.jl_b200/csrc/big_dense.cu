@@ -353,7 +353,7 @@ size_t big_work_bytes(int d, int q) {
   const size_t D = (size_t)d * (q + 1);
   // m, mp, Jp, fu, z, y, jets | S | E | R | W | v0, T | scalars
   return (D * 2 + (size_t)d * 4 + (size_t)d * 3 + D) * 8 + (D - d) * D * 8 + D * D * 8 * 2 + (size_t)NB * D * 8 +
-         (NB + NB * NB) * 8 + sizeof(Scalars) + 4096;
+         2 * (NB + NB * NB) * 8 + sizeof(Scalars) + 8192;
 }
 
 #define BCK(call)                      \
@@ -388,8 +388,13 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
   c.R = (double*)take((size_t)D * D * 8);
   QrWork wk;
   wk.W = (double*)take((size_t)NB * D * 8);
-  wk.v0 = (double*)take(NB * 8);
-  wk.T = (double*)take(NB * NB * 8);
+  wk.v0 = (double*)take(2 * NB * 8);
+  wk.T = (double*)take(2 * NB * NB * 8);
+  BCK(cudaStreamCreateWithFlags(&wk.aux, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    BCK(cudaEventCreateWithFlags(&wk.ev_narrow[i], cudaEventDisableTiming));
+    BCK(cudaEventCreateWithFlags(&wk.ev_panel[i], cudaEventDisableTiming));
+  }
   c.sc = (Scalars*)take(sizeof(Scalars));
   c.diffusion = A.diffusion;
   c.C = A.C;
@@ -459,6 +464,13 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
       *launches += 2;
     }
   }
+  cudaError_t fin = cudaStreamSynchronize(s);  // the auxiliary stream's work is ordered before this point
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(wk.ev_narrow[i]);
+    cudaEventDestroy(wk.ev_panel[i]);
+  }
+  cudaStreamDestroy(wk.aux);
+  if (fin != cudaSuccess) return fin;
   return cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "cov_engine.cuh"
 
@@ -265,17 +266,24 @@ __global__ void __launch_bounds__(128) rank_update_kernel(const double* __restri
     const int r = idx / 64, c = idx % 64;
     Bs[r * LDB_S + c] = (n0 + c < N) ? B[(size_t)r * ldb + n0 + c] : 0.0;
   }
-  __syncthreads();
+  // the C fragment is read up front (acc starts as C, the product is subtracted through -A), so that all
+  // global loads of the tile are in flight together
   double acc[2][8][2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int nt = 0; nt < 8; ++nt) {
+      const int i = i0 + warp * 16 + mt * 8 + (lane >> 2);
+      const int n = n0 + nt * 8 + 2 * (lane & 3);
+      acc[mt][nt][0] = (i < M && n < N) ? Cm[(size_t)i * ldc + n] : 0.0;
+      acc[mt][nt][1] = (i < M && n + 1 < N) ? Cm[(size_t)i * ldc + n + 1] : 0.0;
+    }
+  __syncthreads();
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
     double af[2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) af[mt] = As[(warp * 16 + mt * 8 + (lane >> 2)) * LDA_S + kk * 4 + (lane & 3)];
+    for (int mt = 0; mt < 2; ++mt) af[mt] = -As[(warp * 16 + mt * 8 + (lane >> 2)) * LDA_S + kk * 4 + (lane & 3)];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const double bf = Bs[(kk * 4 + (lane & 3)) * LDB_S + nt * 8 + (lane >> 2)];
@@ -290,8 +298,8 @@ __global__ void __launch_bounds__(128) rank_update_kernel(const double* __restri
       const int i = i0 + warp * 16 + mt * 8 + (lane >> 2);
       const int n = n0 + nt * 8 + 2 * (lane & 3);
       if (i < M) {
-        if (n < N) Cm[(size_t)i * ldc + n] -= acc[mt][nt][0];
-        if (n + 1 < N) Cm[(size_t)i * ldc + n + 1] -= acc[mt][nt][1];
+        if (n < N) Cm[(size_t)i * ldc + n] = acc[mt][nt][0];
+        if (n + 1 < N) Cm[(size_t)i * ldc + n + 1] = acc[mt][nt][1];
       }
     }
 }
@@ -305,44 +313,49 @@ struct W2Args {
   int ldw;
   double* R;
   int ld, c0, ncols, d, mode;
+  int jt0, jt1;  // trailing-column range [jt0, jt1) handled by this launch (jt = j - (c0 + NB))
   const double* v0;
   const double* T;
   const Scalars* sc;
   IwpConsts C;
 };
 
-__global__ void __launch_bounds__(128) w2_kernel(const W2Args a) {
-  __shared__ double sT[NB][NB + 1], sv0[NB];
+__global__ void __launch_bounds__(256) w2_kernel(const W2Args a) {
+  // block = 8 trailing columns x 32 panel rows: thread (k, column) computes W2[k][j]
+  __shared__ double sT[NB][NB + 1], sv0[NB], sw[8][NB + 1];
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) sT[e / NB][e % NB] = a.T[e];
   if (threadIdx.x < NB) sv0[threadIdx.x] = a.v0[threadIdx.x];
   __syncthreads();
-  const int jt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = threadIdx.x % NB, cj = threadIdx.x / NB;
+  const int jt = a.jt0 + blockIdx.x * 8 + cj;
   const int j = a.c0 + NB + jt;
-  if (j >= a.ncols) return;
+  const bool valid = (jt < a.jt1) && (j < a.ncols);
   const double sigma = (a.mode == 0) ? 1.0 : a.sc->sigma;
   const double pi1 = a.sc->pi1;
-  double w[NB], piv[NB];
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    piv[k] = sigma * prior_pivot(a.c0 + k, j, a.d, pi1, a.C, a.mode);
-    w[k] = fma(sv0[k], piv[k], a.W[(size_t)k * a.ldw + jt]);
+  double piv = 0.0;
+  if (valid) {
+    piv = sigma * prior_pivot(a.c0 + k, j, a.d, pi1, a.C, a.mode);
+    sw[cj][k] = fma(sv0[k], piv, a.W[(size_t)k * a.ldw + jt]);
   }
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    double acc = 0.0;
-#pragma unroll
-    for (int m = 0; m <= k; ++m) acc = fma(sT[m][k], w[m], acc);  // T' is lower triangular
-    a.W[(size_t)k * a.ldw + jt] = acc;
-    a.R[(size_t)(a.c0 + k) * a.ld + j] = fma(-sv0[k], acc, piv[k]);
-  }
+  __syncthreads();
+  if (!valid) return;
+  double acc = 0.0;
+  for (int m = 0; m <= k; ++m) acc = fma(sT[m][k], sw[cj][m], acc);  // T' is lower triangular
+  a.W[(size_t)k * a.ldw + jt] = acc;
+  a.R[(size_t)(a.c0 + k) * a.ld + j] = fma(-sv0[k], acc, piv);
 }
 
 // Blocked QR driver: E (nrows x ncols, ld) -> R rows [0, ncols) (upper triangular part written).
-// nrows % (8 * NCLUSTER) == 0, ncols % NB == 0.  work: W [NB][ld], v0 [NB], T [NB*NB].
+// nrows % (8 * NCLUSTER) == 0, ncols % NB == 0.  work: W [NB][ld], v0 [2][NB], T [2][NB*NB].
+// Look-ahead: after panel j, the NB columns of panel j+1 are updated first ("narrow" update) so that the
+// factorisation of panel j+1 (8 SMs, stream `aux`) overlaps the update of the remaining trailing columns
+// with panel j's reflectors ("wide" update, main stream).
 struct QrWork {
   double* W;
-  double* v0;
-  double* T;
+  double* v0;  // [2][NB]
+  double* T;   // [2][NB*NB]
+  cudaStream_t aux;
+  cudaEvent_t ev_narrow[2], ev_panel[2];
 };
 
 inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols, int d, int mode, const Scalars* sc,
@@ -351,7 +364,7 @@ inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols
   const size_t smem = ((size_t)rows_per * (NB + 1) + (PANEL_THREADS / NB + 2) * NB + NB * NB) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  for (int c0 = 0; c0 < ncols; c0 += NB) {
+  auto launch_panel = [&](int c0, int buf, cudaStream_t st) {
     PanelArgs pa;
     pa.E = E;
     pa.R = R;
@@ -361,18 +374,21 @@ inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols
     pa.d = d;
     pa.mode = mode;
     pa.sc = sc;
-    pa.v0 = wk.v0;
-    pa.T = wk.T;
+    pa.v0 = wk.v0 + buf * NB;
+    pa.T = wk.T + buf * NB * NB;
     pa.C = C;
-    panel_kernel<<<NCLUSTER, PANEL_THREADS, smem, s>>>(pa);
+    panel_kernel<<<NCLUSTER, PANEL_THREADS, smem, st>>>(pa);
     ++*launches;
-    const int ntrail = ncols - c0 - NB;
-    if (ntrail <= 0) break;
-    e = cudaMemsetAsync(wk.W, 0, (size_t)NB * ld * sizeof(double), s);
-    if (e != cudaSuccess) return e;
-    const int kchunk = 128;
-    dim3 g1((ntrail + 63) / 64, 1, (nrows + kchunk - 1) / kchunk);
-    atb_kernel<<<g1, 128, 0, s>>>(E + c0, ld, E + c0 + NB, ld, wk.W, ld, ntrail, nrows, kchunk);
+  };
+  // trailing update of the columns jt in [jt0, jt1) (relative to c0 + NB) with the reflectors of panel c0
+  auto update = [&](int c0, int buf, int jt0, int jt1) -> cudaError_t {
+    const int nc = jt1 - jt0;
+    if (nc <= 0) return cudaSuccess;
+    cudaError_t e2 = cudaMemset2DAsync(wk.W + jt0, (size_t)ld * sizeof(double), 0, (size_t)nc * sizeof(double), NB, s);
+    if (e2 != cudaSuccess) return e2;
+    static const int kchunk = getenv("PNDE_ATB_KCHUNK") ? atoi(getenv("PNDE_ATB_KCHUNK")) : 64;
+    dim3 g1((nc + 63) / 64, 1, (nrows + kchunk - 1) / kchunk);
+    atb_kernel<<<g1, 128, 0, s>>>(E + c0, ld, E + c0 + NB + jt0, ld, wk.W + jt0, ld, nc, nrows, kchunk);
     W2Args wa;
     wa.W = wk.W;
     wa.ldw = ld;
@@ -382,14 +398,33 @@ inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols
     wa.ncols = ncols;
     wa.d = d;
     wa.mode = mode;
-    wa.v0 = wk.v0;
-    wa.T = wk.T;
+    wa.jt0 = jt0;
+    wa.jt1 = jt1;
+    wa.v0 = wk.v0 + buf * NB;
+    wa.T = wk.T + buf * NB * NB;
     wa.sc = sc;
     wa.C = C;
-    w2_kernel<<<(ntrail + 127) / 128, 128, 0, s>>>(wa);
-    dim3 g2((ntrail + 63) / 64, (nrows + 63) / 64);
-    rank_update_kernel<<<g2, 128, 0, s>>>(E + c0, ld, wk.W, ld, E + c0 + NB, ld, nrows, ntrail);
+    w2_kernel<<<(nc + 7) / 8, 256, 0, s>>>(wa);
+    dim3 g2((nc + 63) / 64, (nrows + 63) / 64);
+    rank_update_kernel<<<g2, 128, 0, s>>>(E + c0, ld, wk.W + jt0, ld, E + c0 + NB + jt0, ld, nrows, nc);
     *launches += 3;
+    return cudaSuccess;
+  };
+  launch_panel(0, 0, s);
+  for (int c0 = 0, j = 0; c0 < ncols; c0 += NB, ++j) {
+    const int ntrail = ncols - c0 - NB;
+    if (ntrail <= 0) break;
+    const int par = j & 1;
+    const int nn = ntrail < NB ? ntrail : NB;
+    e = update(c0, par, 0, nn);  // narrow: the next panel's columns
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventRecord(wk.ev_narrow[par], s)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(wk.aux, wk.ev_narrow[par], 0)) != cudaSuccess) return e;
+    launch_panel(c0 + NB, 1 - par, wk.aux);
+    if ((e = cudaEventRecord(wk.ev_panel[1 - par], wk.aux)) != cudaSuccess) return e;
+    e = update(c0, par, nn, ntrail);  // wide: everything behind it, overlapping the panel factorisation
+    if (e != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(s, wk.ev_panel[1 - par], 0)) != cudaSuccess) return e;
   }
   return cudaGetLastError();
 }
