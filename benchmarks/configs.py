@@ -81,7 +81,7 @@ def config4(d=1024):
     steps = int(c["naccept"].sum())
     return {"config": 4, "what": f"Lorenz-96 d={d}, EK0(order=3) Kronecker covariance, fixed dt=1e-3, one CTA",
             "steps": steps, "ms": ms, "us_per_step": 1e3 * ms / steps, "all_success": bool((c["retcode"] == 0).all()),
-            "note": "latency bound (one sequential chain, 3 block syncs per step); EK1 dense D=4096 path not built"}
+            "note": "latency bound (one sequential chain, 3 block syncs per step)"}
 
 
 def config4_ek1(d=1024, nsteps=20):
