@@ -268,15 +268,6 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
       else
         n2b = fma(E[i][c], E[i][c], n2b);
     }
-#ifdef PNDE_EXP_CLAMP
-    // clamp instead of a zero test: a structurally zero column gives w = 0, so beta never matters
-    const double n2 = fmax(n2a + n2b, 1e-300);
-    const double rn = fast_rsqrt(n2);
-    const double nrm = n2 * rn;
-    const double snrm = copysign(nrm, pv);
-    const double v0 = pv + snrm;
-    const double beta = fast_rcp(fma(fabs(pv), nrm, n2));
-#else
     const double n2 = n2a + n2b;
     const bool nzcol = n2 > 0.0;
     const double rn = nzcol ? fast_rsqrt(n2) : 0.0;  // 1 / ||x||
@@ -284,7 +275,6 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
     const double snrm = copysign(nrm, pv);
     const double v0 = pv + snrm;
     const double beta = nzcol ? fast_rcp(fma(fabs(pv), nrm, n2)) : 0.0;  // 1 / (||x|| (||x|| + |pv|))
-#endif
     double Rrow[D];
     Rrow[c] = -snrm;
 #pragma unroll
@@ -304,22 +294,6 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
       }
       double w = pnz ? v0 * prj : 0.0;
       bool started = pnz;
-#ifdef PNDE_EXP_SPLITW
-      // two interleaved chains when few trailing columns are left (little column-level parallelism)
-      if (D - 1 - c <= PNDE_EXP_SPLITW) {
-        double w2 = 0.0;
-        bool started2 = false;
-#pragma unroll
-        for (int i = first; i < D; ++i) {
-          if ((i - first) & 1) {
-            if (!started2) { w2 = E[i][c] * E[i][j]; started2 = true; } else { w2 = fma(E[i][c], E[i][j], w2); }
-          } else {
-            if (!started) { w = E[i][c] * E[i][j]; started = true; } else { w = fma(E[i][c], E[i][j], w); }
-          }
-        }
-        if (started2) w += w2;
-      } else
-#endif
       {
 #pragma unroll
         for (int i = first; i < D; ++i) {

@@ -484,8 +484,7 @@ def test_golden_config3_vanderpol_adaptive():
     import odefilters_b200 as B
 
     g = _g("oracle_config3_vdp_ek1q5.npz")
-    sol = gpu_solve("vanderpol", B.EK1(order=5, smooth=False), tspan=(0.0, 1.0)) if False else \
-        B.solve(B.ODEProblem("vanderpol", [0.0, 3.0 ** 0.5], (0.0, 1.0), (1e3,)), B.EK1(order=5, smooth=False))
+    sol = B.solve(B.ODEProblem("vanderpol", [0.0, 3.0 ** 0.5], (0.0, 1.0), (1e3,)), B.EK1(order=5, smooth=False))
     # Stiff, q = 5: FP64 cannot pin the accept/reject decisions of this config.  oracle/arbiter_mpmath.py vdp:
     # the 60-digit recursion takes 325 accepted / 6 rejected steps, the reference's FP64 arithmetic (oracle)
     # 327 / 8, this kernel 324 / 3 -- all within 1 % of each other; u(1) agrees to 3e-7.
@@ -530,3 +529,26 @@ def test_full_size_config2_properties():
     # draws (oracle/arbiter_mpmath.py fhn: numpy oracle 4.1e-10, C restatement 5.4e-10, this kernel's model
     # 4.2e-10 away from the 60-digit recursion), so two FP64 implementations agree to ~1e-8, not 1e-10
     assert rel(es.mean[idx][:, :2], ref["mean"][:, :2]) < 1e-7
+
+
+def test_marginals_getter_matches_history():
+    """pnde_get_marginals (sol.pu, src/integrator_utils.jl:45) = solution block of pnde_get_history, for filtered and
+    smoothed states and for a trajectory sub-range of a ragged (adaptive) ensemble."""
+    import odefilters_b200 as B
+
+    rng = np.random.default_rng(3)
+    P = np.array([1.5, 1.0, 3.0, 1.0]) * (1 + 0.2 * rng.uniform(-1, 1, (9, 4)))
+    prob = B.ODEProblem("lotka_volterra", [1.0, 1.0], (0.0, 1.5), P[0])
+    s = B.FilterSolver(prob, B.EK1(order=2, smooth=True), max_saved=512)
+    s.solve_ensemble(np.ones((9, 2)), P)
+    cnt = s.counts()
+    assert len(set(cnt["n_saved"].tolist())) > 1  # ragged
+    for which in (0, 1):
+        off, t, mean, cov, _ = s.history(which, 2, 7)
+        offm, tm, u, cu, _ = s.history(which, 2, 7, marginals=True)
+        assert np.array_equal(off, offm) and np.array_equal(t, tm) and off[-1] == cnt["n_saved"][2:7].sum()
+        assert np.array_equal(u, mean[:, :2])
+        full = np.zeros((len(t), 6, 6))
+        il = np.tril_indices(6)
+        full[:, il[0], il[1]] = cov
+        assert np.array_equal(cu, np.stack([full[:, 0, 0], full[:, 1, 0], full[:, 1, 1]], axis=1))
