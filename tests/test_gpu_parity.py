@@ -552,3 +552,56 @@ def test_marginals_getter_matches_history():
         il = np.tril_indices(6)
         full[:, il[0], il[1]] = cov
         assert np.array_equal(cu, np.stack([full[:, 0, 0], full[:, 1, 0], full[:, 1, 1]], axis=1))
+
+
+# ---- randomized sweep over the whole option space ---------------------------------------------------
+def _random_cases(n=28, seed=20260118):
+    rng = np.random.default_rng(seed)
+    cases = []
+    names = ["fhn_readme", "fhn_lib", "lotka_volterra", "logistic"]
+    while len(cases) < n:
+        name = names[rng.integers(len(names))]
+        kind = ["EK0", "EK1"][rng.integers(2)]
+        q = int(rng.integers(1, 5))
+        diffs = ["dynamic", "fixed", "fixedMAP"] + (["dynamicMV", "fixedMV"] if kind == "EK0" else [])
+        diffusion = diffs[rng.integers(len(diffs))]
+        adaptive = bool(rng.integers(2))
+        smooth = bool(rng.integers(2))
+        t1 = float(rng.uniform(0.3, 1.5))
+        dt = float(rng.choice([0.01, 0.02, 0.037]))
+        tol = float(10.0 ** rng.uniform(-7, -3))
+        cases.append((name, kind, q, diffusion, adaptive, smooth, round(t1, 3), dt, tol))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_cases(), ids=lambda c: "-".join(map(str, c[:6])))
+def test_randomized_option_sweep(case):
+    """Seeded random draws over (field, EK0/EK1, order, diffusion model, adaptive/fixed, smoothing, span, step,
+    tolerance): solution-block parity with the oracle, identical step counts, smoothed means."""
+    import odefilters_b200 as B
+
+    name, kind, q, diffusion, adaptive, smooth, t1, dt, tol = case
+    kw = dict(tspan=(0.0, t1))
+    kw.update(dict(abstol=tol, reltol=tol * 100) if adaptive else dict(adaptive=False, dt=dt))
+    so = oracle_solve(name, O.Alg(kind, q, diffusion, smooth), **dict(kw))
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, diffusionmodel=diffusion, smooth=smooth)
+    sg = gpu_solve(name, alg, **dict(kw))
+    d = len(PROBLEMS[name][0])
+    assert sg.retcode == "Success" and sg.t[-1] == t1
+    assert (sg.destats["naccept"], sg.destats["nreject"], sg.destats["nf"]) == (so.naccept, so.nreject, so.nf)
+    uf = np.array([g.mu[:d] for g in so.x_filt])
+    assert rel(sg.x_filt.mu[:, :d], uf) < (1e-7 if adaptive else 1e-9)
+    if smooth:
+        us = np.array([g.mu[:d] for g in so.x_smooth])
+        assert rel(sg.x_smooth.mu[:, :d], us) < (1e-6 if adaptive else 1e-8)
+        assert rel(sg.u, np.array(so.u)) < (1e-6 if adaptive else 1e-8)
+    vo = np.array([np.diag(g.Sigma.mat)[:d] for g in so.x_filt])
+    vg = np.diagonal(sg.x_filt.Sigma, axis1=1, axis2=2)[:, :d]
+    assert rel(vg, vo) < 1e-3 + cov_tol(q, 0)
+    # dense output between grid points (filtering or smoothing posterior, calibrated for static models)
+    tq = np.array([0.31, 0.57, 0.83]) * t1
+    dg = sg(tq)
+    for i, tt in enumerate(tq):
+        ref = O.dense_eval(so, float(tt))
+        assert rel(dg.mu[i], ref.mu) < 1e-6
+        assert rel(np.diag(dg.Sigma[i]), np.diag(ref.Sigma.mat)) < 1e-3 + 10 * cov_tol(q, 0)
