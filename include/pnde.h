@@ -143,6 +143,13 @@ int64_t pnde_cov_len(const pnde_handle* h);      /* rows of pnde_get_final's cov
  * u0: [d][n_traj], p: [n_params][n_traj].  Equivalent to pnde_upload + pnde_run (+ pnde_smooth). */
 int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const double* p);
 
+/* pnde_solve_ensemble + pnde_get_final in one call, pipelined: the ensemble is processed in slices and the
+ * device-to-host copy of a finished slice overlaps the kernel of the next one (final-state runs of the
+ * thread-per-trajectory models; other configurations fall back to the plain sequence).  Output layout as in
+ * pnde_get_final; any output pointer may be NULL. */
+int pnde_solve_ensemble_to_host(pnde_handle* h, int64_t n_traj, const double* u0, const double* p, double* mean,
+                                double* cov, double* t_final, double* loglik);
+
 /* Split form, so that inputs can stay resident in HBM across runs. */
 int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* p);
 int pnde_run(pnde_handle* h);         /* initialize! + the whole solve! loop, asynchronous */

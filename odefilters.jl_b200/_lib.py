@@ -34,7 +34,7 @@ class PndeConfig(C.Structure):
 
 EXPORTS = [
     "pnde_default_config", "pnde_create", "pnde_create_custom", "pnde_check_custom", "pnde_destroy", "pnde_last_error", "pnde_state_dim", "pnde_n_params",
-    "pnde_record_len", "pnde_cov_len", "pnde_solve_ensemble", "pnde_upload", "pnde_run", "pnde_synchronize", "pnde_last_run_ms",
+    "pnde_record_len", "pnde_cov_len", "pnde_solve_ensemble", "pnde_solve_ensemble_to_host", "pnde_upload", "pnde_run", "pnde_synchronize", "pnde_last_run_ms",
     "pnde_last_launch_count", "pnde_smooth", "pnde_query_sizes", "pnde_get_counts", "pnde_get_final",
     "pnde_get_history", "pnde_get_marginals", "pnde_sample", "pnde_eval_dense", "pnde_measure_fp64_peak",
     "pnde_measure_hbm_copy",
@@ -67,6 +67,7 @@ def load():
         getattr(lib, f).argtypes = [vp]
         getattr(lib, f).restype = C.c_int64
     lib.pnde_solve_ensemble.argtypes = [vp, C.c_int64, vp, vp]
+    lib.pnde_solve_ensemble_to_host.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp]
     lib.pnde_upload.argtypes = [vp, C.c_int64, vp, vp]
     lib.pnde_run.argtypes = [vp]
     lib.pnde_synchronize.argtypes = [vp]

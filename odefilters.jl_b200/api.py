@@ -365,6 +365,19 @@ class FilterSolver:
         self._check(self.lib.pnde_solve_ensemble(self._h, n, u0s.ctypes.data, ps.ctypes.data), "pnde_solve_ensemble")
         self.n = n
 
+    def solve_to_host(self, u0: np.ndarray, p: np.ndarray, soa: bool = False):
+        """pnde_solve_ensemble_to_host: pipelined solve + final-state download; returns final()'s tuple."""
+        u0s = u0 if soa else self._soa(u0)
+        ps = p if soa else self._soa(p)
+        n, D = u0s.shape[1], self.D
+        self._keep = (u0s, ps)
+        mean, cov, tf, ll = np.empty((D, n)), np.empty((self.ncov, n)), np.empty(n), np.empty(n)
+        self._check(self.lib.pnde_solve_ensemble_to_host(self._h, n, u0s.ctypes.data, ps.ctypes.data, mean.ctypes.data,
+                                                         cov.ctypes.data, tf.ctypes.data, ll.ctypes.data),
+                    "pnde_solve_ensemble_to_host")
+        self.n = n
+        return mean.T.copy(), cov.T.copy(), tf, ll
+
     def last_run_ms(self):
         a, b = C.c_double(), C.c_double()
         self._check(self.lib.pnde_last_run_ms(self._h, C.byref(a), C.byref(b)), "pnde_last_run_ms")

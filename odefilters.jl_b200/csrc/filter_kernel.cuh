@@ -33,7 +33,9 @@ struct CtrlParams {
 };
 
 struct FilterParams {
-  long long n;
+  long long n;       // trajectories in the ensemble = stride of every structure-of-arrays buffer
+  long long first;   // this launch handles trajectories [first, first + count) (pipelined host transfers)
+  long long count;
   const double* u0;  // [d][n]
   const double* p;   // [np][n]
   double* mean;      // [D][n]
@@ -403,8 +405,9 @@ template <class M, bool ADAPTIVE>
 __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_kernel(const FilterParams prm) {
   using VF = typename M::VF;
   constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= prm.n) return;
+  const long long lid_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lid_ >= prm.count) return;
+  const long long tid = prm.first + lid_;
   const long long n = prm.n;
   const CtrlParams& K = prm.K;
   const int diffusion = prm.diffusion;

@@ -10,7 +10,7 @@ namespace pnde {
 template <class M>
 cudaError_t launch_filter_t(const ModelOps*, const FilterParams& prm, bool adaptive, cudaStream_t s) {
   const int block = PNDE_FILTER_BLOCK;
-  const long long grid = (prm.n + block - 1) / block;
+  const long long grid = (prm.count + block - 1) / block;
   if (adaptive)
     filter_kernel<M, true><<<(unsigned)grid, block, 0, s>>>(prm);
   else

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,9 @@ struct pnde_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;  // pnde_solve_ensemble_to_host: device-to-host copies of finished slices
+  cudaStream_t stream2 = nullptr;      // ... and the second compute stream of its slices
+  cudaEvent_t slice_ev[3] = {nullptr, nullptr, nullptr};
   IwpConsts C;
   long long n = 0;
   long long max_saved = 0;
@@ -355,6 +359,11 @@ int pnde_destroy(pnde_handle* h) {
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) {
+    cudaStreamDestroy(h->copy_stream);
+    cudaStreamDestroy(h->stream2);
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(h->slice_ev[i]);
+  }
   if (h->owns_ops) rtc_destroy(h->ops);
   delete h;
   return PNDE_OK;
@@ -419,14 +428,12 @@ int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* 
   return PNDE_OK;
 }
 
-int pnde_run(pnde_handle* h) {
-  if (!h) return PNDE_ERR_ARG;
-  if (h->n <= 0) return h->fail(PNDE_ERR_STATE, "pnde_run: nothing uploaded");
-  CK(cudaSetDevice(h->device), "cudaSetDevice");
+static void fill_filter_params(pnde_handle* h, FilterParams& fp) {
   const pnde_config& c = h->cfg;
-  FilterParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.n = h->n;
+  fp.first = 0;
+  fp.count = h->n;
   fp.u0 = h->u0.as<double>();
   fp.p = h->p.as<double>();
   fp.mean = h->mean.as<double>();
@@ -462,6 +469,15 @@ int pnde_run(pnde_handle* h) {
   fp.K.dtmin = c.dtmin;
   fp.K.dtmax = c.dtmax;
   fp.K.maxiters = c.maxiters;
+}
+
+int pnde_run(pnde_handle* h) {
+  if (!h) return PNDE_ERR_ARG;
+  if (h->n <= 0) return h->fail(PNDE_ERR_STATE, "pnde_run: nothing uploaded");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const pnde_config& c = h->cfg;
+  FilterParams fp;
+  fill_filter_params(h, fp);
   CK(cudaEventRecord(h->ev[0], h->stream), "event record");
   if (h->lorenz && c.alg == PNDE_ALG_EK1) {
     cudaError_t e = h->bigwork.ensure(big::big_work_bytes(h->d, c.order));
@@ -609,6 +625,64 @@ int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const 
     if (rc != PNDE_OK) return rc;
   }
   return pnde_synchronize(h);
+}
+
+// Pipelined variant of solve + get_final for the thread-per-trajectory models: the ensemble is cut into slices;
+// the device-to-host copy of slice k (auxiliary stream) overlaps the filter kernel of slice k+1.
+int pnde_solve_ensemble_to_host(pnde_handle* h, int64_t n_traj, const double* u0, const double* p, double* mean,
+                                double* cov, double* t_final, double* loglik) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ops || h->cfg.smooth || h->cfg.save_mode != PNDE_SAVE_FINAL) {
+    // models without slices (Lorenz-96 paths) or runs that keep history: plain sequence
+    int rc = pnde_solve_ensemble(h, n_traj, u0, p);
+    if (rc != PNDE_OK) return rc;
+    return pnde_get_final(h, mean, cov, t_final, loglik);
+  }
+  int rc = pnde_upload(h, n_traj, u0, p);
+  if (rc != PNDE_OK) return rc;
+  if (!h->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), "copy stream");
+    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking), "second compute stream");
+    for (int i = 0; i < 3; ++i) CK(cudaEventCreateWithFlags(&h->slice_ev[i], cudaEventDisableTiming), "slice event");
+  }
+  FilterParams fp;
+  fill_filter_params(h, fp);
+  const long long n = h->n;
+  const int nslices = n >= 65536 ? 8 : 1;
+  const long long per = ((n + nslices - 1) / nslices + 127) / 128 * 128;
+  CK(cudaEventRecord(h->ev[0], h->stream), "event record");
+  // slices alternate between two compute streams so that the tail wave of one slice is filled by the next
+  CK(cudaEventRecord(h->slice_ev[2], h->stream), "upload event");
+  CK(cudaStreamWaitEvent(h->stream2, h->slice_ev[2], 0), "upload wait");
+  long long launches = 0;
+  for (int k = 0; k < nslices; ++k) {
+    const long long lo = k * per, hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    cudaStream_t cs = (k & 1) ? h->stream2 : h->stream;
+    fp.first = lo;
+    fp.count = hi - lo;
+    CK(h->ops->launch_filter(h->ops, fp, h->cfg.adaptive != 0, cs), "filter kernel launch");
+    ++launches;
+    CK(cudaEventRecord(h->slice_ev[k & 1], cs), "slice event record");
+    CK(cudaStreamWaitEvent(h->copy_stream, h->slice_ev[k & 1], 0), "slice wait");
+    const size_t w = (size_t)(hi - lo) * 8, pitch = (size_t)n * 8;
+    if (mean)
+      CK(cudaMemcpy2DAsync(mean + lo, pitch, h->mean.as<double>() + lo, pitch, w, h->D, cudaMemcpyDeviceToHost, h->copy_stream), "D2H mean");
+    if (cov)
+      CK(cudaMemcpy2DAsync(cov + lo, pitch, h->cov.as<double>() + lo, pitch, w, h->ncov, cudaMemcpyDeviceToHost, h->copy_stream), "D2H cov");
+    if (t_final) CK(cudaMemcpyAsync(t_final + lo, h->t_final.as<double>() + lo, w, cudaMemcpyDeviceToHost, h->copy_stream), "D2H t");
+    if (loglik) CK(cudaMemcpyAsync(loglik + lo, h->loglik.as<double>() + lo, w, cudaMemcpyDeviceToHost, h->copy_stream), "D2H loglik");
+  }
+  CK(cudaEventRecord(h->slice_ev[2], h->stream2), "join event");
+  CK(cudaStreamWaitEvent(h->stream, h->slice_ev[2], 0), "join wait");
+  CK(cudaEventRecord(h->ev[1], h->stream), "event record");
+  h->launches = launches;
+  h->ran = true;
+  h->smoothed = false;
+  h->smooth_ms = 0.0;
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  CK(cudaStreamSynchronize(h->copy_stream), "copy stream synchronize");
+  return PNDE_OK;
 }
 
 static int fetch_i32(pnde_handle* h, const DevBuf& b, std::vector<int>& out) {

@@ -605,3 +605,21 @@ def test_randomized_option_sweep(case):
         ref = O.dense_eval(so, float(tt))
         assert rel(dg.mu[i], ref.mu) < 1e-6
         assert rel(np.diag(dg.Sigma[i]), np.diag(ref.Sigma.mat)) < 1e-3 + 10 * cov_tol(q, 0)
+
+
+def test_pipelined_solve_to_host_equals_plain_path():
+    """pnde_solve_ensemble_to_host (sliced kernel launches + overlapped D2H) is bitwise the plain sequence."""
+    import odefilters_b200 as B
+
+    n = 70001  # > 65536: eight slices, ragged last slice
+    rng = np.random.default_rng(5)
+    P = np.stack([rng.uniform(0.1, 0.3, n), rng.uniform(0.1, 0.3, n), rng.uniform(2, 4, n)], axis=1)
+    U = np.tile([-1.0, 1.0], (n, 1))
+    prob = B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 0.5), P[0])
+    a = B.FilterSolver(prob, B.EK1(order=3, smooth=False), adaptive=False, dt=0.01, save_everystep=False)
+    a.solve_ensemble(U, P)
+    ma, ca, ta, la = a.final()
+    b = B.FilterSolver(prob, B.EK1(order=3, smooth=False), adaptive=False, dt=0.01, save_everystep=False)
+    mb, cb, tb, lb = b.solve_to_host(U, P)
+    assert np.array_equal(ma, mb) and np.array_equal(ca, cb) and np.array_equal(ta, tb) and np.array_equal(la, lb)
+    assert np.all(b.counts()["naccept"] == 50)
