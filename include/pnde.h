@@ -88,7 +88,7 @@ extern "C" {
 typedef struct pnde_config {
   int32_t abi_version; /* PNDE_ABI_VERSION */
   int32_t alg;         /* PNDE_ALG_* */
-  int32_t order;       /* q, src/algorithms.jl:25 */
+  int32_t order;       /* q, src/algorithms.jl:25; 1..7 (1..5 built ahead of time, 6..7 compiled on demand via NVRTC) */
   int32_t d;           /* ODE dimension (fixed by the vector field except Lorenz-96) */
   int32_t vf_kind;     /* PNDE_VF_* */
   int32_t diffusion;   /* PNDE_DIFF_* */

@@ -164,6 +164,7 @@ struct CustomVf {
 };
 
 static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf* custom) {
+  CustomVf catalogue_rtc = {0, 0, nullptr, nullptr};
   if (!cfg || !out) {
     g_create_error = "null argument";
     return PNDE_ERR_ARG;
@@ -177,8 +178,8 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
     g_create_error = "alg must be PNDE_ALG_EK0 or PNDE_ALG_EK1";
     return PNDE_ERR_ARG;
   }
-  if (cfg->order < 1 || cfg->order > 5) {
-    g_create_error = "order must be in 1..5 for the built-in kernels";
+  if (cfg->order < 1 || cfg->order > QMAX) {
+    g_create_error = "order must be in 1..7";
     return PNDE_ERR_UNSUPPORTED;
   }
   if (cfg->diffusion < 0 || cfg->diffusion > 4) {
@@ -223,6 +224,9 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
     } else if (cfg->d < 4 || cfg->d > 8 * LORENZ_THREADS) {
       g_create_error = "Lorenz-96: d must be in 4..2048";
       return PNDE_ERR_ARG;
+    } else if (cfg->order > 5) {
+      g_create_error = "Lorenz-96 EK0: orders 1..5 are built";
+      return PNDE_ERR_UNSUPPORTED;
     }
     if (mv) {
       g_create_error = "Lorenz-96: MV diffusion models are not built for the large-d path";
@@ -240,10 +244,22 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
   } else {
     ops = find_ops(cfg->vf_kind, cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV);
     if (!ops) {
-      g_create_error = "no built-in kernel for this (vf_kind, alg, order)";
-      return PNDE_ERR_UNSUPPORTED;
-    }
-    if (cfg->d != 0 && cfg->d != ops->d) {
+      // orders 6 and 7 of the catalogue are not instantiated at build time: compile them on demand (NVRTC)
+      static const struct { int kind, d, np; const char* name; } cat[] = {
+          {PNDE_VF_FHN_README, 2, 3, "@catalogue:VfFhnReadme"}, {PNDE_VF_FHN_LIB, 2, 4, "@catalogue:VfFhnLib"},
+          {PNDE_VF_LOTKA_VOLTERRA, 2, 4, "@catalogue:VfLotkaVolterra"}, {PNDE_VF_VANDERPOL, 2, 1, "@catalogue:VfVanDerPol"},
+          {PNDE_VF_LINEAR2, 2, 2, "@catalogue:VfLinear2"}, {PNDE_VF_LOGISTIC, 1, 1, "@catalogue:VfLogistic"},
+          {PNDE_VF_LINEAR1, 1, 1, "@catalogue:VfLinear1"}};
+      for (const auto& e : cat)
+        if (e.kind == cfg->vf_kind) {
+          catalogue_rtc = {e.d, e.np, e.name, nullptr};
+          custom = &catalogue_rtc;
+        }
+      if (!custom) {
+        g_create_error = "no built-in kernel for this (vf_kind, alg, order)";
+        return PNDE_ERR_UNSUPPORTED;
+      }
+    } else if (cfg->d != 0 && cfg->d != ops->d) {
       g_create_error = "d does not match the vector field";
       return PNDE_ERR_ARG;
     }

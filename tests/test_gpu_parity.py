@@ -623,3 +623,29 @@ def test_pipelined_solve_to_host_equals_plain_path():
     mb, cb, tb, lb = b.solve_to_host(U, P)
     assert np.array_equal(ma, mb) and np.array_equal(ca, cb) and np.array_equal(ta, tb) and np.array_equal(la, lb)
     assert np.all(b.counts()["naccept"] == 50)
+
+
+@pytest.mark.parametrize("kind", ["EK0", "EK1"])
+def test_order_six_compiled_on_demand(kind):
+    """test/correctness.jl:42-71 uses q = 6 with adaptive steps.  Orders 6 and 7 are not instantiated at build
+    time; the catalogue field is compiled on demand through NVRTC into the same kernel templates."""
+    import time
+
+    import odefilters_b200 as B
+
+    t0 = time.time()
+    so = oracle_solve("lotka_volterra", O.Alg(kind, 6, "dynamic", False), tspan=(0.0, 1.0))
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=6, smooth=False)
+    sg = gpu_solve("lotka_volterra", alg, tspan=(0.0, 1.0))
+    print("order 6", kind, "compile+solve", round(time.time() - t0, 1), "s")
+    assert sg.retcode == "Success" and sg.t[-1] == 1.0
+    # q = 6: the FP64 noise floor moves individual accept/reject decisions (cf. the mpmath arbiter)
+    assert abs(sg.destats["naccept"] - so.naccept) <= 2 and abs(sg.destats["nreject"] - so.nreject) <= 2
+    assert rel(sg.u[-1], so.x_filt[-1].mu[:2]) < 1e-5
+    # accuracy gate of the reference's test: rtol 1e-3 against a tight reference solution
+    u = np.array([1.0, 1.0]); h = 1e-4
+    f = lambda x: np.array([1.5 * x[0] - x[0] * x[1], -3.0 * x[1] + x[0] * x[1]])
+    for _ in range(10000):
+        k1 = f(u); k2 = f(u + h / 2 * k1); k3 = f(u + h / 2 * k2); k4 = f(u + h * k3)
+        u = u + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+    assert np.allclose(sg.u[-1], u, rtol=1e-3)
