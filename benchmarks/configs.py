@@ -84,6 +84,21 @@ def config4(d=1024):
             "note": "latency bound (one sequential chain, 3 block syncs per step)"}
 
 
+def config2_ek0(n=1_000_000):
+    """Not a BASELINE config: the headline workload with EK0 (Kronecker covariance) for comparison."""
+    rng = np.random.default_rng(SEED)
+    p = np.stack([rng.uniform(0.1, 0.3, n), rng.uniform(0.1, 0.3, n), rng.uniform(2.0, 4.0, n)], axis=1)
+    prob = B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 20.0), (0.2, 0.2, 3.0))
+    s = B.FilterSolver(prob, B.EK0(order=3, smooth=False), adaptive=False, dt=0.01, save_everystep=False)
+    s.upload(np.tile([-1.0, 1.0], (n, 1)), p)
+    for _ in range(3):
+        s.run()
+    ms = s.last_run_ms()[0]
+    steps = int(s.counts()["naccept"].sum())
+    return {"config": "2-EK0", "what": "FHN sweep, EK0(order=3) Kronecker, dt=0.01, 2000 steps, final state", "n": n,
+            "ms": ms, "steps_per_s": steps / (ms * 1e-3)}
+
+
 def config4_ek1(d=1024, nsteps=20):
     rng = np.random.default_rng(SEED)
     u0 = 8.0 + 0.01 * rng.standard_normal(d)
@@ -109,6 +124,6 @@ if __name__ == "__main__":
     ap.add_argument("--n3", type=int, default=100000)
     ap.add_argument("--n5", type=int, default=250000)
     a = ap.parse_args()
-    for fn, arg in ((config1, None), (config3, a.n3), (config4, 1024), (config4_ek1, 1024), (config5, a.n5)):
+    for fn, arg in ((config1, None), (config2_ek0, 1_000_000), (config3, a.n3), (config4, 1024), (config4_ek1, 1024), (config5, a.n5)):
         out = fn() if arg is None else fn(arg)
         print(json.dumps(out), flush=True)

@@ -88,6 +88,7 @@ struct DenseEK1 {
   static constexpr bool IS_EK1 = true;
   using Fac = Factor<d, q>;
   static constexpr int REC = 1 + ND + D + Fac::LEN;  // t, diffusion, mean, factor
+  static constexpr int STATE_LEN = D + Fac::LEN;
 
   struct State {
     double m[D];
@@ -239,6 +240,7 @@ struct KronEK0 {
   static constexpr int ND = d;              // diffusion slots (scalar models use slot 0, MV all)
   using Fac = Factor<1, q>;
   static constexpr int REC = 1 + ND + D + NF * Fac::LEN;
+  static constexpr int STATE_LEN = D + NF * Fac::LEN;
 
   struct State {
     double m[D];
@@ -420,6 +422,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
 #pragma unroll
   for (int i = 0; i < d; ++i) u0[i] = prm.u0[(long long)i * n + tid];
 
+  extern __shared__ double stash[];  // ADAPTIVE only: STATE_LEN x blockDim doubles
   typename M::State st;  // natural coordinates between steps when ADAPTIVE, P(hcur) coordinates otherwise
   taylor_init<VF, q>(u0, p, st.m);
   if constexpr (M::IS_EK1) {
@@ -504,9 +507,10 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
       break;
     }
     // ---- perform_step! ----
-    typename M::State old;
     if (ADAPTIVE) {
-      old = st;
+      // the pre-step state is parked in shared memory ([element][thread], conflict free) instead of a second
+      // register copy; it is only read back when the step is rejected
+      M::store(st, stash + threadIdx.x, blockDim.x);
       precond_scales<q>(dt, Pk, PIk);
       M::scale(st, Pk);  // x = P * x   (src/perform_step.jl:38)
     } else if (dt != hcur) {
@@ -571,7 +575,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
       if (commit) {
         M::scale(st, PIk);  // PI * x_filt (:75)
       } else {
-        st = old;
+        M::load(st, stash + threadIdx.x, blockDim.x);
       }
     }
     if (commit) {

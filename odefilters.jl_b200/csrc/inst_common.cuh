@@ -11,9 +11,15 @@ template <class M>
 cudaError_t launch_filter_t(const ModelOps*, const FilterParams& prm, bool adaptive, cudaStream_t s) {
   const int block = PNDE_FILTER_BLOCK;
   const long long grid = (prm.count + block - 1) / block;
-  if (adaptive)
-    filter_kernel<M, true><<<(unsigned)grid, block, 0, s>>>(prm);
-  else
+  if (adaptive) {
+    // shared-memory stash of the pre-step state (read back on rejection)
+    const size_t smem = (size_t)M::STATE_LEN * block * sizeof(double);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(filter_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    filter_kernel<M, true><<<(unsigned)grid, block, smem, s>>>(prm);
+  } else
     filter_kernel<M, false><<<(unsigned)grid, block, 0, s>>>(prm);
   return cudaGetLastError();
 }
