@@ -48,6 +48,10 @@ extern "C" {
 /* algorithms: src/algorithms.jl:23-51 */
 #define PNDE_ALG_EK0 0
 #define PNDE_ALG_EK1 1
+/* Iterated extended Kalman smoother, src/ieks.jl:2-61: an EK1 solve repeated `ieks_iterations` times, the Jacobian
+ * of every iterate evaluated at the dense output sol(t + dt) of the previous one (src/perform_step.jl:111-113).
+ * Needs smooth = 1 and PNDE_SAVE_EVERY; its kernels are compiled at create time through NVRTC. */
+#define PNDE_ALG_IEKS 2
 
 /* diffusion models: src/caches.jl:89-96 / src/diffusions.jl */
 #define PNDE_DIFF_DYNAMIC 0
@@ -97,7 +101,7 @@ typedef struct pnde_config {
   int32_t save_mode;   /* PNDE_SAVE_* */
   int32_t save_stride; /* for PNDE_SAVE_STRIDE */
   int32_t device;      /* CUDA device ordinal, -1 = current device */
-  int32_t reserved0;
+  int32_t ieks_iterations; /* PNDE_ALG_IEKS: re-solves per pnde_solve_ensemble (<= 0: 10, src/ieks.jl:54) */
   double abstol, reltol; /* defaults 1e-6 / 1e-3 (OrdinaryDiffEq) */
   double dt;             /* fixed step, or initial step when adaptive (<= 0: Hairer initdt) */
   double t0, t1;
@@ -140,7 +144,8 @@ int64_t pnde_cov_len(const pnde_handle* h);      /* rows of pnde_get_final's cov
                                                     the Lorenz-96 Kronecker path (Sigma = Ctilde (x) I_d) */
 
 /* One call = one EnsembleProblem solve: host buffers in, results kept on the device.
- * u0: [d][n_traj], p: [n_params][n_traj].  Equivalent to pnde_upload + pnde_run (+ pnde_smooth). */
+ * u0: [d][n_traj], p: [n_params][n_traj].  Equivalent to pnde_upload + pnde_run (+ pnde_smooth);
+ * PNDE_ALG_IEKS: pnde_upload + ieks_iterations x (pnde_run + pnde_smooth)  (solve_ieks, src/ieks.jl:53-61). */
 int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const double* p);
 
 /* pnde_solve_ensemble + pnde_get_final in one call, pipelined: the ensemble is processed in slices and the
@@ -152,7 +157,9 @@ int pnde_solve_ensemble_to_host(pnde_handle* h, int64_t n_traj, const double* u0
 
 /* Split form, so that inputs can stay resident in HBM across runs. */
 int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* p);
-int pnde_run(pnde_handle* h);         /* initialize! + the whole solve! loop, asynchronous */
+int pnde_run(pnde_handle* h);         /* initialize! + the whole solve! loop, asynchronous.  PNDE_ALG_IEKS: every
+                                         pnde_run after the first one since pnde_upload linearises at the solution
+                                         of the previous pnde_run + pnde_smooth pair (which it keeps on the device) */
 int pnde_synchronize(pnde_handle* h); /* wait for the handle's stream */
 /* device time (ms, CUDA events on the handle's stream) of the last pnde_run / pnde_smooth */
 int pnde_last_run_ms(pnde_handle* h, double* filter_ms, double* smooth_ms);

@@ -18,13 +18,15 @@ from .api import (  # noqa: F401
     EnsembleSolution,
     FilterSolver,
     Gaussian,
+    IEKS,
     ODEProblem,
     ProbODESolution,
     SRMatrix,
     shard_range,
     solve,
+    solve_ieks,
 )
 from . import _lib  # noqa: F401
 
 __all__ = ["CustomVectorField", "EK0", "EK1", "EnsembleB200", "EnsembleProblem", "EnsembleSolution", "FilterSolver", "Gaussian",
-           "ODEProblem", "ProbODESolution", "SRMatrix", "shard_range", "solve"]
+           "IEKS", "ODEProblem", "ProbODESolution", "SRMatrix", "shard_range", "solve", "solve_ieks"]

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PNDE_LIB") or os.path.join(_HERE, "libpnde.so")  # PNDE_LIB: experiment builds
 
 ABI_VERSION = 1
-ALG_EK0, ALG_EK1 = 0, 1
+ALG_EK0, ALG_EK1, ALG_IEKS = 0, 1, 2
 DIFFUSIONS = {"dynamic": 0, "fixed": 1, "fixedMAP": 2, "dynamicMV": 3, "fixedMV": 4}
 VF_KINDS = {"fhn_readme": 0, "fhn_lib": 1, "lotka_volterra": 2, "vanderpol": 3, "linear2": 4, "logistic": 5,
             "lorenz96": 6, "linear1": 7, "custom": 100}
@@ -24,7 +24,7 @@ class PndeConfig(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("alg", C.c_int32), ("order", C.c_int32), ("d", C.c_int32),
         ("vf_kind", C.c_int32), ("diffusion", C.c_int32), ("smooth", C.c_int32), ("adaptive", C.c_int32),
-        ("save_mode", C.c_int32), ("save_stride", C.c_int32), ("device", C.c_int32), ("reserved0", C.c_int32),
+        ("save_mode", C.c_int32), ("save_stride", C.c_int32), ("device", C.c_int32), ("ieks_iterations", C.c_int32),
         ("abstol", C.c_double), ("reltol", C.c_double), ("dt", C.c_double), ("t0", C.c_double), ("t1", C.c_double),
         ("qmin", C.c_double), ("qmax", C.c_double), ("gamma", C.c_double), ("qsteady_min", C.c_double),
         ("qsteady_max", C.c_double), ("qoldinit", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),

@@ -26,6 +26,7 @@ class _EK:
     smooth: bool = True
     prior: str = "ibm"
     kind: int = L.ALG_EK1
+    iterations: int = 0  # IEKS only (set by solve_ieks)
 
     def __post_init__(self):
         if self.prior != "ibm":
@@ -42,6 +43,12 @@ def EK0(order: int = 3, diffusionmodel: str = "dynamic", smooth: bool = True, pr
 def EK1(order: int = 3, diffusionmodel: str = "dynamic", smooth: bool = True, prior: str = "ibm") -> _EK:
     """Gaussian ODE filtering with first order extended Kalman filtering (src/algorithms.jl:46-51)."""
     return _EK(order, diffusionmodel, smooth, prior, L.ALG_EK1)
+
+
+def IEKS(order: int = 1, diffusionmodel: str = "dynamic", prior: str = "ibm") -> _EK:
+    """Gaussian ODE filtering with iterated extended Kalman smoothing (src/ieks.jl:10-41): use ``solve_ieks``.
+    ``smooth`` is always on.  Every iterate is an EK1 solve linearised at the previous iterate's dense output."""
+    return _EK(order, diffusionmodel, True, prior, L.ALG_IEKS)
 
 
 @dataclass(frozen=True)
@@ -283,6 +290,7 @@ class FilterSolver:
         cfg.save_mode = L.SAVE_EVERY if save_everystep else (L.SAVE_STRIDE if save_stride else L.SAVE_FINAL)
         cfg.save_stride = int(save_stride or 1)
         cfg.device = device
+        cfg.ieks_iterations = int(alg.iterations)
         cfg.abstol, cfg.reltol = float(abstol), float(reltol)
         cfg.dt = float(dt) if dt is not None else 0.0
         cfg.t0, cfg.t1 = float(prob.tspan[0]), float(prob.tspan[1])
@@ -514,6 +522,15 @@ def _ensemble_arrays(eprob: EnsembleProblem, trajectories: Optional[int]):
     u0 = np.broadcast_to(prob.u0, (n, len(prob.u0))) if eprob.u0 is None else np.asarray(eprob.u0, dtype=np.float64)[:n]
     p = np.broadcast_to(prob.p, (n, len(prob.p))) if eprob.p is None else np.asarray(eprob.p, dtype=np.float64)[:n]
     return u0, p, n
+
+
+def solve_ieks(prob, alg: _EK, *args, iterations: int = 10, **kwargs):
+    """solve_ieks(prob, IEKS(...); iterations=10, kwargs...) (src/ieks.jl:44-61): a fixed number of re-solves, no
+    stopping criterion; all iterates run on the device inside one ``pnde_solve_ensemble`` call."""
+    if alg.kind != L.ALG_IEKS:
+        raise ValueError("solve_ieks needs an IEKS algorithm")
+    from dataclasses import replace
+    return solve(prob, replace(alg, iterations=int(iterations)), *args, **kwargs)
 
 
 def solve(prob, alg: _EK, ensemblealg: Optional[EnsembleB200] = None, *, trajectories: Optional[int] = None,

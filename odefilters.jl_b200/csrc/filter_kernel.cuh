@@ -32,6 +32,17 @@ struct CtrlParams {
   long long maxiters;
 };
 
+// IEKS (src/ieks.jl, src/perform_step.jl:111-113): the previous iterate's filtered + smoothed history, whose dense
+// output sol(t + dt) is where the Jacobian of the current iterate is evaluated.  hist == nullptr: first iterate.
+struct LinParams {
+  const double* hist;
+  const double* smooth;
+  const int* n_saved;
+  const double* final_diff;
+  long long max_saved;
+  int calibrate, is_mv;
+};
+
 struct FilterParams {
   long long n;       // trajectories in the ensemble = stride of every structure-of-arrays buffer
   long long first;   // this launch handles trajectories [first, first + count) (pipelined host transfers)
@@ -54,6 +65,12 @@ struct FilterParams {
   int save_mode, save_stride, diffusion;
   IwpConsts C;
   CtrlParams K;
+  LinParams lin;
+};
+
+// Linearisation-point policy of filter_kernel: the default evaluates J at the predicted mean (EK1).
+struct NoLin {
+  static constexpr bool enabled = false;
 };
 
 // P(h) block scales h^(k-q-1/2) (src/preconditioning.jl:4-13) and their inverses.
@@ -106,13 +123,14 @@ struct DenseEK1 {
   // kernel accumulates without a per-step log.
   __device__ __forceinline__ static void step(State& s, const double* p, double pi0, double pi1, double ipi1,
                                               int diffusion, const IwpConsts& C, double (&u_new)[d], double (&err)[d],
-                                              double (&local)[ND], double& quad, double& detS) {
+                                              double (&local)[ND], double& quad, double& detS,
+                                              const double* ulin = nullptr) {
     apply_A<d, q>(s.m);  // predict_mean!  src/filtering.jl:22-25
     double uhat[d], fu[d], J[d][d], Jp[d][d], z[d];
 #pragma unroll
     for (int i = 0; i < d; ++i) uhat[i] = pi0 * s.m[i];  // src/perform_step.jl:44
     VF::template f<double>(uhat, p, fu);                  // :106
-    VF::jac(uhat, p, J);                                  // :116-122
+    VF::jac(ulin ? ulin : uhat, p, J);                    // :111-122 (IEKS: at the previous iterate's sol(t))
 #pragma unroll
     for (int i = 0; i < d; ++i) {
       z[i] = fma(pi1, s.m[d + i], -fu[i]);  // :108
@@ -256,7 +274,8 @@ struct KronEK0 {
 
   __device__ __forceinline__ static void step(State& s, const double* p, double pi0, double pi1, double ipi1,
                                               int diffusion, const IwpConsts& C, double (&u_new)[d], double (&err)[d],
-                                              double (&local)[ND], double& quad, double& detS) {
+                                              double (&local)[ND], double& quad, double& detS,
+                                              const double* = nullptr) {
     apply_A<d, q>(s.m);
     double uhat[d], fu[d], z[d];
 #pragma unroll
@@ -403,7 +422,7 @@ __device__ __forceinline__ double initdt(const double* u0, const double* p, cons
 #ifndef PNDE_FILTER_BLOCK
 #define PNDE_FILTER_BLOCK 128
 #endif
-template <class M, bool ADAPTIVE>
+template <class M, bool ADAPTIVE, class LIN = NoLin>
 __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_kernel(const FilterParams prm) {
   using VF = typename M::VF;
   constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC;
@@ -528,7 +547,13 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
     double unew[d], err[d], local[ND], quad, detS;
 #pragma unroll
     for (int i = 0; i < ND; ++i) local[i] = 1.0;
-    M::step(st, p, PIk[0], PIk[1], Pk[1], diffusion, prm.C, unew, err, local, quad, detS);
+    if constexpr (LIN::enabled) {
+      double ulin[d];
+      const bool have = LIN::template point<M>(prm, tid, t + dt, ulin);
+      M::step(st, p, PIk[0], PIk[1], Pk[1], diffusion, prm.C, unew, err, local, quad, detS, have ? ulin : nullptr);
+    } else {
+      M::step(st, p, PIk[0], PIk[1], Pk[1], diffusion, prm.C, unew, err, local, quad, detS);
+    }
     ++nfe;
     // global diffusion (src/diffusions.jl): success_iter == number of accepted steps so far
     double gcur[ND];

@@ -88,6 +88,9 @@ struct pnde_handle {
   const ModelOps* ops = nullptr;  // nullptr for the CTA-per-trajectory Lorenz-96 path
   bool owns_ops = false;           // run-time compiled model (pnde_create_custom)
   bool lorenz = false;
+  bool ieks = false;       // PNDE_ALG_IEKS: cfg.alg is stored as EK1, the filter kernels carry the DenseLin policy
+  bool have_prev = false;  // ... and prev_* hold the previous iterate (linearisation points of the next pnde_run)
+  long long prev_max_saved = 0;
   int d = 0, D = 0, np = 0, nd = 1, ncov = 0;  // dimensions (from ops, or from cfg for Lorenz-96)
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -102,7 +105,7 @@ struct pnde_handle {
   double filter_ms = 0.0, smooth_ms = 0.0;
   long long launches = 0;
   DevBuf u0, p, mean, cov, t_final, loglik, final_diff, retcode, naccept, nreject, nf, njacs, n_saved, hist, smooth,
-      sstatus, scratch_off, scratch_out, bigwork;
+      sstatus, scratch_off, scratch_out, bigwork, prev_hist, prev_smooth, prev_n_saved, prev_final_diff;
   std::string err;
 
   int fail(int code, const std::string& msg) {
@@ -163,7 +166,7 @@ struct CustomVf {
   const char* jac_body;
 };
 
-static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf* custom) {
+static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf* custom, bool as_ieks = false) {
   CustomVf catalogue_rtc = {0, 0, nullptr, nullptr};
   if (!cfg || !out) {
     g_create_error = "null argument";
@@ -174,9 +177,23 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
     g_create_error = "abi_version mismatch";
     return PNDE_ERR_ARG;
   }
-  if (cfg->alg != PNDE_ALG_EK0 && cfg->alg != PNDE_ALG_EK1) {
-    g_create_error = "alg must be PNDE_ALG_EK0 or PNDE_ALG_EK1";
+  if (cfg->alg != PNDE_ALG_EK0 && cfg->alg != PNDE_ALG_EK1 && cfg->alg != PNDE_ALG_IEKS) {
+    g_create_error = "alg must be PNDE_ALG_EK0, PNDE_ALG_EK1 or PNDE_ALG_IEKS";
     return PNDE_ERR_ARG;
+  }
+  const bool ieks = cfg->alg == PNDE_ALG_IEKS;
+  if (ieks) {
+    if (!cfg->smooth || cfg->save_mode != PNDE_SAVE_EVERY) {
+      g_create_error = "IEKS requires smooth = 1 and save_mode = PNDE_SAVE_EVERY (src/ieks.jl:38-40)";
+      return PNDE_ERR_ARG;
+    }
+    if (cfg->vf_kind == PNDE_VF_LORENZ96) {
+      g_create_error = "IEKS is not built for the large-d Lorenz-96 paths";
+      return PNDE_ERR_UNSUPPORTED;
+    }
+    pnde_config c2 = *cfg;  // everything below sees an EK1
+    c2.alg = PNDE_ALG_EK1;
+    return create_impl(&c2, out, custom, true);
   }
   if (cfg->order < 1 || cfg->order > QMAX) {
     g_create_error = "order must be in 1..7";
@@ -242,9 +259,10 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
       return PNDE_ERR_ARG;
     }
   } else {
-    ops = find_ops(cfg->vf_kind, cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV);
+    ops = as_ieks ? nullptr : find_ops(cfg->vf_kind, cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV);
     if (!ops) {
-      // orders 6 and 7 of the catalogue are not instantiated at build time: compile them on demand (NVRTC)
+      // orders 6 and 7 of the catalogue, and the IEKS flavour of every order, are not instantiated at build
+      // time: compile them on demand (NVRTC)
       static const struct { int kind, d, np; const char* name; } cat[] = {
           {PNDE_VF_FHN_README, 2, 3, "@catalogue:VfFhnReadme"}, {PNDE_VF_FHN_LIB, 2, 4, "@catalogue:VfFhnLib"},
           {PNDE_VF_LOTKA_VOLTERRA, 2, 4, "@catalogue:VfLotkaVolterra"}, {PNDE_VF_VANDERPOL, 2, 1, "@catalogue:VfVanDerPol"},
@@ -290,7 +308,7 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
     }
     std::string rerr;
     ops = rtc_build(cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV, custom->d, custom->np, custom->f_body,
-                    custom->jac_body, rerr);
+                    custom->jac_body, rerr, as_ieks);
     if (!ops) {
       g_create_error = rerr;
       return PNDE_ERR_ARG;
@@ -302,6 +320,7 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
   h->ops = ops;
   h->owns_ops = owns;
   h->lorenz = lorenz;
+  h->ieks = as_ieks;
   if (lorenz) {
     h->d = cfg->d;
     h->D = cfg->d * (cfg->order + 1);
@@ -355,7 +374,9 @@ int pnde_create_custom(const pnde_config* cfg, int32_t d, int32_t n_params, cons
 int pnde_check_custom(int32_t alg, int32_t order, int32_t diffusion, int32_t d, int32_t n_params, const char* f_body,
                       const char* jac_body, char* log, int64_t log_len) {
   std::string err;
-  const bool ok = rtc_check(alg, order, diffusion == PNDE_DIFF_DYNAMIC_MV, d, n_params, f_body, jac_body, err);
+  const bool ieks = alg == PNDE_ALG_IEKS;
+  const bool ok = rtc_check(ieks ? PNDE_ALG_EK1 : alg, order, diffusion == PNDE_DIFF_DYNAMIC_MV, d, n_params, f_body, jac_body,
+                            err, ieks);
   if (log && log_len > 0) {
     strncpy(log, err.c_str(), (size_t)log_len - 1);
     log[log_len - 1] = 0;
@@ -370,7 +391,7 @@ int pnde_destroy(pnde_handle* h) {
   DevBuf* bufs[] = {&h->u0,      &h->p,      &h->mean,  &h->cov,     &h->t_final, &h->loglik,
                     &h->final_diff, &h->retcode, &h->naccept, &h->nreject, &h->nf,      &h->njacs,
                     &h->n_saved, &h->hist,   &h->smooth, &h->sstatus, &h->scratch_off, &h->scratch_out,
-                    &h->bigwork};
+                    &h->bigwork, &h->prev_hist, &h->prev_smooth, &h->prev_n_saved, &h->prev_final_diff};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -441,6 +462,7 @@ int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* 
   h->n = n_traj;
   h->ran = false;
   h->smoothed = false;
+  h->have_prev = false;
   return PNDE_OK;
 }
 
@@ -492,8 +514,32 @@ int pnde_run(pnde_handle* h) {
   if (h->n <= 0) return h->fail(PNDE_ERR_STATE, "pnde_run: nothing uploaded");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   const pnde_config& c = h->cfg;
+  if (h->ieks && h->ran) {
+    // next IEKS iterate (src/ieks.jl:57-59): the solution so far becomes the linearisation trajectory
+    if (!h->smoothed)
+      return h->fail(PNDE_ERR_STATE, "IEKS: pnde_smooth the previous iterate before the next pnde_run (src/ieks.jl:38)");
+    std::swap(h->hist, h->prev_hist);
+    std::swap(h->smooth, h->prev_smooth);
+    std::swap(h->n_saved, h->prev_n_saved);
+    std::swap(h->final_diff, h->prev_final_diff);
+    h->prev_max_saved = h->max_saved;
+    CK(h->hist.ensure((size_t)h->n * (size_t)h->max_saved * h->ops->rec * 8), "alloc history (IEKS iterate)");
+    CK(h->n_saved.ensure((size_t)h->n * 4), "alloc n_saved");
+    CK(h->final_diff.ensure((size_t)h->n * h->nd * 8), "alloc final_diff");
+    h->have_prev = true;
+  }
   FilterParams fp;
   fill_filter_params(h, fp);
+  if (h->ieks && h->have_prev) {
+    fp.lin.hist = h->prev_hist.as<double>();
+    fp.lin.smooth = h->prev_smooth.as<double>();
+    fp.lin.n_saved = h->prev_n_saved.as<int>();
+    fp.lin.final_diff = h->prev_final_diff.as<double>();
+    fp.lin.max_saved = h->prev_max_saved;
+    const int df = c.diffusion;
+    fp.lin.calibrate = (df == PNDE_DIFF_FIXED || df == PNDE_DIFF_FIXED_MAP || df == PNDE_DIFF_FIXED_MV);
+    fp.lin.is_mv = 0;
+  }
   CK(cudaEventRecord(h->ev[0], h->stream), "event record");
   if (h->lorenz && c.alg == PNDE_ALG_EK1) {
     cudaError_t e = h->bigwork.ensure(big::big_work_bytes(h->d, c.order));
@@ -634,11 +680,14 @@ int64_t pnde_last_launch_count(const pnde_handle* h) { return h ? h->launches : 
 int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const double* p) {
   int rc = pnde_upload(h, n_traj, u0, p);
   if (rc != PNDE_OK) return rc;
-  rc = pnde_run(h);
-  if (rc != PNDE_OK) return rc;
-  if (h->cfg.smooth) {
-    rc = pnde_smooth(h);
+  const int iterations = h->ieks ? (h->cfg.ieks_iterations > 0 ? h->cfg.ieks_iterations : 10) : 1;
+  for (int it = 0; it < iterations; ++it) {
+    rc = pnde_run(h);
     if (rc != PNDE_OK) return rc;
+    if (h->cfg.smooth) {
+      rc = pnde_smooth(h);
+      if (rc != PNDE_OK) return rc;
+    }
   }
   return pnde_synchronize(h);
 }

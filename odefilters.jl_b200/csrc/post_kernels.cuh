@@ -231,28 +231,23 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams sp) {
   (void)status;
 }
 
-// one thread per (trajectory, query time)
+// Posterior N(mean, cov) of trajectory `tr` at time `tval` (src/solution.jl:165-215): the stored state on an exact
+// hit of the grid, otherwise a prediction from the left filtered neighbour, smoothed against the right smoothed
+// neighbour when dp.smoothed.  Shared by dense_kernel and the IEKS linearisation point (ieks_kernel.cuh).
 template <class M>
-__global__ void __launch_bounds__(128) dense_kernel(const DenseParams dp) {
+__device__ __forceinline__ void dense_state(const DenseParams& dp, long long tr, double tval, double (&mean)[M::D],
+                                            double (&cov)[M::D * (M::D + 1) / 2]) {
   using PT = PostTraits<M>;
   using SM = SmoothModel<M>;
   using SC = typename PT::SC;
   constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, SREC = SM::SREC, NF = PT::NF, DC = PT::DC,
                 DCOV = PT::DCOV, R = PT::R;
-  const long long ntr = dp.traj_end - dp.traj_begin;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= ntr * dp.n_t) return;
-  const long long it = gid / ntr;  // trajectory fastest: record loads coalesce for a common query time
-  const long long tr = dp.traj_begin + gid % ntr;
   const long long n = dp.n;
   const int ns = dp.n_saved[tr];
-  double* omean = dp.mean + ((tr - dp.traj_begin) * dp.n_t + it) * D;
-  double* ocov = dp.cov + ((tr - dp.traj_begin) * dp.n_t + it) * (D * (D + 1) / 2);
-  const double tval = dp.tq[it];
   auto rec = [&](int slot) { return dp.hist + ((long long)slot * REC) * n + tr; };
   if (ns <= 0 || tval < rec(0)[0]) {  // "Invalid t<t0" (src/solution.jl:169-171): NaN, data not an exception
-    for (int i = 0; i < D; ++i) omean[i] = nan("");
-    for (int i = 0; i < D * (D + 1) / 2; ++i) ocov[i] = nan("");
+    for (int i = 0; i < D; ++i) mean[i] = nan("");
+    for (int i = 0; i < D * (D + 1) / 2; ++i) cov[i] = nan("");
     return;
   }
   // idx = number of saved times <= tval (binary search), prev = idx - 1
@@ -270,7 +265,6 @@ __global__ void __launch_bounds__(128) dense_kernel(const DenseParams dp) {
   for (int a = 0; a < d; ++a)
     dimscale[a] = (dp.calibrate && !M::IS_EK1) ? (dp.is_mv ? gfin[a < ND ? a : 0] : gfin[0]) : 1.0;
   const double dense_cal = (dp.calibrate && M::IS_EK1) ? sqrt(gfin[0]) : 1.0;
-  double mean[D], cov[D * (D + 1) / 2];
   if (rec(prev)[0] == tval) {  // exact hit: the stored state (src/solution.jl:172-176)
     if (dp.smoothed) {
       SM::load_cov(dp.smooth + ((long long)prev * SREC) * n + tr, n, mean, cov);
@@ -403,6 +397,21 @@ __global__ void __launch_bounds__(128) dense_kernel(const DenseParams dp) {
         cov[i * (i + 1) / 2 + j] = acc;
       }
   }
+}
+
+// one thread per (trajectory, query time)
+template <class M>
+__global__ void __launch_bounds__(128) dense_kernel(const DenseParams dp) {
+  constexpr int D = M::D;
+  const long long ntr = dp.traj_end - dp.traj_begin;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= ntr * dp.n_t) return;
+  const long long it = gid / ntr;  // trajectory fastest: record loads coalesce for a common query time
+  const long long tr = dp.traj_begin + gid % ntr;
+  double* omean = dp.mean + ((tr - dp.traj_begin) * dp.n_t + it) * D;
+  double* ocov = dp.cov + ((tr - dp.traj_begin) * dp.n_t + it) * (D * (D + 1) / 2);
+  double mean[D], cov[D * (D + 1) / 2];
+  dense_state<M>(dp, tr, dp.tq[it], mean, cov);
   for (int i = 0; i < D; ++i) omean[i] = mean[i];
   for (int i = 0; i < D * (D + 1) / 2; ++i) ocov[i] = cov[i];
 }

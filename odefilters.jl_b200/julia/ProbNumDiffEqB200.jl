@@ -30,7 +30,7 @@ Base.@kwdef mutable struct PndeConfig
     save_mode::Int32 = 0
     save_stride::Int32 = 1
     device::Int32 = -1
-    reserved0::Int32 = 0
+    ieks_iterations::Int32 = 0
     abstol::Float64 = 1e-6
     reltol::Float64 = 1e-3
     dt::Float64 = 0.0

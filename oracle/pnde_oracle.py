@@ -749,6 +749,7 @@ class Alg:
     order: int = 3
     diffusionmodel: str = "dynamic"
     smooth: bool = True
+    linearize_at: object = None  # IEKS only: the previous iteration's Solution (src/ieks.jl:2-8)
 
 
 def EK0(order=3, diffusionmodel="dynamic", smooth=True):
@@ -757,6 +758,22 @@ def EK0(order=3, diffusionmodel="dynamic", smooth=True):
 
 def EK1(order=3, diffusionmodel="dynamic", smooth=True):
     return Alg("EK1", order, diffusionmodel, smooth)
+
+
+def IEKS(order=1, diffusionmodel="dynamic", linearize_at=None):
+    """src/ieks.jl:32-41: an EK1 whose Jacobian is evaluated at the previous iterate's dense output; smooth is forced on."""
+    if linearize_at is not None:
+        assert linearize_at.q == order and linearize_at.smoothed
+    return Alg("EK1", order, diffusionmodel, True, linearize_at)
+
+
+def solve_ieks(prob, alg: "Alg", iterations=10, **kwargs):
+    """src/ieks.jl:53-61: fixed number of re-solves, each linearised at the previous solution; no stopping rule."""
+    sol = None
+    for _ in range(iterations):
+        alg.linearize_at = sol
+        sol = solve_ivp(prob, alg, **kwargs)
+    return sol
 
 
 @dataclass
@@ -856,7 +873,9 @@ def measure(cache: _Cache, prob: Problem, alg: Alg, x_pred: Gaussian, PI, t, sol
     sol.nf += 1
     z = cache.E1 @ (PI * x_pred.mu) - du
     if alg.kind == "EK1":
-        ddu = np.array(prob.vf.jac(list(cache.u_pred), prob.p, t), dtype=cache.dtype if cache.dtype is object else float)
+        # IEKS: J at the previous solution's sol(t).mu, f still at u_pred (src/perform_step.jl:111-113, 116)
+        lin = cache.u_pred if alg.linearize_at is None else dense_eval(alg.linearize_at, t).mu
+        ddu = np.array(prob.vf.jac(list(lin), prob.p, t), dtype=cache.dtype if cache.dtype is object else float)
         sol.njacs += 1
         H = (cache.E1 - ddu @ cache.E0) * PI[None, :]
     else:

@@ -649,3 +649,65 @@ def test_order_six_compiled_on_demand(kind):
         k1 = f(u); k2 = f(u + h / 2 * k1); k3 = f(u + h / 2 * k2); k4 = f(u + h * k3)
         u = u + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
     assert np.allclose(sg.u[-1], u, rtol=1e-3)
+
+
+@pytest.mark.parametrize("name,q,diffusion,adaptive,iterations", [
+    ("fhn_lib", 4, "fixed", True, 3),        # the reference's own IEKS test case (test/ieks.jl:10-13), fewer iterates
+    ("fhn_lib", 2, "dynamic", False, 4),
+    ("lotka_volterra", 3, "dynamic", True, 3),
+])
+def test_ieks_matches_oracle(name, q, diffusion, adaptive, iterations):
+    """solve_ieks (src/ieks.jl:53-61): every iterate linearises at the previous iterate's dense output
+    (src/perform_step.jl:111-113).  All iterates run on the device; compared with the oracle's loop."""
+    import odefilters_b200 as B
+
+    u0, p = PROBLEMS[name]
+    tspan = (0.0, 5.0)
+    kw = dict(adaptive=False, dt=0.05) if not adaptive else {}
+    so = O.solve_ieks(O.Problem(O.CATALOGUE[name], list(u0), tspan, list(p)), O.IEKS(order=q, diffusionmodel=diffusion),
+                      iterations=iterations, **kw)
+    so1 = O.solve_ivp(O.Problem(O.CATALOGUE[name], list(u0), tspan, list(p)), O.Alg("EK1", q, diffusion, True), **kw)
+    sg = B.solve_ieks(B.ODEProblem(name, u0, tspan, p), B.IEKS(order=q, diffusionmodel=diffusion), iterations=iterations, **kw)
+    assert sg.retcode == "Success"
+    assert (sg.destats["naccept"], sg.destats["nreject"]) == (so.naccept, so.nreject)
+    assert np.allclose(sg.t, np.asarray(so.t), rtol=1e-7, atol=0)
+    mo = np.array([g.mu for g in so.x_smooth])
+    assert rel(sg.u, mo[:, :2]) < 1e-7
+    assert rel(sg.x_filt.mu[:, :2], np.array([g.mu[:2] for g in so.x_filt])) < 1e-7
+    # the iteration did something: the result differs from a plain EK1 solve by more than the parity tolerance
+    m1 = np.array([g.mu[:2] for g in so1.x_smooth])
+    if len(so1.t) == len(so.t):
+        assert rel(mo[:, :2], m1) > 1e-9
+    # one iterate == EK1
+    s1 = B.solve_ieks(B.ODEProblem(name, u0, tspan, p), B.IEKS(order=q, diffusionmodel=diffusion), iterations=1, **kw)
+    se = B.solve(B.ODEProblem(name, u0, tspan, p), B.EK1(order=q, diffusionmodel=diffusion, smooth=True), **kw)
+    assert len(s1.t) == len(se.t) and rel(s1.u, se.u) < 1e-9
+
+
+def test_ieks_ensemble_and_errors():
+    import odefilters_b200 as B
+
+    prob = B.ODEProblem("lotka_volterra", [1.0, 1.0], (0.0, 2.0), (1.5, 1.0, 3.0, 1.0))
+    with pytest.raises(ValueError):
+        B.solve_ieks(prob, B.EK1(order=2))
+    rng = np.random.default_rng(3)
+    n = 300
+    p = np.array([1.5, 1.0, 3.0, 1.0]) * (1 + 0.1 * rng.uniform(-1, 1, (n, 4)))
+    s = B.FilterSolver(prob, B.IEKS(order=2), adaptive=False, dt=0.02, save_everystep=True)
+    s.upload(np.ones((n, 2)), p)
+    s.run(); s.smooth()
+    m1 = s.final()[0].copy()
+    s.run(); s.smooth()      # second iterate: linearised at the first
+    m2 = s.final()[0].copy()
+    s.run()
+    with pytest.raises(RuntimeError):
+        s.run()              # the previous iterate has not been smoothed
+    s.smooth()
+    m3 = s.final()[0].copy()
+    assert np.isfinite(m3).all() and (s.counts()["retcode"] == 0).all()
+    # fixed-point iteration: successive iterates contract
+    assert np.abs(m3 - m2).max() < np.abs(m2 - m1).max()
+    k = 17
+    so = O.solve_ieks(O.Problem(O.CATALOGUE["lotka_volterra"], [1.0, 1.0], (0.0, 2.0), list(p[k])), O.IEKS(order=2),
+                      iterations=3, adaptive=False, dt=0.02)
+    assert rel(m3[k, :2], so.x_filt[-1].mu[:2]) < 1e-9

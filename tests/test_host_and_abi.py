@@ -140,3 +140,15 @@ def test_custom_vector_field_source_is_validated_without_gpu():
     bad = B.CustomVectorField(2, 1, "du[0] = u[1] du[1] = 0.0;")
     with pytest.raises(ValueError, match="expected a"):
         bad.check(B.EK0(order=2))
+
+
+def test_ieks_kernels_compile_without_gpu():
+    """The IEKS flavour of the filter kernel (ieks_kernel.cuh: linearisation at the previous iterate's dense output) is
+    compiled on demand; the compile-only check runs here."""
+    import odefilters_b200 as B
+
+    vf = B.CustomVectorField(2, 1, "du[0] = u[1]; du[1] = -p[0]*sin(u[0]);",
+                             "J[0][0] = 0.0; J[0][1] = 1.0; J[1][0] = -p[0]*cos(u[0]); J[1][1] = 0.0;")
+    assert vf.check(B.IEKS(order=2)) == ""
+    with pytest.raises(ValueError):
+        B.solve_ieks(B.ODEProblem("fhn_lib", [1.0, 1.0], (0.0, 1.0), (0.7, 0.8, 0.08, 0.5)), B.EK1(order=2))

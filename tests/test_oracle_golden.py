@@ -239,3 +239,20 @@ def test_oracle_reproduces_committed_fixtures():
     s = O.solve_ivp(O.Problem(O.CATALOGUE["lotka_volterra"], [1.0, 1.0], (0.0, 10.0), [1.5, 1.0, 3.0, 1.0]),
                     O.EK1(order=3, smooth=True), adaptive=False, dt=0.05)
     assert np.allclose(np.array([x.mu for x in s.x_smooth]), g["smooth_mean"], rtol=1e-9, atol=1e-12)
+
+
+def test_ieks_oracle_first_iterate_is_ek1_and_iterates_contract():
+    """src/ieks.jl:53-61 + src/perform_step.jl:111-113: iterate 1 has no linearisation trajectory and equals an EK1
+    solve; on a fixed grid the iterates then contract towards the MAP estimate."""
+    prob = O.Problem(O.CATALOGUE["fhn_lib"], [1.0, 1.0], (0.0, 5.0), [0.7, 0.8, 1 / 12.5, 0.5])
+    kw = dict(adaptive=False, dt=0.05)
+    s1 = O.solve_ieks(prob, O.IEKS(order=2), iterations=1, **kw)
+    se = O.solve_ivp(prob, O.EK1(order=2, smooth=True), **kw)
+    assert np.array_equal(np.array(s1.u), np.array(se.u))
+    its = [np.array(O.solve_ieks(prob, O.IEKS(order=2), iterations=k, **kw).u) for k in (1, 2, 3)]
+    d12, d23 = np.abs(its[1] - its[0]).max(), np.abs(its[2] - its[1]).max()
+    assert 0 < d23 < d12
+    # the reference's own test (test/ieks.jl:10-13: runs and returns a solution), with fewer iterates
+    s = O.solve_ieks(O.Problem(O.CATALOGUE["fhn_lib"], [1.0, 1.0], (0.0, 10.0), [0.7, 0.8, 1 / 12.5, 0.5]),
+                     O.IEKS(order=4, diffusionmodel="fixed"), iterations=3)
+    assert s.retcode == "Success" and s.t[-1] == 10.0 and s.smoothed
