@@ -10,7 +10,7 @@
 module ProbNumDiffEqB200
 
 using ProbNumDiffEq
-using ProbNumDiffEq: AbstractEK, EK0, EK1, SRMatrix, ProbODESolution
+using ProbNumDiffEq: AbstractEK, EK0, EK1, IEKS, SRMatrix, ProbODESolution
 using DiffEqBase
 using GaussianDistributions: Gaussian
 using StructArrays
@@ -71,12 +71,12 @@ function _create(cfg::PndeConfig)
 end
 
 function _config(prob, alg::AbstractEK; abstol=1e-6, reltol=1e-3, adaptive=true, dt=nothing,
-                 save_everystep=true, maxiters=100000, max_saved=0, device=-1, kwargs...)
+                 save_everystep=true, maxiters=100000, max_saved=0, device=-1, ieks_iterations=0, kwargs...)
     !adaptive && dt === nothing && error("Fixed timestep methods require a choice of dt")
     f = prob.f.f
     f isa CatalogueFunction || error("ProbNumDiffEqB200 needs a catalogue vector field (see include/pnde.h)")
     smooth = alg.smooth && save_everystep
-    PndeConfig(alg = alg isa EK1 ? 1 : 0, order = alg.order, vf_kind = f.kind,
+    PndeConfig(alg = alg isa IEKS ? 2 : alg isa EK1 ? 1 : 0, ieks_iterations = ieks_iterations, order = alg.order, vf_kind = f.kind,
                diffusion = DIFFUSIONS[alg.diffusionmodel], smooth = smooth, adaptive = adaptive,
                save_mode = save_everystep ? 1 : 0, device = device, abstol = abstol, reltol = reltol,
                dt = dt === nothing ? 0.0 : dt, t0 = prob.tspan[1], t1 = prob.tspan[2],
@@ -118,6 +118,11 @@ function _srmatrix(mat)
     S = F.vectors * Diagonal(sqrt.(max.(F.values, 0)))
     return SRMatrix(S, mat)
 end
+
+"""solve_ieks (src/ieks.jl:53-61) as ONE library call: all iterates (EK1 solves linearised at the previous iterate's
+dense output, src/perform_step.jl:111-113) run on the device; `alg.linearize_at` is not used."""
+solve_ieks_b200(prob::DiffEqBase.AbstractODEProblem, alg::IEKS, args...; iterations=10, kwargs...) =
+    DiffEqBase.solve(prob, alg, args...; ieks_iterations=iterations, kwargs...)
 
 function DiffEqBase.__solve(prob::DiffEqBase.AbstractODEProblem, alg::AbstractEK; kwargs...)
     cfg = _config(prob, alg; kwargs...)
