@@ -40,6 +40,11 @@ def main():
     solver = B.FilterSolver(prob, B.EK1(order=3, smooth=True), adaptive=False, dt=0.05, save_everystep=True, device=local)
     waves = [(a, min(n, a + WAVE)) for a in range(0, n, WAVE)]
 
+    to_host = "--marginals" in sys.argv  # also bring the smoothed marginals (t, u, Sigma_u) of every step to the host
+    d2h = [0.0, 0]
+    nrec = min(WAVE, n) * (STEPS + 1)
+    pinned = (B.pinned_empty(nrec), B.pinned_empty((nrec, 2)), B.pinned_empty((nrec, 3))) if to_host else None
+
     def one_pass():
         f_ms = s_ms = 0.0
         for a, b in waves:
@@ -49,9 +54,15 @@ def main():
             fm, sm = solver.last_run_ms()
             f_ms += fm
             s_ms += sm
+            if to_host:
+                t1 = time.perf_counter()
+                _, t, u, cu, _ = solver.history(1, 0, b - a, marginals=True, out=pinned)
+                d2h[0] += time.perf_counter() - t1
+                d2h[1] += t.nbytes + u.nbytes + cu.nbytes
         return f_ms, s_ms
 
     one_pass()  # warm-up
+    d2h[:] = [0.0, 0]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -68,7 +79,10 @@ def main():
         f, s, w = (float(x) for x in dev)
         print(json.dumps({"config": 5, "n_gpus": world, "trajectories": N_TOTAL, "steps_per_trajectory": STEPS,
                           "filter_ms_max": f, "smoother_ms_max": s, "wall_ms_incl_h2d": w,
-                          "filter_plus_smooth_steps_per_s": N_TOTAL * STEPS / ((f + s) * 1e-3), "ok": ok}))
+                          "filter_plus_smooth_steps_per_s": N_TOTAL * STEPS / ((f + s) * 1e-3), "ok": ok,
+                          "marginals_to_host": ({"seconds_rank0": d2h[0], "bytes_rank0": d2h[1],
+                                                 "note": "pnde_get_marginals into reused pinned host arrays (pnde_host_alloc): convert kernel + D2H copy"}
+                                                if to_host else None)}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -213,6 +213,11 @@ int pnde_sample(pnde_handle* h, int64_t traj_begin, int64_t traj_end, int32_t n_
 int pnde_eval_dense(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end, int64_t n_t,
                     const double* t, double* mean, double* cov);
 
+/* Page-locked host memory for the output getters: results copied into such buffers move at the full host-link
+ * rate (the copies into pageable memory are staged by the driver).  Julia: unsafe_wrap(Array, ptr, dims). */
+int pnde_host_alloc(void** ptr, int64_t bytes);
+int pnde_host_free(void* ptr);
+
 /* Device micro-benchmarks used as roofline denominators by bench.py (not part of the path). */
 int pnde_measure_fp64_peak(int32_t device, double* tflops);
 int pnde_measure_hbm_copy(int32_t device, double* gbs);

@@ -21,6 +21,7 @@ from .api import (  # noqa: F401
     IEKS,
     ODEProblem,
     ProbODESolution,
+    pinned_empty,
     SRMatrix,
     shard_range,
     solve,
@@ -29,4 +30,4 @@ from .api import (  # noqa: F401
 from . import _lib  # noqa: F401
 
 __all__ = ["CustomVectorField", "EK0", "EK1", "EnsembleB200", "EnsembleProblem", "EnsembleSolution", "FilterSolver", "Gaussian",
-           "IEKS", "ODEProblem", "ProbODESolution", "SRMatrix", "shard_range", "solve", "solve_ieks"]
+           "IEKS", "ODEProblem", "ProbODESolution", "SRMatrix", "pinned_empty", "shard_range", "solve", "solve_ieks"]

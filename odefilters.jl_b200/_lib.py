@@ -37,7 +37,7 @@ EXPORTS = [
     "pnde_record_len", "pnde_cov_len", "pnde_solve_ensemble", "pnde_solve_ensemble_to_host", "pnde_upload", "pnde_run", "pnde_synchronize", "pnde_last_run_ms",
     "pnde_last_launch_count", "pnde_smooth", "pnde_query_sizes", "pnde_get_counts", "pnde_get_final",
     "pnde_get_history", "pnde_get_marginals", "pnde_sample", "pnde_eval_dense", "pnde_measure_fp64_peak",
-    "pnde_measure_hbm_copy",
+    "pnde_measure_hbm_copy", "pnde_host_alloc", "pnde_host_free",
 ]
 
 _lib = None
@@ -82,5 +82,7 @@ def load():
     lib.pnde_eval_dense.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp]
     lib.pnde_measure_fp64_peak.argtypes = [C.c_int32, dp]
     lib.pnde_measure_hbm_copy.argtypes = [C.c_int32, dp]
+    lib.pnde_host_alloc.argtypes = [C.POINTER(vp), C.c_int64]
+    lib.pnde_host_free.argtypes = [vp]
     _lib = lib
     return lib

@@ -169,6 +169,31 @@ class Gaussian:
     Sigma: SRMatrix
 
 
+class _PinnedBlock:
+    def __init__(self, nbytes: int):
+        self.lib = L.load()
+        self.ptr = C.c_void_p()
+        rc = self.lib.pnde_host_alloc(C.byref(self.ptr), int(nbytes))
+        if rc != 0:
+            raise MemoryError(f"pnde_host_alloc({nbytes}) failed ({rc}): {self.lib.pnde_last_error(None).decode()}")
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.lib.pnde_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array in page-locked host memory (pnde_host_alloc): device-to-host copies into it run at the full
+    host-link rate instead of being staged through the driver's bounce buffer."""
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    blk = _PinnedBlock(max(nbytes, 8))
+    buf = (C.c_char * max(nbytes, 8)).from_address(blk.ptr.value)
+    buf._pnde_block = blk  # the array's base keeps the allocation alive
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
 def _unpack_lower(packed: np.ndarray, D: int) -> np.ndarray:
     """[..., D(D+1)/2] packed lower triangle (rows) -> [..., D, D] symmetric."""
     out = np.zeros(packed.shape[:-1] + (D, D))
@@ -424,17 +449,26 @@ class FilterSolver:
         self._check(self.lib.pnde_get_final(self._h, mean.ctypes.data, None, tf.ctypes.data, None), "pnde_get_final")
         return mean[: self.d].T.copy(), tf
 
-    def history(self, which: int, lo: int, hi: int, marginals: bool = False):
-        """CSR history of trajectories [lo, hi): (offsets, t, mean, cov_packed, diffusion)."""
+    def history(self, which: int, lo: int, hi: int, marginals: bool = False, pinned: bool = False, out=None):
+        """CSR history of trajectories [lo, hi): (offsets, t, mean, cov_packed, diffusion).
+        pinned: allocate the outputs in page-locked memory (large reads: several times the pageable copy rate);
+        out = (t, mean, cov) reuses caller buffers (e.g. from pinned_empty) that are at least as large."""
+        empty = pinned_empty if pinned else np.empty
+        if out is not None:
+            bufs = iter(out)
+            def empty(shape, _b=bufs):  # noqa: E306
+                shape = (shape,) if np.isscalar(shape) else tuple(shape)
+                a = next(_b).reshape(-1)
+                return a[: int(np.prod(shape, dtype=np.int64))].reshape(shape)
         tot, mx = C.c_int64(), C.c_int64()
         self._check(self.lib.pnde_query_sizes(self._h, C.byref(tot), C.byref(mx)), "pnde_query_sizes")
         cnt = self.counts()["n_saved"][lo:hi]
         total = int(cnt.sum())
         DM = self.d if marginals else self.D
         offsets = np.zeros(hi - lo + 1, dtype=np.int64)
-        t = np.empty(total)
-        mean = np.empty((total, DM))
-        cov = np.empty((total, DM * (DM + 1) // 2))
+        t = empty(total)
+        mean = empty((total, DM))
+        cov = empty((total, DM * (DM + 1) // 2))
         if marginals:
             self._check(self.lib.pnde_get_marginals(self._h, which, lo, hi, offsets.ctypes.data, t.ctypes.data,
                                                     mean.ctypes.data, cov.ctypes.data), "pnde_get_marginals")

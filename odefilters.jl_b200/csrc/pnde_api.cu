@@ -1052,6 +1052,23 @@ int pnde_measure_fp64_peak(int32_t device, double* tflops) {
   return PNDE_OK;
 }
 
+int pnde_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return PNDE_ERR_ARG;
+  *ptr = nullptr;
+  const cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    g_create_error = std::string("pnde_host_alloc: ") + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? PNDE_ERR_ALLOC : PNDE_ERR_CUDA;
+  }
+  return PNDE_OK;
+}
+
+int pnde_host_free(void* ptr) {
+  if (!ptr) return PNDE_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? PNDE_OK : PNDE_ERR_CUDA;
+}
+
 int pnde_measure_hbm_copy(int32_t device, double* gbs) {
   if (!gbs) return PNDE_ERR_ARG;
   if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PNDE_ERR_CUDA;

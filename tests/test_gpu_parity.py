@@ -711,3 +711,20 @@ def test_ieks_ensemble_and_errors():
     so = O.solve_ieks(O.Problem(O.CATALOGUE["lotka_volterra"], [1.0, 1.0], (0.0, 2.0), list(p[k])), O.IEKS(order=2),
                       iterations=3, adaptive=False, dt=0.02)
     assert rel(m3[k, :2], so.x_filt[-1].mu[:2]) < 1e-9
+
+
+def test_pinned_host_buffers_for_history_reads():
+    """pnde_host_alloc / pnde_host_free: getters write into page-locked caller buffers (same values as pageable)."""
+    import odefilters_b200 as B
+
+    prob = B.ODEProblem("lotka_volterra", [1.0, 1.0], (0.0, 1.0), (1.5, 1.0, 3.0, 1.0))
+    s = B.FilterSolver(prob, B.EK1(order=3, smooth=True), adaptive=False, dt=0.05, save_everystep=True)
+    n = 500
+    s.solve_ensemble(np.ones((n, 2)), np.tile([1.5, 1.0, 3.0, 1.0], (n, 1)) * np.linspace(0.9, 1.1, n)[:, None])
+    a = s.history(1, 0, n, marginals=True)
+    b = s.history(1, 0, n, marginals=True, pinned=True)
+    bufs = (B.pinned_empty(n * 21 + 5), B.pinned_empty((n * 21 + 5, 2)), B.pinned_empty((n * 21 + 5, 3)))
+    c = s.history(1, 0, n, marginals=True, out=bufs)
+    for x, y, z in zip(a[:4], b[:4], c[:4]):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    assert c[1].base is not None and a[1].shape == (n * 21,)
