@@ -26,8 +26,11 @@ from .api import (  # noqa: F401
     shard_range,
     solve,
     solve_ieks,
+    mean,
+    std,
+    var,
 )
 from . import _lib  # noqa: F401
 
 __all__ = ["CustomVectorField", "EK0", "EK1", "EnsembleB200", "EnsembleProblem", "EnsembleSolution", "FilterSolver", "Gaussian",
-           "IEKS", "ODEProblem", "ProbODESolution", "SRMatrix", "pinned_empty", "shard_range", "solve", "solve_ieks"]
+           "IEKS", "ODEProblem", "ProbODESolution", "SRMatrix", "pinned_empty", "shard_range", "solve", "solve_ieks", "mean", "std", "var"]

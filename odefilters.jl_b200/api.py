@@ -216,6 +216,22 @@ class _GaussianList:
         return Gaussian(self.mu[i], SRMatrix(self.Sigma[i]))
 
 
+def mean(x):
+    """mean(::SRGaussianList) = s.mu (src/ProbNumDiffEq.jl:64); also for a single Gaussian."""
+    return x.mu
+
+
+def var(x):
+    """var = diag(Sigma), per state for a list (src/ProbNumDiffEq.jl:62,65)."""
+    S = x.Sigma.mat if isinstance(x, Gaussian) else x.Sigma
+    return np.diagonal(S, axis1=-2, axis2=-1).copy()
+
+
+def std(x):
+    """std = sqrt.(diag(Sigma)) (src/ProbNumDiffEq.jl:63,66)."""
+    return np.sqrt(np.maximum(var(x), 0.0))
+
+
 @dataclass
 class ProbODESolution:
     """Fields of the reference's ProbODESolution (src/solution.jl:8-24)."""

@@ -152,3 +152,17 @@ def test_ieks_kernels_compile_without_gpu():
     assert vf.check(B.IEKS(order=2)) == ""
     with pytest.raises(ValueError):
         B.solve_ieks(B.ODEProblem("fhn_lib", [1.0, 1.0], (0.0, 1.0), (0.7, 0.8, 0.08, 0.5)), B.EK1(order=2))
+
+
+def test_gaussian_list_moments():
+    """mean / var / std of SRGaussian and SRGaussianList (src/ProbNumDiffEq.jl:61-66)."""
+    import odefilters_b200 as B
+    from odefilters_b200.api import _GaussianList
+
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((5, 3, 3))
+    cov = A @ A.transpose(0, 2, 1)
+    gl = _GaussianList(rng.standard_normal((5, 3)), cov)
+    assert np.array_equal(B.mean(gl), gl.mu)
+    assert np.allclose(B.var(gl), np.stack([np.diag(c) for c in cov]))
+    assert np.allclose(B.std(gl[2]), np.sqrt(np.diag(cov[2])))
