@@ -728,3 +728,46 @@ def test_pinned_host_buffers_for_history_reads():
     for x, y, z in zip(a[:4], b[:4], c[:4]):
         assert np.array_equal(x, y) and np.array_equal(x, z)
     assert c[1].base is not None and a[1].shape == (n * 21,)
+
+
+def test_ieks_with_a_custom_vector_field():
+    """IEKS on a user ODE compiled at run time equals IEKS on the same ODE from the catalogue."""
+    import odefilters_b200 as B
+
+    u0, p = PROBLEMS["lotka_volterra"]
+    alg = B.IEKS(order=2)
+    a = B.solve_ieks(B.ODEProblem("lotka_volterra", u0, (0.0, 2.0), p), alg, iterations=3)
+    b = B.solve_ieks(B.ODEProblem(B.CustomVectorField(**LV_SRC), u0, (0.0, 2.0), p), alg, iterations=3)
+    assert a.destats == b.destats and np.array_equal(a.t, b.t)
+    assert rel(b.u, a.u) < 1e-12
+
+
+def test_distinct_handles_from_distinct_host_threads():
+    """include/pnde.h threading contract: a handle is not re-entrant, distinct handles may run concurrently."""
+    import threading
+
+    import odefilters_b200 as B
+
+    rng = np.random.default_rng(11)
+    n = 20000
+    ps = [np.stack([rng.uniform(0.1, 0.3, n), rng.uniform(0.1, 0.3, n), rng.uniform(2, 4, n)], axis=1) for _ in range(3)]
+    prob = B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 2.0), (0.2, 0.2, 3.0))
+    mk = lambda: B.FilterSolver(prob, B.EK1(order=3, smooth=False), adaptive=True, save_everystep=False)  # noqa: E731
+    u0 = np.tile([-1.0, 1.0], (n, 1))
+    ref = []
+    for p in ps:
+        s = mk(); s.solve_ensemble(u0, p); ref.append((s.final()[0], s.counts()["naccept"])); s.close()
+    out = [None] * 3
+
+    def work(i):
+        s = mk()
+        for _ in range(3):
+            s.solve_ensemble(u0, ps[i])
+        out[i] = (s.final()[0], s.counts()["naccept"])
+        s.close()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for (m, c), (mr, cr) in zip(out, ref):
+        assert np.array_equal(m, mr) and np.array_equal(c, cr)   # bitwise: same kernel, same inputs
