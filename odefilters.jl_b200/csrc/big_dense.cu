@@ -390,7 +390,13 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
   wk.W = (double*)take((size_t)NB * D * 8);
   wk.v0 = (double*)take(2 * NB * 8);
   wk.T = (double*)take(2 * NB * NB * 8);
-  BCK(cudaStreamCreateWithFlags(&wk.aux, cudaStreamNonBlocking));
+  {
+    // the panel chain is the critical path of the blocked QR: its clusters must not queue behind the CTAs of the
+    // trailing update that runs beside it
+    int prio_lo = 0, prio_hi = 0;
+    BCK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    BCK(cudaStreamCreateWithPriority(&wk.aux, cudaStreamNonBlocking, prio_hi));
+  }
   for (int i = 0; i < 2; ++i) {
     BCK(cudaEventCreateWithFlags(&wk.ev_narrow[i], cudaEventDisableTiming));
     BCK(cudaEventCreateWithFlags(&wk.ev_panel[i], cudaEventDisableTiming));
@@ -414,9 +420,8 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
     long long iter = 0;
     const int trsv_smem = d * 8;
     BCK(cudaFuncSetAttribute(trsv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsv_smem));
-    while (t < A.K.t1) {
-      if (++iter > A.K.maxiters) break;
-      const double h = fmin(A.K.dt, A.K.t1 - t);
+    // one attempted step (fixed h): every launch below depends on the step only through h
+    auto step_body = [&](double h) -> cudaError_t {
       set_step_kernel<<<1, 1, 0, s>>>(c.sc, h, q);
       measure_kernel<<<(d + TB - 1) / TB, TB, 0, s>>>(c);
       *launches += 2;
@@ -440,6 +445,14 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
       build_s_kernel<<<(unsigned)(((long long)(D - d) * d + TB - 1) / TB), TB, 0, s>>>(c);
       finish_step_kernel<<<1, 1, 0, s>>>(c.sc, d, A.diffusion);
       *launches += 4;
+      return cudaGetLastError();
+    };
+    // (capturing the ~650 launches of a step into a CUDA graph was measured: 23.5 ms/step either way -- the panel
+    // chain is bound by the kernels themselves, not by launch gaps -- so the plain launches stay)
+    while (t < A.K.t1) {
+      if (++iter > A.K.maxiters) break;
+      const double h = fmin(A.K.dt, A.K.t1 - t);
+      BCK(step_body(h));
       const double ttmp = t + h;
       t = (fabs(ttmp - A.K.t1) < 10.0 * ulp_host(fmax(t, A.K.t1))) ? A.K.t1 : ttmp;
     }

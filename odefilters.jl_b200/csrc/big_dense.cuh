@@ -30,7 +30,10 @@ namespace big {
 namespace cg = cooperative_groups;
 
 constexpr int NB = 32;        // panel width
-constexpr int NCLUSTER = 8;   // CTAs per panel cluster
+#ifndef PNDE_PANEL_CLUSTER
+#define PNDE_PANEL_CLUSTER 8
+#endif
+constexpr int NCLUSTER = PNDE_PANEL_CLUSTER;  // CTAs per panel cluster (16 needs the non-portable opt-in)
 constexpr int PANEL_THREADS = 1024;
 
 struct Geometry {
@@ -61,6 +64,21 @@ __device__ __forceinline__ double prior_pivot(int c, int j, int d, double pi1, c
   return 0.0;
 }
 
+// the same with (block, dimension) = (index / d, index % d) of both indices supplied by the caller
+__device__ __forceinline__ double prior_pivot_split(int c, int cd, int ca, int j, int jd, int ja, int d, double pi1,
+                                                    const IwpConsts& C, int mode) {
+  (void)d;
+  if (mode == 0) return 0.0;
+  if (cd == 0) {
+    if (j == c) return pi1 * C.Lt[1][1];
+    if (jd >= 2 && ja == c) return C.Lt[jd][1];
+    return 0.0;
+  }
+  if (cd == 1) return 0.0;
+  if (ja == ca && jd >= cd) return C.Lt[jd][cd];
+  return 0.0;
+}
+
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
@@ -71,6 +89,33 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // (1) panel factorisation: columns [c0, c0+NB) of E (nrows x .), cluster of NCLUSTER CTAs
 // outputs: E panel <- Vb;  R[c0+k][c0+j] (k <= j < NB);  v0[NB], T[NB][NB] (compact WY)
 // ---------------------------------------------------------------------------------------------
+// Explicit shared-window accesses for the hot loops of the panel kernel: with cluster launch the compiler addresses
+// `extern __shared__` through the cluster window and, short of registers, rebuilds the window base (S2R CgaCtaId)
+// in front of every access.
+__device__ __forceinline__ double lds64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ void lds128(unsigned addr, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(unsigned addr, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+
+constexpr int panel_kc(int rpt) { return rpt <= 16 ? 4 : 2; }
+constexpr int panel_rs(int rpt) { return (PANEL_THREADS / NB) * rpt + 2; }  // +2: the 32 columns start in different banks
+inline size_t panel_smem_bytes(int rows_per, int rpt) {
+  const int nstripe = PANEL_THREADS / NB;
+  (void)rows_per;
+  return ((size_t)NB * panel_rs(rpt) + (nstripe + 2) * NB + 3 * NB * NB + (panel_kc(rpt) == 4 ? nstripe * 4 * NB : 0)) * sizeof(double);
+}
+
 struct PanelArgs {
   double* E;
   double* R;
@@ -78,48 +123,174 @@ struct PanelArgs {
   const Scalars* sc;
   double* v0;    // [NB]
   double* T;     // [NB][NB]
+  // previous panel (columns [cprev, cprev+NB), cprev < 0: none): its reflectors are applied to this panel's
+  // columns inside the kernel before the factorisation starts (the "narrow" trailing update of a look-ahead QR)
+  int cprev;
+  const double* v0p;
+  const double* Tp;
   IwpConsts C;
 };
 
+// Thread (col, stripe): the lanes of a warp are the NB panel columns, warp w owns the RPT consecutive rows
+// [w RPT, (w+1) RPT) of the CTA's slab.  Every thread keeps ITS column's entries of those rows in registers (creg)
+// for the whole kernel.  Shared memory holds a column-major copy slabT[k][r] (so that a thread's rows of one
+// column are contiguous: 128-bit broadcast loads): the previous panel's reflectors during the fused update,
+// afterwards the panel itself, of which only the current pivot column has to be up to date (its owner lane
+// publishes it right after its last update).  The kernel is bound by shared-memory instructions and by the
+// per-column synchronisation chain, not by FP64 throughput.
+template <int RPT>
 __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS) panel_kernel(const PanelArgs a) {
+  static_assert(RPT % 2 == 0, "rows per thread are processed in pairs");
   extern __shared__ double smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int rows_per = a.nrows / NCLUSTER;
   const int row0 = rank * rows_per;
-  constexpr int LDS = NB + 1;
-  double* slab = smem;                         // [rows_per][LDS]
-  double* part = slab + (size_t)rows_per * LDS;      // [NSTRIPE][NB] partial sums + [2][NB] column sums
-  double* gram = part + (PANEL_THREADS / NB + 2) * NB;  // [NB][NB] Gram of Vb (local, then total in rank 0)
-  __shared__ double s_v0[NB], s_beta[NB], s_T[NB][NB];
+  constexpr int NSTRIPE = PANEL_THREADS / NB;
+  constexpr int KC = panel_kc(RPT);                  // reflectors per pass of the block products
+  constexpr int RS = panel_rs(RPT);                  // row stride of slabT (rows >= rows_per are zero padding)
+  double* slab = smem;                               // [NB][RS]
+  double* part = slab + (size_t)NB * RS;             // [NSTRIPE][NB] partial sums + [2][NB] column sums
+  double* gram = part + (NSTRIPE + 2) * NB;          // [NB][NB] Gram of Vb (cluster total, rank 0)
+  double* wloc = gram + NB * NB;                     // [NB][NB] this CTA's share of a block product
+  double* wful = wloc + NB * NB;                     // [NB][NB] cluster total, then W2
+  double* red = (KC == 4) ? wful + NB * NB : part;   // [NSTRIPE][KC][NB]; KC == 2: aliases part + gram (unused then)
+  __shared__ double s_v0[NB], s_beta[NB], s_T[NB][NB + 1], s_coef[NB];
+  __shared__ int s_cd[NB], s_ca[NB];
   const int tid = threadIdx.x;
+  const int col = tid % NB, stripe = tid / NB;
   const double sigma = (a.mode == 0) ? 1.0 : a.sc->sigma;
   const double pi1 = a.sc->pi1;
+  const bool fused = a.cprev >= 0;
+  // byte address (shared window) of this thread's first row in column 0 of slabT
+  const unsigned tbase = (unsigned)__cvta_generic_to_shared(slab) + (unsigned)(stripe * RPT) * 8u;
+  const unsigned red_s = (unsigned)__cvta_generic_to_shared(red);
+  const unsigned part_s = (unsigned)__cvta_generic_to_shared(part);
 
-  for (int idx = tid; idx < rows_per * NB; idx += PANEL_THREADS) {
-    const int r = idx / NB, k = idx % NB;
-    slab[r * LDS + k] = a.E[(size_t)(row0 + r) * a.ld + a.c0 + k];
+  {
+    const int cload = fused ? a.cprev : a.c0;
+    for (int idx = tid; idx < NSTRIPE * RPT * NB; idx += PANEL_THREADS) {
+      const int r = idx / NB, k = idx % NB;
+      slab[k * RS + r] = (r < rows_per) ? a.E[(size_t)(row0 + r) * a.ld + cload + k] : 0.0;
+    }
+  }
+  double creg[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int r = stripe * RPT + i;
+    creg[i] = (r < rows_per) ? a.E[(size_t)(row0 + r) * a.ld + a.c0 + col] : 0.0;
+  }
+  if (fused) {
+    for (int e = tid; e < NB * NB; e += PANEL_THREADS) s_T[e / NB][e % NB] = a.Tp[e];
+    if (tid < NB) s_v0[tid] = a.v0p[tid];
+  }
+  if (tid < NB) {  // (block, dimension) of the panel's columns for the sparse prior pivots
+    s_cd[tid] = (a.c0 + tid) / a.d;
+    s_ca[tid] = (a.c0 + tid) % a.d;
   }
   __syncthreads();
-  // Thread (col, stripe): lanes of a warp are the NB panel columns, warp w owns row stripe w.  Per column:
-  // partial inner products -> block reduction -> one value per column published to the cluster ->
-  // warp 0 gathers the 8 ranks through DSMEM, computes the reflector scalars and broadcasts s_j.
-  const int col = tid % NB, stripe = tid / NB;
-  constexpr int NSTRIPE = PANEL_THREADS / NB;
+
+  // wloc[k][col] = sum over this CTA's rows of slabT[k][r] * creg[r]   (k = 0..NB-1)
+  auto block_product = [&]() {
+    double acc[KC];
+    for (int k0 = 0; k0 < NB; k0 += KC) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < RPT; i += 2) {
+          double x, y;
+          lds128(tbase + (unsigned)((k0 + k) * RS + i) * 8u, x, y);  // one address per warp: broadcast
+          a0 = fma(x, creg[i], a0);
+          a1 = fma(y, creg[i + 1], a1);
+        }
+        acc[k] = a0 + a1;
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k) sts64(red_s + (unsigned)((stripe * KC + k) * NB + col) * 8u, acc[k]);
+      __syncthreads();
+      if (tid < KC * NB) {
+        const int kk = tid / NB;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int st = 0; st < NSTRIPE; st += 4) {
+          s0 += lds64(red_s + (unsigned)(((st + 0) * KC + kk) * NB + col) * 8u);
+          s1 += lds64(red_s + (unsigned)(((st + 1) * KC + kk) * NB + col) * 8u);
+          s2 += lds64(red_s + (unsigned)(((st + 2) * KC + kk) * NB + col) * 8u);
+          s3 += lds64(red_s + (unsigned)(((st + 3) * KC + kk) * NB + col) * 8u);
+        }
+        wloc[(k0 + kk) * NB + col] = (s0 + s1) + (s2 + s3);
+      }
+      __syncthreads();
+    }
+  };
+
+  if (fused) {
+    // ---- apply the previous panel's block reflector to these NB columns (C in creg, Vp in slabT) ----
+    //   W = Vp' C (cluster-wide sum);  W2 = T' (W + diag(v0) pivots);  R rows;  C -= Vp W2
+    block_product();
+    cluster.sync();
+    {
+      const int k = stripe, c = col;  // one entry of the NB x NB block per thread
+      double w = 0.0;
+#pragma unroll
+      for (int rk = 0; rk < NCLUSTER; ++rk) w += cluster.map_shared_rank(wloc, rk)[k * NB + c];
+      const double piv = sigma * prior_pivot(a.cprev + k, a.c0 + c, a.d, pi1, a.C, a.mode);
+      wful[k * NB + c] = fma(s_v0[k], piv, w);
+      __syncthreads();
+      double w2 = 0.0;
+      for (int m = 0; m <= k; ++m) w2 = fma(s_T[m][k], wful[m * NB + c], w2);  // T' is lower triangular
+      if (rank == 0) a.R[(size_t)(a.cprev + k) * a.ld + a.c0 + c] = fma(-s_v0[k], w2, piv);
+      __syncthreads();
+      wful[k * NB + c] = w2;
+      __syncthreads();
+    }
+    for (int k0 = 0; k0 < NB; k0 += KC) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const double w2 = wful[(k0 + k) * NB + col];
+#pragma unroll
+        for (int i = 0; i < RPT; i += 2) {
+          double x, y;
+          lds128(tbase + (unsigned)((k0 + k) * RS + i) * 8u, x, y);
+          creg[i] = fma(-x, w2, creg[i]);
+          creg[i + 1] = fma(-y, w2, creg[i + 1]);
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with Vp: slabT <- C
+#pragma unroll
+    for (int i = 0; i < RPT; i += 2) sts128(tbase + (unsigned)(col * RS + i) * 8u, creg[i], creg[i + 1]);
+    __syncthreads();
+  }
+  // ---- factorisation.  Per column: partial inner products -> block reduction -> one value per column published
+  // to the cluster -> warp 0 gathers the 8 ranks through DSMEM, computes the reflector scalars and broadcasts s_j.
   double* gl = part + NSTRIPE * NB;  // [2][NB]
-  __shared__ double s_coef[NB];
+  const int jd = (a.c0 + col) / a.d, ja = (a.c0 + col) % a.d;  // used by warp 0 (tid == col)
   for (int k = 0; k < NB; ++k) {
-    double acc = 0.0;
-    if (col >= k)
-      for (int r = stripe; r < rows_per; r += NSTRIPE) acc = fma(slab[r * LDS + k], slab[r * LDS + col], acc);
-    part[stripe * NB + col] = acc;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (col >= k) {
+#pragma unroll
+      for (int i = 0; i < RPT; i += 2) {
+        double x, y;
+        lds128(tbase + (unsigned)(k * RS + i) * 8u, x, y);
+        acc0 = fma(x, creg[i], acc0);
+        acc1 = fma(y, creg[i + 1], acc1);
+      }
+    }
+    sts64(part_s + (unsigned)(stripe * NB + col) * 8u, acc0 + acc1);
     __syncthreads();
     double* glk = gl + (k & 1) * NB;
     if (tid < NB) {
-      double sm_ = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-      for (int st = 0; st < NSTRIPE; ++st) sm_ += part[st * NB + tid];
-      glk[tid] = sm_;
+      for (int st = 0; st < NSTRIPE; st += 4) {
+        s0 += lds64(part_s + (unsigned)((st + 0) * NB + tid) * 8u);
+        s1 += lds64(part_s + (unsigned)((st + 1) * NB + tid) * 8u);
+        s2 += lds64(part_s + (unsigned)((st + 2) * NB + tid) * 8u);
+        s3 += lds64(part_s + (unsigned)((st + 3) * NB + tid) * 8u);
+      }
+      glk[tid] = (s0 + s1) + (s2 + s3);
     }
     cluster.sync();
     if (tid < NB) {
@@ -128,7 +299,8 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
       for (int rk = 0; rk < NCLUSTER; ++rk) g += cluster.map_shared_rank(glk, rk)[tid];
       const double gk = __shfl_sync(0xffffffffu, g, k);
       const int c = a.c0 + k;
-      const double pv = sigma * prior_pivot(c, c, a.d, pi1, a.C, a.mode);
+      const int cd = s_cd[k], ca = s_ca[k];
+      const double pv = sigma * prior_pivot_split(c, cd, ca, c, cd, ca, a.d, pi1, a.C, a.mode);
       const double n2 = fma(pv, pv, gk);
       const bool nz = n2 > 0.0;
       const double rn = nz ? fast_rsqrt(n2) : 0.0;
@@ -137,7 +309,7 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
       const double beta = nz ? fast_rcp(fma(pv, nrm, n2)) : 0.0;
       double sj = 0.0;
       if (tid > k) {
-        const double prj = sigma * prior_pivot(c, a.c0 + tid, a.d, pi1, a.C, a.mode);
+        const double prj = sigma * prior_pivot_split(c, cd, ca, a.c0 + tid, jd, ja, a.d, pi1, a.C, a.mode);
         sj = beta * fma(v0, prj, g);
         if (rank == 0) a.R[(size_t)c * a.ld + a.c0 + tid] = fma(-sj, v0, prj);
       }
@@ -151,45 +323,50 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
     __syncthreads();
     if (col > k) {
       const double sj = s_coef[col];
-      for (int r = stripe; r < rows_per; r += NSTRIPE) slab[r * LDS + col] = fma(-sj, slab[r * LDS + k], slab[r * LDS + col]);
+#pragma unroll
+      for (int i = 0; i < RPT; i += 2) {
+        double x, y;
+        lds128(tbase + (unsigned)(k * RS + i) * 8u, x, y);
+        creg[i] = fma(-sj, x, creg[i]);
+        creg[i + 1] = fma(-sj, y, creg[i + 1]);
+      }
+      if (col == k + 1) {  // the next pivot column: publish it for the other lanes of this warp (same rows)
+#pragma unroll
+        for (int i = 0; i < RPT; i += 2) sts128(tbase + (unsigned)(col * RS + i) * 8u, creg[i], creg[i + 1]);
+      }
     }
     __syncwarp();
   }
   __syncthreads();
-  // write Vb back, local Gram of Vb
-  for (int idx = tid; idx < rows_per * NB; idx += PANEL_THREADS) {
-    const int r = idx / NB, k = idx % NB;
-    a.E[(size_t)(row0 + r) * a.ld + a.c0 + k] = slab[r * LDS + k];
+  // Vb (= the final column entries, still in registers) back to E; Gram of Vb as one more block product
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int r = stripe * RPT + i;
+    if (r < rows_per) a.E[(size_t)(row0 + r) * a.ld + a.c0 + col] = creg[i];
   }
-  for (int e = tid; e < NB * NB; e += PANEL_THREADS) {
-    const int i = e / NB, j = e % NB;
-    double acc = 0.0;
-    if (i <= j)
-      for (int r = 0; r < rows_per; ++r) acc = fma(slab[r * LDS + i], slab[r * LDS + j], acc);
-    gram[e] = acc;
-  }
+  block_product();  // wloc = Vb' Vb over this CTA's rows (every column of slabT is in its final state by now)
   cluster.sync();
   if (rank == 0) {
     for (int e = tid; e < NB * NB; e += PANEL_THREADS) {
-      double s = gram[e];
-      for (int rk = 1; rk < NCLUSTER; ++rk) s += cluster.map_shared_rank(gram, rk)[e];
-      gram[e] = s;  // only entries i <= j are meaningful
+      double sg = 0.0;
+#pragma unroll
+      for (int rk = 0; rk < NCLUSTER; ++rk) sg += cluster.map_shared_rank(wloc, rk)[e];
+      gram[e] = sg;
     }
     __syncthreads();
-    // T (upper triangular): T[k][k] = beta_k, T[0:k,k] = -beta_k T[0:k,0:k] (Vb[:,0:k]' Vb[:,k])
+    // T = U^-1 with U = striu(Vb'Vb) + diag(1/beta) (compact WY).  From T U = I, row i of T only depends on itself:
+    //   T[i][i] = beta_i,  T[i][k] = -beta_k sum_{m=i}^{k-1} T[i][m] G[m][k]   -- one thread per row, no barriers
     if (tid < NB) {
-      for (int j = 0; j < NB; ++j) s_T[tid][j] = 0.0;
+      const int i = tid;
+      for (int j = 0; j < i; ++j) s_T[i][j] = 0.0;
+      s_T[i][i] = s_beta[i];
+      for (int k = i + 1; k < NB; ++k) {
+        double acc = 0.0;
+        for (int m = i; m < k; ++m) acc = fma(s_T[i][m], gram[m * NB + k], acc);
+        s_T[i][k] = -s_beta[k] * acc;
+      }
     }
     __syncthreads();
-    for (int k = 0; k < NB; ++k) {
-      if (tid < k) {
-        double acc = 0.0;
-        for (int m = tid; m < k; ++m) acc = fma(s_T[tid][m], gram[m * NB + k], acc);
-        s_T[tid][k] = -s_beta[k] * acc;
-      }
-      if (tid == k) s_T[k][k] = s_beta[k];
-      __syncthreads();
-    }
     for (int e = tid; e < NB * NB; e += PANEL_THREADS) a.T[e] = s_T[e / NB][e % NB];
     if (tid < NB) a.v0[tid] = s_v0[tid];
   }
@@ -361,11 +538,18 @@ struct QrWork {
 inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols, int d, int mode, const Scalars* sc,
                               const IwpConsts& C, const QrWork& wk, cudaStream_t s, long long* launches) {
   const int rows_per = nrows / NCLUSTER;
-  const size_t smem = ((size_t)rows_per * (NB + 1) + (PANEL_THREADS / NB + 2) * NB + NB * NB) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int rpt = rows_per <= 8 * 32 ? 8 : (rows_per <= 16 * 32 ? 16 : 20);
+  if (rows_per > 20 * 32) return cudaErrorInvalidValue;
+  const size_t smem = panel_smem_bytes(rows_per, rpt);
+  void (*kern)(const PanelArgs) = rpt == 8 ? panel_kernel<8> : (rpt == 16 ? panel_kernel<16> : panel_kernel<20>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  auto launch_panel = [&](int c0, int buf, cudaStream_t st) {
+  if (NCLUSTER > 8 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) return e;
+  auto launch_panel = [&](int c0, int buf, cudaStream_t st, int cprev) {
     PanelArgs pa;
+    pa.cprev = cprev;
+    pa.v0p = wk.v0 + (1 - buf) * NB;
+    pa.Tp = wk.T + (1 - buf) * NB * NB;
     pa.E = E;
     pa.R = R;
     pa.ld = ld;
@@ -377,7 +561,7 @@ inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols
     pa.v0 = wk.v0 + buf * NB;
     pa.T = wk.T + buf * NB * NB;
     pa.C = C;
-    panel_kernel<<<NCLUSTER, PANEL_THREADS, smem, st>>>(pa);
+    kern<<<NCLUSTER, PANEL_THREADS, smem, st>>>(pa);
     ++*launches;
   };
   // trailing update of the columns jt in [jt0, jt1) (relative to c0 + NB) with the reflectors of panel c0
@@ -410,22 +594,28 @@ inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols
     *launches += 3;
     return cudaSuccess;
   };
-  launch_panel(0, 0, s);
+  // Look-ahead: the panel chain runs on `aux` (panel j+1 applies panel j's reflectors to its own NB columns
+  // itself), the update of the remaining trailing columns with panel j's reflectors ("wide") on `s`:
+  //   panel(j+1) needs panel(j) [stream order] and wide(j-1);   wide(j) needs panel(j) and wide(j-1) [stream order]
+  if ((e = cudaEventRecord(wk.ev_narrow[0], s)) != cudaSuccess) return e;  // everything that built E
+  if ((e = cudaStreamWaitEvent(wk.aux, wk.ev_narrow[0], 0)) != cudaSuccess) return e;
+  launch_panel(0, 0, wk.aux, -1);
+  if ((e = cudaEventRecord(wk.ev_panel[0], wk.aux)) != cudaSuccess) return e;
+  int last = 0;
   for (int c0 = 0, j = 0; c0 < ncols; c0 += NB, ++j) {
     const int ntrail = ncols - c0 - NB;
     if (ntrail <= 0) break;
     const int par = j & 1;
-    const int nn = ntrail < NB ? ntrail : NB;
-    e = update(c0, par, 0, nn);  // narrow: the next panel's columns
-    if (e != cudaSuccess) return e;
-    if ((e = cudaEventRecord(wk.ev_narrow[par], s)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(wk.aux, wk.ev_narrow[par], 0)) != cudaSuccess) return e;
-    launch_panel(c0 + NB, 1 - par, wk.aux);
+    if (j >= 1 && (e = cudaStreamWaitEvent(wk.aux, wk.ev_narrow[(j - 1) & 1], 0)) != cudaSuccess) return e;
+    launch_panel(c0 + NB, 1 - par, wk.aux, c0);
     if ((e = cudaEventRecord(wk.ev_panel[1 - par], wk.aux)) != cudaSuccess) return e;
-    e = update(c0, par, nn, ntrail);  // wide: everything behind it, overlapping the panel factorisation
+    last = 1 - par;
+    if ((e = cudaStreamWaitEvent(s, wk.ev_panel[par], 0)) != cudaSuccess) return e;
+    e = update(c0, par, NB, ntrail);  // wide: everything behind the next panel
     if (e != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(s, wk.ev_panel[1 - par], 0)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(wk.ev_narrow[par], s)) != cudaSuccess) return e;  // "wide(j) done"
   }
+  if ((e = cudaStreamWaitEvent(s, wk.ev_panel[last], 0)) != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

@@ -230,8 +230,8 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
   if (lorenz) {
     if (cfg->alg == PNDE_ALG_EK1) {
       // large-D dense path (blocked Householder QR with FP64 tensor-core updates, big_dense.cu)
-      if (cfg->d < 32 || cfg->d % 32 != 0 || cfg->d * (cfg->order + 1) > 6144) {
-        g_create_error = "Lorenz-96 EK1 (dense, D >= 64): d must be a multiple of 32 with d (q+1) <= 6144";
+      if (cfg->d < 32 || cfg->d % 32 != 0 || cfg->d * (cfg->order + 1) > 5120) {
+        g_create_error = "Lorenz-96 EK1 (dense, D >= 64): d must be a multiple of 32 with d (q+1) <= 5120";
         return PNDE_ERR_UNSUPPORTED;
       }
       if (cfg->adaptive) {
