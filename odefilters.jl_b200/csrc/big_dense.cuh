@@ -34,7 +34,8 @@ constexpr int NB = 32;        // panel width
 #define PNDE_PANEL_CLUSTER 8
 #endif
 constexpr int NCLUSTER = PNDE_PANEL_CLUSTER;  // CTAs per panel cluster (16 needs the non-portable opt-in)
-constexpr int PANEL_THREADS = 1024;
+constexpr int PANEL_THREADS = 256;
+constexpr int CPW = NB / (PANEL_THREADS / 32);  // panel columns per warp
 
 struct Geometry {
   int d, q, D;
@@ -108,12 +109,19 @@ __device__ __forceinline__ void sts128(unsigned addr, double x, double y) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }
 
-constexpr int panel_kc(int rpt) { return rpt <= 16 ? 4 : 2; }
-constexpr int panel_rs(int rpt) { return (PANEL_THREADS / NB) * rpt + 2; }  // +2: the 32 columns start in different banks
-inline size_t panel_smem_bytes(int rows_per, int rpt) {
-  const int nstripe = PANEL_THREADS / NB;
-  (void)rows_per;
-  return ((size_t)NB * panel_rs(rpt) + (nstripe + 2) * NB + 3 * NB * NB + (panel_kc(rpt) == 4 ? nstripe * 4 * NB : 0)) * sizeof(double);
+constexpr int panel_rs(int rpt) { return 32 * rpt + 2; }  // +2: the 32 columns start in different banks
+inline size_t panel_smem_bytes(int rpt) { return ((size_t)NB * panel_rs(rpt) + 2 * NB + 3 * NB * NB) * sizeof(double); }
+
+// Sum over the warp of 4 values per lane with 6 shuffles: lanes 8c .. 8c+7 return the total of v[c].
+__device__ __forceinline__ double warp_reduce4(const double (&v)[4], int lane) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+  const double u0 = (b4 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, b4 ? v[0] : v[2], 16);
+  const double u1 = (b4 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, b4 ? v[1] : v[3], 16);
+  double t = (b3 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, b3 ? u0 : u1, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 4);
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  return t;
 }
 
 struct PanelArgs {
@@ -131,98 +139,78 @@ struct PanelArgs {
   IwpConsts C;
 };
 
-// Thread (col, stripe): the lanes of a warp are the NB panel columns, warp w owns the RPT consecutive rows
-// [w RPT, (w+1) RPT) of the CTA's slab.  Every thread keeps ITS column's entries of those rows in registers (creg)
-// for the whole kernel.  Shared memory holds a column-major copy slabT[k][r] (so that a thread's rows of one
-// column are contiguous: 128-bit broadcast loads): the previous panel's reflectors during the fused update,
-// afterwards the panel itself, of which only the current pivot column has to be up to date (its owner lane
-// publishes it right after its last update).  The kernel is bound by shared-memory instructions and by the
-// per-column synchronisation chain, not by FP64 throughput.
+// Mapping: 8 warps, warp w owns the CPW = 4 panel columns [4w, 4w+4); the lanes of a warp are rows: lane l holds the
+// row pairs (64 p + 2 l, 64 p + 2 l + 1), p < RPT/2, of its warp's columns in registers (creg) for the whole kernel.
+// Shared memory holds a column-major copy slabT[k][r] (a lane's row pair of one column is one 128-bit access):
+// the previous panel's reflectors during the fused update, afterwards the panel itself, of which only the current
+// pivot column has to be up to date (its owner warp publishes it right after its last update).  A column lives in
+// one warp, so inner products are warp-shuffle reductions (no block reduction), and every pivot value read from
+// shared memory feeds 4 columns.
 template <int RPT>
-__global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS) panel_kernel(const PanelArgs a) {
-  static_assert(RPT % 2 == 0, "rows per thread are processed in pairs");
+__global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS, 1) panel_kernel(const PanelArgs a) {
+  static_assert(RPT % 2 == 0, "rows per lane are processed in pairs");
   extern __shared__ double smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int rows_per = a.nrows / NCLUSTER;
   const int row0 = rank * rows_per;
-  constexpr int NSTRIPE = PANEL_THREADS / NB;
-  constexpr int KC = panel_kc(RPT);                  // reflectors per pass of the block products
-  constexpr int RS = panel_rs(RPT);                  // row stride of slabT (rows >= rows_per are zero padding)
-  double* slab = smem;                               // [NB][RS]
-  double* part = slab + (size_t)NB * RS;             // [NSTRIPE][NB] partial sums + [2][NB] column sums
-  double* gram = part + (NSTRIPE + 2) * NB;          // [NB][NB] Gram of Vb (cluster total, rank 0)
-  double* wloc = gram + NB * NB;                     // [NB][NB] this CTA's share of a block product
-  double* wful = wloc + NB * NB;                     // [NB][NB] cluster total, then W2
-  double* red = (KC == 4) ? wful + NB * NB : part;   // [NSTRIPE][KC][NB]; KC == 2: aliases part + gram (unused then)
+  constexpr int RS = panel_rs(RPT);  // row stride of slabT (rows >= rows_per are zero padding)
+  constexpr int NP = RPT / 2;
+  double* slab = smem;                       // [NB][RS]
+  double* gl = slab + (size_t)NB * RS;       // [2][NB] this CTA's inner products of the current column (double buffered)
+  double* gram = gl + 2 * NB;                // [NB][NB] Gram of Vb (cluster total, rank 0)
+  double* wloc = gram + NB * NB;             // [NB][NB] this CTA's share of a block product
+  double* wful = wloc + NB * NB;             // [NB][NB] cluster total, then W2
   __shared__ double s_v0[NB], s_beta[NB], s_T[NB][NB + 1], s_coef[NB];
   __shared__ int s_cd[NB], s_ca[NB];
-  const int tid = threadIdx.x;
-  const int col = tid % NB, stripe = tid / NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wc0 = warp * CPW;  // first column of this warp
   const double sigma = (a.mode == 0) ? 1.0 : a.sc->sigma;
   const double pi1 = a.sc->pi1;
   const bool fused = a.cprev >= 0;
-  // byte address (shared window) of this thread's first row in column 0 of slabT
-  const unsigned tbase = (unsigned)__cvta_generic_to_shared(slab) + (unsigned)(stripe * RPT) * 8u;
-  const unsigned red_s = (unsigned)__cvta_generic_to_shared(red);
-  const unsigned part_s = (unsigned)__cvta_generic_to_shared(part);
+  // byte address (shared window) of this lane's first row pair in column 0 of slabT
+  const unsigned lbase = (unsigned)__cvta_generic_to_shared(slab) + (unsigned)(2 * lane) * 8u;
 
-  {
-    const int cload = fused ? a.cprev : a.c0;
-    for (int idx = tid; idx < NSTRIPE * RPT * NB; idx += PANEL_THREADS) {
+  auto stage = [&](int cfirst) {  // slabT <- columns [cfirst, cfirst + NB) of this CTA's rows of E (coalesced reads)
+    for (int idx = tid; idx < 32 * RPT * NB; idx += PANEL_THREADS) {
       const int r = idx / NB, k = idx % NB;
-      slab[k * RS + r] = (r < rows_per) ? a.E[(size_t)(row0 + r) * a.ld + cload + k] : 0.0;
+      slab[k * RS + r] = (r < rows_per) ? a.E[(size_t)(row0 + r) * a.ld + cfirst + k] : 0.0;
     }
-  }
-  double creg[RPT];
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    const int r = stripe * RPT + i;
-    creg[i] = (r < rows_per) ? a.E[(size_t)(row0 + r) * a.ld + a.c0 + col] : 0.0;
-  }
-  if (fused) {
-    for (int e = tid; e < NB * NB; e += PANEL_THREADS) s_T[e / NB][e % NB] = a.Tp[e];
-    if (tid < NB) s_v0[tid] = a.v0p[tid];
-  }
+  };
+  stage(a.c0);
   if (tid < NB) {  // (block, dimension) of the panel's columns for the sparse prior pivots
     s_cd[tid] = (a.c0 + tid) / a.d;
     s_ca[tid] = (a.c0 + tid) % a.d;
   }
   __syncthreads();
+  double creg[CPW][RPT];
+#pragma unroll
+  for (int j = 0; j < CPW; ++j)
+#pragma unroll
+    for (int p = 0; p < NP; ++p) lds128(lbase + (unsigned)((wc0 + j) * RS + 64 * p) * 8u, creg[j][2 * p], creg[j][2 * p + 1]);
+  if (fused) {
+    __syncthreads();
+    stage(a.cprev);
+    for (int e = tid; e < NB * NB; e += PANEL_THREADS) s_T[e / NB][e % NB] = a.Tp[e];
+    if (tid < NB) s_v0[tid] = a.v0p[tid];
+    __syncthreads();
+  }
 
-  // wloc[k][col] = sum over this CTA's rows of slabT[k][r] * creg[r]   (k = 0..NB-1)
+  // wloc[k][wc0 + c] = sum over this CTA's rows of slabT[k][r] * creg[c][r]   (k = 0..NB-1)
   auto block_product = [&]() {
-    double acc[KC];
-    for (int k0 = 0; k0 < NB; k0 += KC) {
+    for (int k = 0; k < NB; ++k) {
+      double v[CPW] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        double a0 = 0.0, a1 = 0.0;
+      for (int p = 0; p < NP; ++p) {
+        double x, y;
+        lds128(lbase + (unsigned)(k * RS + 64 * p) * 8u, x, y);
 #pragma unroll
-        for (int i = 0; i < RPT; i += 2) {
-          double x, y;
-          lds128(tbase + (unsigned)((k0 + k) * RS + i) * 8u, x, y);  // one address per warp: broadcast
-          a0 = fma(x, creg[i], a0);
-          a1 = fma(y, creg[i + 1], a1);
-        }
-        acc[k] = a0 + a1;
+        for (int j = 0; j < CPW; ++j) v[j] = fma(y, creg[j][2 * p + 1], fma(x, creg[j][2 * p], v[j]));
       }
-#pragma unroll
-      for (int k = 0; k < KC; ++k) sts64(red_s + (unsigned)((stripe * KC + k) * NB + col) * 8u, acc[k]);
-      __syncthreads();
-      if (tid < KC * NB) {
-        const int kk = tid / NB;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-        for (int st = 0; st < NSTRIPE; st += 4) {
-          s0 += lds64(red_s + (unsigned)(((st + 0) * KC + kk) * NB + col) * 8u);
-          s1 += lds64(red_s + (unsigned)(((st + 1) * KC + kk) * NB + col) * 8u);
-          s2 += lds64(red_s + (unsigned)(((st + 2) * KC + kk) * NB + col) * 8u);
-          s3 += lds64(red_s + (unsigned)(((st + 3) * KC + kk) * NB + col) * 8u);
-        }
-        wloc[(k0 + kk) * NB + col] = (s0 + s1) + (s2 + s3);
-      }
-      __syncthreads();
+      const double t = warp_reduce4(v, lane);
+      if ((lane & 7) == 0) wloc[k * NB + wc0 + (lane >> 3)] = t;
     }
+    __syncthreads();
   };
 
   if (fused) {
@@ -230,67 +218,68 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
     //   W = Vp' C (cluster-wide sum);  W2 = T' (W + diag(v0) pivots);  R rows;  C -= Vp W2
     block_product();
     cluster.sync();
-    {
-      const int k = stripe, c = col;  // one entry of the NB x NB block per thread
+    constexpr int EPT = NB * NB / PANEL_THREADS;  // entries of an NB x NB block per thread
+    double w2r[EPT], pivr[EPT];
+#pragma unroll
+    for (int m = 0; m < EPT; ++m) {
+      const int e = tid + m * PANEL_THREADS, k = e / NB, c = e % NB;
       double w = 0.0;
 #pragma unroll
-      for (int rk = 0; rk < NCLUSTER; ++rk) w += cluster.map_shared_rank(wloc, rk)[k * NB + c];
-      const double piv = sigma * prior_pivot(a.cprev + k, a.c0 + c, a.d, pi1, a.C, a.mode);
-      wful[k * NB + c] = fma(s_v0[k], piv, w);
-      __syncthreads();
-      double w2 = 0.0;
-      for (int m = 0; m <= k; ++m) w2 = fma(s_T[m][k], wful[m * NB + c], w2);  // T' is lower triangular
-      if (rank == 0) a.R[(size_t)(a.cprev + k) * a.ld + a.c0 + c] = fma(-s_v0[k], w2, piv);
-      __syncthreads();
-      wful[k * NB + c] = w2;
-      __syncthreads();
+      for (int rk = 0; rk < NCLUSTER; ++rk) w += cluster.map_shared_rank(wloc, rk)[e];
+      pivr[m] = sigma * prior_pivot(a.cprev + k, a.c0 + c, a.d, pi1, a.C, a.mode);
+      wful[e] = fma(s_v0[k], pivr[m], w);
     }
-    for (int k0 = 0; k0 < NB; k0 += KC) {
+    __syncthreads();
 #pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const double w2 = wful[(k0 + k) * NB + col];
+    for (int m = 0; m < EPT; ++m) {
+      const int e = tid + m * PANEL_THREADS, k = e / NB, c = e % NB;
+      double w2 = 0.0;
+      for (int mm = 0; mm <= k; ++mm) w2 = fma(s_T[mm][k], wful[mm * NB + c], w2);  // T' is lower triangular
+      w2r[m] = w2;
+      if (rank == 0) a.R[(size_t)(a.cprev + k) * a.ld + a.c0 + c] = fma(-s_v0[k], w2, pivr[m]);
+    }
+    __syncthreads();
 #pragma unroll
-        for (int i = 0; i < RPT; i += 2) {
-          double x, y;
-          lds128(tbase + (unsigned)((k0 + k) * RS + i) * 8u, x, y);
-          creg[i] = fma(-x, w2, creg[i]);
-          creg[i + 1] = fma(-y, w2, creg[i + 1]);
+    for (int m = 0; m < EPT; ++m) wful[tid + m * PANEL_THREADS] = w2r[m];
+    __syncthreads();
+    for (int k = 0; k < NB; ++k) {
+      double w2[CPW];
+#pragma unroll
+      for (int j = 0; j < CPW; ++j) w2[j] = wful[k * NB + wc0 + j];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        double x, y;
+        lds128(lbase + (unsigned)(k * RS + 64 * p) * 8u, x, y);
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) {
+          creg[j][2 * p] = fma(-x, w2[j], creg[j][2 * p]);
+          creg[j][2 * p + 1] = fma(-y, w2[j], creg[j][2 * p + 1]);
         }
       }
     }
     __syncthreads();  // every warp is done with Vp: slabT <- C
 #pragma unroll
-    for (int i = 0; i < RPT; i += 2) sts128(tbase + (unsigned)(col * RS + i) * 8u, creg[i], creg[i + 1]);
+    for (int j = 0; j < CPW; ++j)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) sts128(lbase + (unsigned)((wc0 + j) * RS + 64 * p) * 8u, creg[j][2 * p], creg[j][2 * p + 1]);
     __syncthreads();
   }
-  // ---- factorisation.  Per column: partial inner products -> block reduction -> one value per column published
-  // to the cluster -> warp 0 gathers the 8 ranks through DSMEM, computes the reflector scalars and broadcasts s_j.
-  double* gl = part + NSTRIPE * NB;  // [2][NB]
-  const int jd = (a.c0 + col) / a.d, ja = (a.c0 + col) % a.d;  // used by warp 0 (tid == col)
+  // ---- factorisation.  Per column: inner products with the pivot column (warp reductions) -> one value per column
+  // published to the cluster -> warp 0 gathers the ranks through DSMEM, computes the reflector scalars s_j -> update.
+  const int jd = (a.c0 + lane) / a.d, ja = (a.c0 + lane) % a.d;  // used by warp 0 (lane == panel column)
   for (int k = 0; k < NB; ++k) {
-    double acc0 = 0.0, acc1 = 0.0;
-    if (col >= k) {
-#pragma unroll
-      for (int i = 0; i < RPT; i += 2) {
-        double x, y;
-        lds128(tbase + (unsigned)(k * RS + i) * 8u, x, y);
-        acc0 = fma(x, creg[i], acc0);
-        acc1 = fma(y, creg[i + 1], acc1);
-      }
-    }
-    sts64(part_s + (unsigned)(stripe * NB + col) * 8u, acc0 + acc1);
-    __syncthreads();
     double* glk = gl + (k & 1) * NB;
-    if (tid < NB) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (wc0 + CPW - 1 >= k) {
+      double v[CPW] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int st = 0; st < NSTRIPE; st += 4) {
-        s0 += lds64(part_s + (unsigned)((st + 0) * NB + tid) * 8u);
-        s1 += lds64(part_s + (unsigned)((st + 1) * NB + tid) * 8u);
-        s2 += lds64(part_s + (unsigned)((st + 2) * NB + tid) * 8u);
-        s3 += lds64(part_s + (unsigned)((st + 3) * NB + tid) * 8u);
+      for (int p = 0; p < NP; ++p) {
+        double x, y;
+        lds128(lbase + (unsigned)(k * RS + 64 * p) * 8u, x, y);
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) v[j] = fma(y, creg[j][2 * p + 1], fma(x, creg[j][2 * p], v[j]));
       }
-      glk[tid] = (s0 + s1) + (s2 + s3);
+      const double t = warp_reduce4(v, lane);
+      if ((lane & 7) == 0) glk[wc0 + (lane >> 3)] = t;
     }
     cluster.sync();
     if (tid < NB) {
@@ -321,30 +310,36 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
       }
     }
     __syncthreads();
-    if (col > k) {
-      const double sj = s_coef[col];
+    if (wc0 + CPW - 1 > k) {
+      double sj[CPW];
 #pragma unroll
-      for (int i = 0; i < RPT; i += 2) {
+      for (int j = 0; j < CPW; ++j) sj[j] = s_coef[wc0 + j];  // zero for columns <= k
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
         double x, y;
-        lds128(tbase + (unsigned)(k * RS + i) * 8u, x, y);
-        creg[i] = fma(-sj, x, creg[i]);
-        creg[i + 1] = fma(-sj, y, creg[i + 1]);
-      }
-      if (col == k + 1) {  // the next pivot column: publish it for the other lanes of this warp (same rows)
+        lds128(lbase + (unsigned)(k * RS + 64 * p) * 8u, x, y);
 #pragma unroll
-        for (int i = 0; i < RPT; i += 2) sts128(tbase + (unsigned)(col * RS + i) * 8u, creg[i], creg[i + 1]);
+        for (int j = 0; j < CPW; ++j) {
+          creg[j][2 * p] = fma(-sj[j], x, creg[j][2 * p]);
+          creg[j][2 * p + 1] = fma(-sj[j], y, creg[j][2 * p + 1]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CPW; ++j) {
+        if (wc0 + j == k + 1) {  // the next pivot column: publish it for the other warps
+#pragma unroll
+          for (int p = 0; p < NP; ++p) sts128(lbase + (unsigned)((k + 1) * RS + 64 * p) * 8u, creg[j][2 * p], creg[j][2 * p + 1]);
+        }
       }
     }
-    __syncwarp();
+    __syncthreads();
   }
-  __syncthreads();
-  // Vb (= the final column entries, still in registers) back to E; Gram of Vb as one more block product
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    const int r = stripe * RPT + i;
-    if (r < rows_per) a.E[(size_t)(row0 + r) * a.ld + a.c0 + col] = creg[i];
+  // every column of slabT is in its final state (= Vb): back to E, then the Gram of Vb as one more block product
+  for (int idx = tid; idx < rows_per * NB; idx += PANEL_THREADS) {
+    const int r = idx / NB, k = idx % NB;
+    a.E[(size_t)(row0 + r) * a.ld + a.c0 + k] = slab[k * RS + r];
   }
-  block_product();  // wloc = Vb' Vb over this CTA's rows (every column of slabT is in its final state by now)
+  block_product();
   cluster.sync();
   if (rank == 0) {
     for (int e = tid; e < NB * NB; e += PANEL_THREADS) {
@@ -540,7 +535,7 @@ inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols
   const int rows_per = nrows / NCLUSTER;
   const int rpt = rows_per <= 8 * 32 ? 8 : (rows_per <= 16 * 32 ? 16 : 20);
   if (rows_per > 20 * 32) return cudaErrorInvalidValue;
-  const size_t smem = panel_smem_bytes(rows_per, rpt);
+  const size_t smem = panel_smem_bytes(rpt);
   void (*kern)(const PanelArgs) = rpt == 8 ? panel_kernel<8> : (rpt == 16 ? panel_kernel<16> : panel_kernel<20>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
