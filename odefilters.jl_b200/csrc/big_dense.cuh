@@ -384,16 +384,35 @@ __global__ void __launch_bounds__(128) atb_kernel(const double* __restrict__ A, 
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  for (int k0 = kbeg; k0 < kend; k0 += 32) {
-    for (int idx = threadIdx.x; idx < 32 * 32; idx += 128) {
-      const int r = idx / 32, c = idx % 32;
-      As[r * LDA_S + c] = (k0 + r < kend) ? A[(size_t)(k0 + r) * lda + m0 + c] : 0.0;
+  // software pipeline: the next 32-row slice travels from global memory into registers while the tensor cores
+  // work on the current one (8 + 16 doubles per thread)
+  double ra[8], rb[16];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = threadIdx.x + i * 128, r = idx / 32, c = idx % 32;
+      ra[i] = (k0 + r < kend) ? A[(size_t)(k0 + r) * lda + m0 + c] : 0.0;
     }
-    for (int idx = threadIdx.x; idx < 32 * 64; idx += 128) {
-      const int r = idx / 64, c = idx % 64;
-      Bs[r * LDB_S + c] = (k0 + r < kend && n0 + c < N) ? B[(size_t)(k0 + r) * ldb + n0 + c] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int idx = threadIdx.x + i * 128, r = idx / 64, c = idx % 64;
+      rb[i] = (k0 + r < kend && n0 + c < N) ? B[(size_t)(k0 + r) * ldb + n0 + c] : 0.0;
+    }
+  };
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = threadIdx.x + i * 128;
+      As[(idx / 32) * LDA_S + idx % 32] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int idx = threadIdx.x + i * 128;
+      Bs[(idx / 64) * LDB_S + idx % 64] = rb[i];
     }
     __syncthreads();
+    if (k0 + 32 < kend) fetch(k0 + 32);
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       double bf[2];
@@ -565,7 +584,7 @@ inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols
     if (nc <= 0) return cudaSuccess;
     cudaError_t e2 = cudaMemset2DAsync(wk.W + jt0, (size_t)ld * sizeof(double), 0, (size_t)nc * sizeof(double), NB, s);
     if (e2 != cudaSuccess) return e2;
-    static const int kchunk = getenv("PNDE_ATB_KCHUNK") ? atoi(getenv("PNDE_ATB_KCHUNK")) : 64;
+    static const int kchunk = getenv("PNDE_ATB_KCHUNK") ? atoi(getenv("PNDE_ATB_KCHUNK")) : 256;
     dim3 g1((nc + 63) / 64, 1, (nrows + kchunk - 1) / kchunk);
     atb_kernel<<<g1, 128, 0, s>>>(E + c0, ld, E + c0 + NB + jt0, ld, wk.W + jt0, ld, nc, nrows, kchunk);
     W2Args wa;
