@@ -351,15 +351,19 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
     __syncthreads();
     // T = U^-1 with U = striu(Vb'Vb) + diag(1/beta) (compact WY).  From T U = I, row i of T only depends on itself:
     //   T[i][i] = beta_i,  T[i][k] = -beta_k sum_{m=i}^{k-1} T[i][m] G[m][k]   -- one thread per row, no barriers
+    // (the row lives in registers: fully unrolled, entries left of the diagonal are zero and drop out by themselves)
     if (tid < NB) {
       const int i = tid;
-      for (int j = 0; j < i; ++j) s_T[i][j] = 0.0;
-      s_T[i][i] = s_beta[i];
-      for (int k = i + 1; k < NB; ++k) {
+      double Ti[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
         double acc = 0.0;
-        for (int m = i; m < k; ++m) acc = fma(s_T[i][m], gram[m * NB + k], acc);
-        s_T[i][k] = -s_beta[k] * acc;
+#pragma unroll
+        for (int m = 0; m < k; ++m) acc = fma(Ti[m], gram[m * NB + k], acc);  // gram[m][k]: one address per warp
+        Ti[k] = (k < i) ? 0.0 : (k == i ? s_beta[k] : -s_beta[k] * acc);
       }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) s_T[i][k] = Ti[k];
     }
     __syncthreads();
     for (int e = tid; e < NB * NB; e += PANEL_THREADS) a.T[e] = s_T[e / NB][e % NB];
