@@ -40,7 +40,7 @@ struct SmoothCov {
   // Householder triangularisation of the (NR1 + D) x D stack [Y ; T'] -> packed lower factor L (= R').
   // Y: NR1 x D dense rows.  Tt: D x D where Tt[c][i] = T[i][c]; rows of the stack are Tt[c][:].
   template <int NR1>
-  __device__ __forceinline__ static void triangularize(double (&Y)[NR1 > 0 ? NR1 : 1][D], double (&Tt)[D][D],
+  __device__ __forceinline__ static void triangularize_impl(double (&Y)[NR1 > 0 ? NR1 : 1][D], double (&Tt)[D][D],
                                                        double (&L)[NP], int& status) {
 #pragma unroll
     for (int c = 0; c < D; ++c) {
@@ -115,7 +115,7 @@ struct SmoothCov {
   //   out: Rm = R-' packed lower (Rm[tri(j,c)] = R-[c][j]), rinv[c] = 1/R-[c][c], X = top-right block,
   //        Er = Y (backward-kernel noise factor: Y'Y = Sigma - G Sigma- G')
   template <int NR, class XV>
-  __device__ __forceinline__ static void stage1(double (&Er)[NR][D], const double sig, const IwpConsts& C,
+  __device__ __forceinline__ static void stage1_impl(double (&Er)[NR][D], const double sig, const IwpConsts& C,
                                                 double (&Rm)[NP], double (&rinv)[D], XV& X) {
     double sL[q + 1][q + 1];
 #pragma unroll
@@ -173,7 +173,7 @@ struct SmoothCov {
 
   // delta <- G delta = X' (R-^-T delta)
   template <int NREP, class XV>
-  __device__ __forceinline__ static void apply_gain(const double (&Rm)[NP], const double (&rinv)[D], const XV& X,
+  __device__ __forceinline__ static void apply_gain_impl(const double (&Rm)[NP], const double (&rinv)[D], const XV& X,
                                                     double (&delta)[NREP][D]) {
 #pragma unroll
     for (int r = 0; r < NREP; ++r) {
@@ -196,7 +196,7 @@ struct SmoothCov {
   }
 
   // Tt[c][i] = (G Ls)[i][c]:  Z = R-^-T Ls (lower triangular, forward substitution), T = X' Z
-  __device__ __forceinline__ static void gain_times_lower(const double (&Rm)[NP], const double (&rinv)[D],
+  __device__ __forceinline__ static void gain_times_lower_impl(const double (&Rm)[NP], const double (&rinv)[D],
                                                           const RegMat<D>& X, const double (&Ls)[NP],
                                                           double (&Tt)[D][D]) {
     double Z[NP];
@@ -241,7 +241,7 @@ struct SmoothCov {
   // Row-block Householder update: R_acc (upper triangular, stored as its transpose: Racc[tri(j,c)] = R[c][j])
   // <- triangular factor of [R_acc ; rows].  Reflector c = [R_acc[c][c] ; rows[:, c]] (length NCH + 1).
   template <int NCH>
-  __device__ __forceinline__ static void qr_update_rows(double (&Racc)[NP], double (&rows)[NCH][D], int& status) {
+  __device__ __forceinline__ static void qr_update_rows_impl(double (&Racc)[NP], double (&rows)[NCH][D], int& status) {
 #pragma unroll
     for (int c = 0; c < D; ++c) {
       const double pv = Racc[tri(c, c)];
@@ -328,6 +328,57 @@ struct SmoothCov {
     for (int j = 0; j < D; ++j)
 #pragma unroll
       for (int c = 0; c <= j; ++c) Lsv[tri(j, c) * lst] = Racc[tri(j, c)] * PIk[j / dc];
+  }
+
+  // For D >= 10 the fully inlined smoother exceeds what ptxas optimises as one function (it falls back to 32 registers
+  // and a 50 KB stack: measured 10 M steps/s at q = 5); as separate functions the same pieces compile normally
+  // (43 M steps/s).  Below D = 10 everything stays inlined (noinline costs 6x at q = 3).
+  static constexpr bool OUTLINE = (D >= 10);
+  template <int NR1>
+  __device__ __noinline__ static void triangularize_ni(double (&Y)[NR1 > 0 ? NR1 : 1][D], double (&Tt)[D][D], double (&L)[NP],
+                                                       int& status) {
+    triangularize_impl<NR1>(Y, Tt, L, status);
+  }
+  template <int NR1>
+  __device__ __forceinline__ static void triangularize(double (&Y)[NR1 > 0 ? NR1 : 1][D], double (&Tt)[D][D], double (&L)[NP],
+                                                       int& status) {
+    if constexpr (OUTLINE) triangularize_ni<NR1>(Y, Tt, L, status); else triangularize_impl<NR1>(Y, Tt, L, status);
+  }
+  template <int NR, class XV>
+  __device__ __noinline__ static void stage1_ni(double (&Er)[NR][D], const double sig, const IwpConsts& C, double (&Rm)[NP],
+                                                double (&rinv)[D], XV& X) {
+    stage1_impl<NR, XV>(Er, sig, C, Rm, rinv, X);
+  }
+  template <int NR, class XV>
+  __device__ __forceinline__ static void stage1(double (&Er)[NR][D], const double sig, const IwpConsts& C, double (&Rm)[NP],
+                                                double (&rinv)[D], XV& X) {
+    if constexpr (OUTLINE) stage1_ni<NR, XV>(Er, sig, C, Rm, rinv, X); else stage1_impl<NR, XV>(Er, sig, C, Rm, rinv, X);
+  }
+  template <int NREP, class XV>
+  __device__ __noinline__ static void apply_gain_ni(const double (&Rm)[NP], const double (&rinv)[D], const XV& X,
+                                                    double (&delta)[NREP][D]) {
+    apply_gain_impl<NREP, XV>(Rm, rinv, X, delta);
+  }
+  template <int NREP, class XV>
+  __device__ __forceinline__ static void apply_gain(const double (&Rm)[NP], const double (&rinv)[D], const XV& X,
+                                                    double (&delta)[NREP][D]) {
+    if constexpr (OUTLINE) apply_gain_ni<NREP, XV>(Rm, rinv, X, delta); else apply_gain_impl<NREP, XV>(Rm, rinv, X, delta);
+  }
+  __device__ __noinline__ static void gain_times_lower_ni(const double (&Rm)[NP], const double (&rinv)[D], const RegMat<D>& X,
+                                                          const double (&Ls)[NP], double (&Tt)[D][D]) {
+    gain_times_lower_impl(Rm, rinv, X, Ls, Tt);
+  }
+  __device__ __forceinline__ static void gain_times_lower(const double (&Rm)[NP], const double (&rinv)[D], const RegMat<D>& X,
+                                                          const double (&Ls)[NP], double (&Tt)[D][D]) {
+    if constexpr (OUTLINE) gain_times_lower_ni(Rm, rinv, X, Ls, Tt); else gain_times_lower_impl(Rm, rinv, X, Ls, Tt);
+  }
+  template <int NCH>
+  __device__ __noinline__ static void qr_update_rows_ni(double (&Racc)[NP], double (&rows)[NCH][D], int& status) {
+    qr_update_rows_impl<NCH>(Racc, rows, status);
+  }
+  template <int NCH>
+  __device__ __forceinline__ static void qr_update_rows(double (&Racc)[NP], double (&rows)[NCH][D], int& status) {
+    if constexpr (OUTLINE) qr_update_rows_ni<NCH>(Racc, rows, status); else qr_update_rows_impl<NCH>(Racc, rows, status);
   }
 
   template <int NREP>
