@@ -446,57 +446,51 @@ __global__ void __launch_bounds__(128) atb_kernel(const double* __restrict__ A, 
 // (4) Cm[i][n] -= sum_k A[i][k] * B[k][n]   (A: M x 32, B: 32 x N; rank-32 update, DMMA)
 // CTA tile 64 (i) x 64 (n)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) rank_update_kernel(const double* __restrict__ A, int lda,
-                                                          const double* __restrict__ B, int ldb,
-                                                          double* __restrict__ Cm, int ldc, int M, int N) {
+__global__ void __launch_bounds__(256, 3) rank_update_kernel(const double* __restrict__ A, int lda,
+                                                             const double* __restrict__ B, int ldb,
+                                                             double* __restrict__ Cm, int ldc, int M, int N) {
+  // 8 warps, warp w owns rows [8w, 8w+8) of the 64 x 64 tile: 16 accumulators per thread keep the register count low
+  // enough for 3-4 CTAs (24-32 warps) per SM -- the kernel is bound by the latency of its global loads
   constexpr int LDA_S = 36, LDB_S = 68;
   __shared__ double As[64 * LDA_S], Bs[32 * LDB_S];
   const int i0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int idx = threadIdx.x; idx < 64 * 32; idx += 128) {
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
     const int r = idx / 32, c = idx % 32;
     As[r * LDA_S + c] = (i0 + r < M) ? A[(size_t)(i0 + r) * lda + c] : 0.0;
   }
-  for (int idx = threadIdx.x; idx < 32 * 64; idx += 128) {
+  for (int idx = threadIdx.x; idx < 32 * 64; idx += 256) {
     const int r = idx / 64, c = idx % 64;
     Bs[r * LDB_S + c] = (n0 + c < N) ? B[(size_t)r * ldb + n0 + c] : 0.0;
   }
   // the C fragment is read up front (acc starts as C, the product is subtracted through -A), so that all
   // global loads of the tile are in flight together
-  double acc[2][8][2];
+  double acc[8][2];
+  const int i = i0 + warp * 8 + (lane >> 2);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int i = i0 + warp * 16 + mt * 8 + (lane >> 2);
-      const int n = n0 + nt * 8 + 2 * (lane & 3);
-      acc[mt][nt][0] = (i < M && n < N) ? Cm[(size_t)i * ldc + n] : 0.0;
-      acc[mt][nt][1] = (i < M && n + 1 < N) ? Cm[(size_t)i * ldc + n + 1] : 0.0;
-    }
+  for (int nt = 0; nt < 8; ++nt) {
+    const int n = n0 + nt * 8 + 2 * (lane & 3);
+    acc[nt][0] = (i < M && n < N) ? Cm[(size_t)i * ldc + n] : 0.0;
+    acc[nt][1] = (i < M && n + 1 < N) ? Cm[(size_t)i * ldc + n + 1] : 0.0;
+  }
   __syncthreads();
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
-    double af[2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) af[mt] = -As[(warp * 16 + mt * 8 + (lane >> 2)) * LDA_S + kk * 4 + (lane & 3)];
+    const double af = -As[(warp * 8 + (lane >> 2)) * LDA_S + kk * 4 + (lane & 3)];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const double bf = Bs[(kk * 4 + (lane & 3)) * LDB_S + nt * 8 + (lane >> 2)];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf);
+      dmma(acc[nt][0], acc[nt][1], af, bf);
     }
   }
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  if (i < M) {
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const int i = i0 + warp * 16 + mt * 8 + (lane >> 2);
       const int n = n0 + nt * 8 + 2 * (lane & 3);
-      if (i < M) {
-        if (n < N) Cm[(size_t)i * ldc + n] = acc[mt][nt][0];
-        if (n + 1 < N) Cm[(size_t)i * ldc + n + 1] = acc[mt][nt][1];
-      }
+      if (n < N) Cm[(size_t)i * ldc + n] = acc[nt][0];
+      if (n + 1 < N) Cm[(size_t)i * ldc + n + 1] = acc[nt][1];
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -608,7 +602,7 @@ inline cudaError_t blocked_qr(double* E, double* R, int ld, int nrows, int ncols
     wa.C = C;
     w2_kernel<<<(nc + 7) / 8, 256, 0, s>>>(wa);
     dim3 g2((nc + 63) / 64, (nrows + 63) / 64);
-    rank_update_kernel<<<g2, 128, 0, s>>>(E + c0, ld, wk.W + jt0, ld, E + c0 + NB + jt0, ld, nrows, nc);
+    rank_update_kernel<<<g2, 256, 0, s>>>(E + c0, ld, wk.W + jt0, ld, E + c0 + NB + jt0, ld, nrows, nc);
     *launches += 3;
     return cudaSuccess;
   };
