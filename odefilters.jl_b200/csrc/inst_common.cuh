@@ -37,8 +37,9 @@ cudaError_t launch_convert_t(const ModelOps*, const ConvertParams& c, cudaStream
 template <class M>
 cudaError_t launch_smooth_t(const ModelOps*, const SmoothParams& sp, cudaStream_t s) {
   // dense EK1: D*D + D(D+1)/2 doubles of shared memory per thread (X / T' scratch + smoothed factor)
-  const int block = (M::IS_EK1 && M::D >= 10) ? 64 : 128;
-  const size_t smem = M::IS_EK1 ? (size_t)(M::D * M::D + M::D * (M::D + 1) / 2) * block * sizeof(double) : 0;
+  const int block = 128;
+  const size_t smem =
+      SmoothModel<M>::USE_SMEM ? (size_t)(M::D * M::D + M::D * (M::D + 1) / 2) * block * sizeof(double) : 0;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(smoother_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -402,6 +402,7 @@ struct SmoothModel<DenseEK1<VF, q_>> {
   static constexpr int d = M::d, q = M::q, D = M::D, NF = 1, DC = d;
   using SC = SmoothCov<d, q>;
   static constexpr int SREC = D + SC::NP;
+  static constexpr bool USE_SMEM = (D < 10);  // shared-memory scratch of the smoother kernel (see there)
   __device__ static void load_cov(const double* sb, long long n, double* mean, double* cov) {
     double L[SC::NP];
 #pragma unroll
@@ -426,6 +427,7 @@ struct SmoothModel<KronEK0<VF, q_, MVDYN>> {
   static constexpr int d = M::d, q = M::q, D = M::D, NF = M::NF, DC = 1;
   using SC = SmoothCov<1, q>;
   static constexpr int SREC = D + NF * SC::NP + d;  // mean, factors, per-dimension calibration scale
+  static constexpr bool USE_SMEM = false;
   __device__ static void load_cov(const double* sb, long long n, double* mean, double* cov) {
 #pragma unroll
     for (int i = 0; i < D; ++i) mean[i] = sb[(long long)i * n];
@@ -494,7 +496,10 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
 
   double ms[D];          // smoothed mean at i+1 (natural coordinates)
   double Ls[NF][SC::NP]; // smoothed factor(s) at i+1 (natural coordinates), packed lower (Kronecker models)
-  // dense EK1: the D x D scratch X / T' and the smoothed factor live in shared memory (no register spills)
+  // dense EK1 up to D = 8: the D x D scratch X / T' and the smoothed factor live in shared memory (no register
+  // spills).  For D >= 10 that layout leaves 128 threads per SM; the plain path (everything in registers / local
+  // memory, the whole L1 for the stack, 256 threads per SM) is faster there.
+  constexpr bool USE_SMEM = SmoothModel<M>::USE_SMEM;
   extern __shared__ double sm_dyn[];
   const int lst = blockDim.x;
   SmemMat<DCOV> Xs{sm_dyn + threadIdx.x, lst};
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
     for (int f = 0; f < NF; ++f)
 #pragma unroll
       for (int i = 0; i < SC::NP; ++i)
-        o[(long long)(D + f * SC::NP + i) * n] = M::IS_EK1 ? Lsv[i * lst] : Ls[f][i];
+        o[(long long)(D + f * SC::NP + i) * n] = USE_SMEM ? Lsv[i * lst] : Ls[f][i];
     if constexpr (!M::IS_EK1) {
 #pragma unroll
       for (int a = 0; a < d; ++a) o[(long long)(D + NF * SC::NP + a) * n] = dimscale[a];
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
 #pragma unroll
         for (int i = 0; i < DCOV; ++i) Tt[c][i] = 0.0;
       SC::template triangularize<SC::R>(Y, Tt, Ls[f], status);
-      if constexpr (M::IS_EK1) {
+      if constexpr (USE_SMEM) {
 #pragma unroll
         for (int i = 0; i < SC::NP; ++i) Lsv[i * lst] = Ls[0][i];
       }
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
 #pragma unroll
     for (int k = 0; k < D; ++k) mpred[k] = st.m[k];
     apply_A<d, q>(mpred);
-    if constexpr (!M::IS_EK1) {
+    if constexpr (!USE_SMEM) {
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
         // scale smoothed factor at i+1 into P(h) coordinates
@@ -590,7 +595,15 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
           for (int c = 0; c <= r; ++c) Ls[f][SC::tri(r, c)] *= Pk[r / DC];
       }
     }
-    if constexpr (M::IS_EK1) {
+    if constexpr (M::IS_EK1 && !USE_SMEM) {
+      st.F.scale_all(dense_cal);
+      double delta[1][D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) delta[0][k] = fma(Pk[k / d], ms[k], -mpred[k]);
+      SC::template step<1>(st.F, sig[0], sp.C, Ls[0], delta, status);
+#pragma unroll
+      for (int k = 0; k < D; ++k) ms[k] = (st.m[k] + delta[0][k]) * PIk[k / d];
+    } else if constexpr (M::IS_EK1) {
       st.F.scale_all(dense_cal);
       double delta[1][D];
 #pragma unroll
@@ -627,7 +640,7 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
         for (int k = 0; k <= q; ++k) ms[k * d + a] = (st.m[k * d + a] + delta[0][k]) * PIk[k];
       }
     }
-    if constexpr (!M::IS_EK1) {
+    if constexpr (!USE_SMEM) {
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
 #pragma unroll
