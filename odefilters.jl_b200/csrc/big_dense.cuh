@@ -14,9 +14,11 @@
 //             new posterior factor.
 //   The other prior rows are sparse "pivot rows" generated on the fly (prior_pivot): reflector c is
 //   [pivot(c,c) ; E[:,c]], so V = [diag(v0) ; Vb] and the compact-WY T needs only Vb'Vb.
-// One panel of NB = 32 columns: (1) cluster panel factorisation (8 CTAs, slab in shared memory,
-// DSMEM reductions), (2) W = Vb' E_trail (DMMA, split-K atomics), (3) W2 = T'(W + pivots), R rows,
-// (4) E_trail -= Vb W2 (DMMA).
+// One panel of NB = 32 columns: (1) cluster panel factorisation (8 CTAs, entries in registers, pivot column in
+// shared memory, warp-shuffle + DSMEM reductions), preceded inside the same kernel by the previous panel's block
+// reflector applied to these 32 columns (look-ahead), (2) W = Vb' E_trail (DMMA, split-K atomics),
+// (3) W2 = T'(W + pivots), R rows, (4) E_trail -= Vb W2 (DMMA).  (2)-(4) cover the columns behind the next panel
+// and run on the main stream while the next panel is factored on a high-priority auxiliary stream.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -535,10 +537,9 @@ __global__ void __launch_bounds__(256) w2_kernel(const W2Args a) {
 }
 
 // Blocked QR driver: E (nrows x ncols, ld) -> R rows [0, ncols) (upper triangular part written).
-// nrows % (8 * NCLUSTER) == 0, ncols % NB == 0.  work: W [NB][ld], v0 [2][NB], T [2][NB*NB].
-// Look-ahead: after panel j, the NB columns of panel j+1 are updated first ("narrow" update) so that the
-// factorisation of panel j+1 (8 SMs, stream `aux`) overlaps the update of the remaining trailing columns
-// with panel j's reflectors ("wide" update, main stream).
+// nrows % NCLUSTER == 0 with nrows / NCLUSTER <= 640, ncols % NB == 0.  work: W [NB][ld], v0 [2][NB], T [2][NB*NB].
+// Look-ahead: the panel kernel of panel j+1 (8 SMs, stream `aux`) applies panel j's reflectors to its own NB columns
+// and overlaps the update of the remaining trailing columns with panel j's reflectors ("wide" update, main stream).
 struct QrWork {
   double* W;
   double* v0;  // [2][NB]

@@ -308,7 +308,7 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
     }
     std::string rerr;
     ops = rtc_build(cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV, custom->d, custom->np, custom->f_body,
-                    custom->jac_body, rerr, as_ieks);
+                    custom->jac_body, rerr, as_ieks, cfg->adaptive ? 1 : 0);
     if (!ops) {
       g_create_error = rerr;
       return PNDE_ERR_ARG;
