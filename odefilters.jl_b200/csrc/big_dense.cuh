@@ -38,6 +38,7 @@ constexpr int NB = 32;        // panel width
 constexpr int NCLUSTER = PNDE_PANEL_CLUSTER;  // CTAs per panel cluster (16 needs the non-portable opt-in)
 constexpr int PANEL_THREADS = 256;
 constexpr int CPW = NB / (PANEL_THREADS / 32);  // panel columns per warp
+static_assert(CPW == 4, "the panel kernel loads and reduces its columns four at a time");
 
 struct Geometry {
   int d, q, D;
@@ -179,24 +180,35 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
       slab[k * RS + r] = (r < rows_per) ? a.E[(size_t)(row0 + r) * a.ld + cfirst + k] : 0.0;
     }
   };
-  stage(a.c0);
+  // this thread's entries straight from global memory (4 consecutive doubles per row: one full sector per lane)
+  // while the block stages what the sweep reads from shared memory first: Vp (fused) or the panel itself
+  double creg[CPW][RPT];
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = 64 * p + 2 * lane + h;
+      if (r < rows_per) {
+        const double2* src = reinterpret_cast<const double2*>(a.E + (size_t)(row0 + r) * a.ld + a.c0 + wc0);
+        const double2 v01 = src[0], v23 = src[1];
+        creg[0][2 * p + h] = v01.x;
+        creg[1][2 * p + h] = v01.y;
+        creg[2][2 * p + h] = v23.x;
+        creg[3][2 * p + h] = v23.y;
+      } else {
+        creg[0][2 * p + h] = creg[1][2 * p + h] = creg[2][2 * p + h] = creg[3][2 * p + h] = 0.0;
+      }
+    }
+  stage(fused ? a.cprev : a.c0);
   if (tid < NB) {  // (block, dimension) of the panel's columns for the sparse prior pivots
     s_cd[tid] = (a.c0 + tid) / a.d;
     s_ca[tid] = (a.c0 + tid) % a.d;
   }
-  __syncthreads();
-  double creg[CPW][RPT];
-#pragma unroll
-  for (int j = 0; j < CPW; ++j)
-#pragma unroll
-    for (int p = 0; p < NP; ++p) lds128(lbase + (unsigned)((wc0 + j) * RS + 64 * p) * 8u, creg[j][2 * p], creg[j][2 * p + 1]);
   if (fused) {
-    __syncthreads();
-    stage(a.cprev);
     for (int e = tid; e < NB * NB; e += PANEL_THREADS) s_T[e / NB][e % NB] = a.Tp[e];
     if (tid < NB) s_v0[tid] = a.v0p[tid];
-    __syncthreads();
   }
+  __syncthreads();
 
   // wloc[k][wc0 + c] = sum over this CTA's rows of slabT[k][r] * creg[c][r]   (k = 0..NB-1)
   auto block_product = [&]() {
@@ -232,13 +244,25 @@ __global__ void __cluster_dims__(NCLUSTER, 1, 1) __launch_bounds__(PANEL_THREADS
       wful[e] = fma(s_v0[k], pivr[m], w);
     }
     __syncthreads();
+    {
+      // W2[k][c] = sum_{mm <= k} T[mm][k] (W + ...)[mm][c]  (T' is lower triangular).  A thread's EPT entries share
+      // the column c (PANEL_THREADS % NB == 0): one pass over mm feeds all of them
+      const int c = tid % NB, kg = tid / NB;
 #pragma unroll
-    for (int m = 0; m < EPT; ++m) {
-      const int e = tid + m * PANEL_THREADS, k = e / NB, c = e % NB;
-      double w2 = 0.0;
-      for (int mm = 0; mm <= k; ++mm) w2 = fma(s_T[mm][k], wful[mm * NB + c], w2);  // T' is lower triangular
-      w2r[m] = w2;
-      if (rank == 0) a.R[(size_t)(a.cprev + k) * a.ld + a.c0 + c] = fma(-s_v0[k], w2, pivr[m]);
+      for (int m = 0; m < EPT; ++m) w2r[m] = 0.0;
+      for (int mm = 0; mm < NB; ++mm) {
+        const double w = wful[mm * NB + c];
+#pragma unroll
+        for (int m = 0; m < EPT; ++m) {
+          const int k = kg + m * (PANEL_THREADS / NB);
+          if (mm <= k) w2r[m] = fma(s_T[mm][k], w, w2r[m]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < EPT; ++m) {
+        const int k = kg + m * (PANEL_THREADS / NB);
+        if (rank == 0) a.R[(size_t)(a.cprev + k) * a.ld + a.c0 + c] = fma(-s_v0[k], w2r[m], pivr[m]);
+      }
     }
     __syncthreads();
 #pragma unroll
