@@ -12,7 +12,15 @@
 #pragma once
 #include "model_ops.cuh"
 
+// The smoother's hot loop is ~100 KB of straight-line code and is sensitive to instruction-cache misses (ncu: 13 % of
+// the stall samples are no_instruction): the two loops of step_cols_smem that only index shared memory are kept
+// rolled (PNDE_SMOOTH_UNROLL = 1: -12 % instructions, -15 % time at q = 3).
+#ifndef PNDE_SMOOTH_UNROLL
+#define PNDE_SMOOTH_UNROLL 1
+#endif
+
 namespace pnde {
+constexpr int kSmoothUnroll = PNDE_SMOOTH_UNROLL;
 
 // D x D matrix either in registers or in shared memory (one column of shared memory per thread, stride =
 // block size, so consecutive threads hit consecutive banks)
@@ -295,7 +303,7 @@ struct SmoothCov {
       }
     }
     // T' in place of X: Tt[c][i] = sum_{k >= c} X[k][i] Z[k][c], one column i of X at a time
-#pragma unroll
+#pragma unroll kSmoothUnroll
     for (int i = 0; i < D; ++i) {
       double xc[D];
 #pragma unroll
@@ -314,7 +322,7 @@ struct SmoothCov {
     for (int i = 0; i < NP; ++i) Racc[i] = 0.0;
     qr_update_rows<NR>(Racc, cols, status);
     constexpr int CH = 4;
-#pragma unroll
+#pragma unroll kSmoothUnroll
     for (int r0 = 0; r0 < D; r0 += CH) {
       double rows[CH][D];
 #pragma unroll
@@ -564,10 +572,7 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
       for (int k = 0; k < REC; ++k) asm volatile(PNDE_PREFETCH_OP " [%0];" ::"l"(rp + (long long)k * n));
     }
     const double h = rn[0] - ri[0];
-    if (h == 0.0) {  // src/smoothing.jl:13-16
-      write(i);
-      continue;
-    }
+    if (h != 0.0) {  // h == 0: the state is kept as it is (src/smoothing.jl:13-16); one copy of write() below
     double Pk[q + 1], PIk[q + 1];
     precond_scales<q>(h, Pk, PIk);
     typename M::State st;
@@ -654,6 +659,7 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
 #pragma unroll
     for (int k = 0; k < D; ++k)
       if (!(ms[k] == ms[k])) status |= 1;
+    }
     write(i);
   }
   if (ns >= 2) {
