@@ -24,6 +24,7 @@ from .api import (  # noqa: F401
     pinned_empty,
     SRMatrix,
     shard_range,
+    shard_strided,
     solve,
     solve_ieks,
     mean,
@@ -33,4 +34,4 @@ from .api import (  # noqa: F401
 from . import _lib  # noqa: F401
 
 __all__ = ["CustomVectorField", "EK0", "EK1", "EnsembleB200", "EnsembleProblem", "EnsembleSolution", "FilterSolver", "Gaussian",
-           "IEKS", "ODEProblem", "ProbODESolution", "SRMatrix", "pinned_empty", "shard_range", "solve", "solve_ieks", "mean", "std", "var"]
+           "IEKS", "ODEProblem", "ProbODESolution", "SRMatrix", "pinned_empty", "shard_range", "shard_strided", "solve", "solve_ieks", "mean", "std", "var"]

@@ -137,6 +137,14 @@ def shard_range(n: int, rank: int, world: int):
     return lo, hi
 
 
+def shard_strided(n: int, rank: int, world: int) -> np.ndarray:
+    """Interleaved assignment rank, rank + world, ...: for adaptive ensembles whose cost varies smoothly with
+    the trajectory index, every rank then sees the same mix of cheap and expensive trajectories."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return np.arange(rank, n, world)
+
+
 # --------------------------------------------------------------------------------------------
 # Result containers (src/squarerootmatrix.jl, GaussianDistributions.Gaussian, src/solution.jl:8-24)
 # --------------------------------------------------------------------------------------------
@@ -297,6 +305,7 @@ class EnsembleSolution:
     retcode: np.ndarray
     converged: bool = True
     _cache: dict = field(default_factory=dict)
+    _slot: Optional[np.ndarray] = None  # device slot of trajectory i when the ensemble was reordered (balance_by)
 
     def __len__(self):
         return self.n
@@ -306,7 +315,7 @@ class EnsembleSolution:
         return self.mean[:, : self.solver.d]
 
     def __getitem__(self, i: int) -> ProbODESolution:
-        return self.solver.solution(i)
+        return self.solver.solution(int(self._slot[i]) if self._slot is not None else i)
 
 
 # --------------------------------------------------------------------------------------------
@@ -585,20 +594,30 @@ def solve_ieks(prob, alg: _EK, *args, iterations: int = 10, **kwargs):
 
 def solve(prob, alg: _EK, ensemblealg: Optional[EnsembleB200] = None, *, trajectories: Optional[int] = None,
           abstol=1e-6, reltol=1e-3, adaptive=True, dt=None, dense=None, save_everystep=None, save_stride=None,
-          maxiters=100000, max_saved=0, device=-1, **ctrl):
+          maxiters=100000, max_saved=0, device=-1, balance_by=None, **ctrl):
     """solve(prob, EK0/EK1(order=q); abstol, reltol, adaptive, dt) -> ProbODESolution, or
     solve(EnsembleProblem, alg, EnsembleB200(); trajectories=N, ...) -> EnsembleSolution.
 
     ``dense`` must equal ``alg.smooth`` (the reference asserts this, src/perform_step.jl:3); it defaults to it.
+    ``balance_by`` (ensembles): a per-trajectory cost key, e.g. the stiffness parameter.  The ensemble is processed in
+    the order of that key so that the 32 trajectories of a warp take similar numbers of adaptive steps (SURVEY 8e;
+    -16 % on BASELINE config 3); results are returned in the caller's order.
     """
     if dense is not None and bool(dense) != bool(alg.smooth):
         raise ValueError("`dense` and `smooth` should have the same value! ")
     ensemble = isinstance(prob, EnsembleProblem)
     if save_everystep is None:
         save_everystep = not ensemble
+    perm = None
     if ensemble:
         u0, p, n = _ensemble_arrays(prob, trajectories)
         base = prob.prob
+        if balance_by is not None:
+            key = np.asarray(balance_by, dtype=np.float64)
+            if key.shape != (n,):
+                raise ValueError("balance_by must hold one key per trajectory")
+            perm = np.argsort(key, kind="stable")
+            u0, p = u0[perm], p[perm]
     else:
         base = prob
         u0, p, n = base.u0[None, :], base.p[None, :], 1
@@ -619,6 +638,12 @@ def solve(prob, alg: _EK, ensemblealg: Optional[EnsembleB200] = None, *, traject
     if not ensemble:
         return solver.solution(0, counts)
     mean, cov, tf, ll = solver.final()
+    slot = None
+    if perm is not None:  # back to the caller's order
+        slot = np.empty(n, dtype=np.int64)
+        slot[perm] = np.arange(n)
+        mean, cov, tf, ll = mean[slot], cov[slot], tf[slot], ll[slot]
+        counts = {k: v[slot] for k, v in counts.items()}
     return EnsembleSolution(solver=solver, n=n, mean=mean, cov=cov, t_final=tf, log_likelihood=ll,
                             destats={k: counts[k] for k in ("naccept", "nreject", "nf", "njacs")},
-                            retcode=counts["retcode"], converged=bool((counts["retcode"] == 0).all()))
+                            retcode=counts["retcode"], converged=bool((counts["retcode"] == 0).all()), _slot=slot)

@@ -771,3 +771,20 @@ def test_distinct_handles_from_distinct_host_threads():
     [t.join() for t in th]
     for (m, c), (mr, cr) in zip(out, ref):
         assert np.array_equal(m, mr) and np.array_equal(c, cr)   # bitwise: same kernel, same inputs
+
+
+def test_balanced_ensemble_order_returns_results_in_caller_order():
+    """balance_by: the ensemble runs sorted by a cost key, results come back in the caller's order."""
+    import odefilters_b200 as B
+
+    rng = np.random.default_rng(5)
+    n = 700
+    mu = np.exp(rng.uniform(np.log(5.0), np.log(50.0), n))
+    prob = B.ODEProblem("vanderpol", [0.0, 3.0 ** 0.5], (0.0, 1.0), (10.0,))
+    ep = B.EnsembleProblem(prob, p=mu[:, None])
+    a = B.solve(ep, B.EK1(order=3, smooth=False), B.EnsembleB200(), trajectories=n, save_everystep=True)
+    b = B.solve(ep, B.EK1(order=3, smooth=False), B.EnsembleB200(), trajectories=n, save_everystep=True, balance_by=mu)
+    assert np.array_equal(a.mean, b.mean) and np.array_equal(a.destats["naccept"], b.destats["naccept"])
+    assert np.array_equal(a.retcode, b.retcode) and np.array_equal(a.t_final, b.t_final)
+    for i in (0, 17, n - 1):
+        assert np.array_equal(a[i].t, b[i].t) and np.array_equal(a[i].u, b[i].u)

@@ -166,3 +166,14 @@ def test_gaussian_list_moments():
     assert np.array_equal(B.mean(gl), gl.mu)
     assert np.allclose(B.var(gl), np.stack([np.diag(c) for c in cov]))
     assert np.allclose(B.std(gl[2]), np.sqrt(np.diag(cov[2])))
+
+
+def test_strided_sharding_covers_the_ensemble_once():
+    import odefilters_b200 as B
+
+    n, world = 1003, 4
+    parts = [B.shard_strided(n, r, world) for r in range(world)]
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(n))
+    assert max(len(x) for x in parts) - min(len(x) for x in parts) <= 1
+    with pytest.raises(ValueError):
+        B.shard_strided(n, 4, 4)
