@@ -93,18 +93,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // (1) panel factorisation: columns [c0, c0+NB) of E (nrows x .), cluster of NCLUSTER CTAs
 // outputs: E panel <- Vb;  R[c0+k][c0+j] (k <= j < NB);  v0[NB], T[NB][NB] (compact WY)
 // ---------------------------------------------------------------------------------------------
-// Explicit shared-window accesses for the hot loops of the panel kernel: with cluster launch the compiler addresses
-// `extern __shared__` through the cluster window and, short of registers, rebuilds the window base (S2R CgaCtaId)
-// in front of every access.
-__device__ __forceinline__ double lds64(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts64(unsigned addr, double v) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
-}
-
+// Explicit 128-bit shared-window accesses for the hot loops of the panel kernel (with cluster launch the compiler
+// addresses `extern __shared__` through the cluster window and may rebuild the window base in front of an access).
 __device__ __forceinline__ void lds128(unsigned addr, double& x, double& y) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
 }
