@@ -37,7 +37,7 @@ cudaError_t launch_convert_t(const ModelOps*, const ConvertParams& c, cudaStream
 template <class M>
 cudaError_t launch_smooth_t(const ModelOps*, const SmoothParams& sp, cudaStream_t s) {
   // dense EK1: D*D + D(D+1)/2 doubles of shared memory per thread (X / T' scratch + smoothed factor)
-  const int block = 128;
+  const int block = PNDE_SMOOTH_BLOCK;  // compile-time stride of the shared-memory scratch
   const size_t smem =
       SmoothModel<M>::USE_SMEM ? (size_t)(M::D * M::D + M::D * (M::D + 1) / 2) * block * sizeof(double) : 0;
   if (smem > 48 * 1024) {
