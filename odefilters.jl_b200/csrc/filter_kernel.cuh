@@ -84,8 +84,15 @@ __device__ __forceinline__ void precond_scales(double h, double (&P)[q + 1], dou
     v *= h;
     PI[k] = v;
   }
+  // P_k = 1 / PI_k with two divisions instead of q + 1: P_q = 1 / sqrt(h), P_{k-1} = P_k / h
+  const double ih = 1.0 / h;
+  double w = 1.0 / PI[q];
+  P[q] = w;
 #pragma unroll
-  for (int k = 0; k <= q; ++k) P[k] = 1.0 / PI[k];
+  for (int k = q - 1; k >= 0; --k) {
+    w *= ih;
+    P[k] = w;
+  }
 }
 
 __device__ __forceinline__ double ulp_of(double x) {  // Julia eps(x)
