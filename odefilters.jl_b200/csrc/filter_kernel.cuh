@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
   } else {
     dt = K.dt;
   }
-  double dtpropose = dt, qold = K.qoldinit, q11 = 1.0;
+  const double lqold0 = log(K.qoldinit);
+  double dtpropose = dt, lqold = lqold0, q11 = 1.0;
   bool accepted_prev = true;
   double hcur = -1.0;  // fixed-step mode: the h the state is currently preconditioned with (<0: natural)
   double Pk[q + 1], PIk[q + 1];
@@ -632,25 +633,27 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
     // ---- loopfooter! ----
     const double ttmp = t + dt;
     if (ADAPTIVE) {
-      double qc;
+      double qc, lE = __longlong_as_double(0xfff0000000000000LL);  // -inf: EEst == 0
       if (EEst == 0.0) {
         qc = 1.0 / K.qmax;
       } else {
         // EEst^beta1 / qold^beta2 (PI controller) through exp/log: 2-3 ulp instead of pow's <= 2, a
         // third of its instructions (-13 % on an adaptive EK1(3) ensemble); both EEst and qold are > 0 here
-        q11 = exp(K.beta1 * log(EEst));
-        qc = q11 * exp(-K.beta2 * log(qold));
+        // (one log and one exp per step: log qold is carried along, q11 itself is only needed after a rejection)
+        lE = log(EEst);
+        qc = exp(K.beta1 * lE - K.beta2 * lqold);
         qc = fmax(1.0 / K.qmax, fmin(1.0 / K.qmin, qc / K.gamma));
       }
       if (accept) {
         ++nacc;
         if (K.qsteady_min <= qc && qc <= K.qsteady_max) qc = 1.0;
-        qold = fmax(EEst, K.qoldinit);
+        lqold = fmax(lE, lqold0);  // qold = max(EEst, qoldinit)
         const double dtnew = dt / qc;
         t = (fabs(ttmp - K.t1) < 10.0 * ulp_of(fmax(t, K.t1))) ? K.t1 : ttmp;
         dtpropose = fmax(K.dtmin, fmin(K.dtmax, dtnew));
       } else {
         ++nrej;
+        q11 = exp(K.beta1 * lE);
       }
     } else {
       ++nacc;
