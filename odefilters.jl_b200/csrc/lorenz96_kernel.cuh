@@ -337,17 +337,8 @@ __global__ void __launch_bounds__(LORENZ_THREADS) lorenz96_kernel(const LorenzPa
     }
     const double ttmp = t + dt;
     if (adaptive) {
-      double qc, lE = __longlong_as_double(0xfff0000000000000LL);  // -inf: EEst == 0
-      if (EEst == 0.0) {
-        qc = 1.0 / K.qmax;
-      } else {
-        // EEst^beta1 / qold^beta2 (PI controller) through exp/log: 2-3 ulp instead of pow's <= 2, a
-        // third of its instructions (-13 % on an adaptive EK1(3) ensemble); both EEst and qold are > 0 here
-        // (one log and one exp per step: log qold is carried along, q11 itself is only needed after a rejection)
-        lE = log(EEst);
-        qc = exp(K.beta1 * lE - K.beta2 * lqold);
-        qc = fmax(1.0 / K.qmax, fmin(1.0 / K.qmin, qc / K.gamma));
-      }
+      double lE;
+      double qc = controller_factor(EEst, K, lqold, lE);
       if (accept) {
         ++nacc;
         if (K.qsteady_min <= qc && qc <= K.qsteady_max) qc = 1.0;
