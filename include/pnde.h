@@ -18,8 +18,9 @@
  * Conventions: plain C, no exceptions; all reals are double, all sizes int64_t.  Return code 0 =
  * ok, <0 = argument / CUDA error (text via pnde_last_error).  Per-trajectory numerical failures are
  * DATA (the retcode array), never a failed call.  The caller allocates every output buffer; the
- * library owns device memory inside the handle.  A handle is bound to one CUDA device and is not
- * re-entrant; distinct handles may be used from distinct host threads / processes (one per GPU).
+ * library owns device memory inside the handle.  A handle is bound to one CUDA device -- or, with
+ * cfg.n_devices > 1, to several, over which it shards the ensemble -- and is not re-entrant; distinct handles
+ * may be used from distinct host threads / processes.
  * There is no CPU fallback: every entry point that computes fails with PNDE_ERR_CUDA when no
  * device is present.
  *
@@ -35,7 +36,8 @@
 extern "C" {
 #endif
 
-#define PNDE_ABI_VERSION 1
+#define PNDE_ABI_VERSION 2 /* 2: n_devices / flags / device_list appended to pnde_config */
+#define PNDE_MAX_DEVICES 16
 
 /* return codes */
 #define PNDE_OK 0
@@ -84,6 +86,16 @@ extern "C" {
 #define PNDE_RET_NONFINITE 3
 #define PNDE_RET_HISTORY_FULL 4
 #define PNDE_RET_DTMIN 5
+#define PNDE_RET_ZERO_RESIDUAL 6 /* only with PNDE_FLAG_REFERENCE_QUIRKS: FixedDiffusion met an exactly zero residual,
+                                    where the reference throws (src/diffusions.jl:18-20) */
+
+/* pnde_config.flags */
+#define PNDE_FLAG_REFERENCE_QUIRKS 1 /* reproduce two accidents of the reference instead of the intended behaviour:
+   (a) static diffusion model + smooth = 0: sol.pu keeps the UNcalibrated covariances, because savevalues!
+       (src/integrator_utils.jl:43-45) fills it before postamble! rescales x_filt (:4-18) -- pnde_get_marginals(
+       PNDE_HIST_FILTERED) then returns uncalibrated cov_u (pnde_get_history stays calibrated, like sol.x_filt);
+   (b) FixedDiffusion with z == 0 exactly: the reference returns one value where two are destructured and throws
+       (src/diffusions.jl:18-20) -- the trajectory ends with PNDE_RET_ZERO_RESIDUAL instead of sigma^2 = 0. */
 
 /* which states pnde_get_history returns */
 #define PNDE_HIST_FILTERED 0
@@ -109,6 +121,13 @@ typedef struct pnde_config {
   double qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit, beta1, beta2, dtmin, dtmax;
   int64_t maxiters;  /* attempted steps per trajectory (default 100000) */
   int64_t max_saved; /* history slots per trajectory incl. the initial state; 0 = derive (fixed step) */
+  /* --- ABI version 2 --- */
+  int32_t n_devices; /* 0 or 1: the single device `device`.  > 1: the ensemble is sharded over device_list[0..n_devices):
+                        contiguous blocks of trajectories, one host thread + stream per GPU inside every call, results
+                        written straight into disjoint slices of the caller's arrays (EnsembleProblem over
+                        the GPUs of one box, no exchange step).  Every entry point then acts on the whole ensemble. */
+  int32_t flags;     /* PNDE_FLAG_* */
+  int32_t device_list[PNDE_MAX_DEVICES];
 } pnde_config;
 
 typedef struct pnde_handle pnde_handle;
@@ -155,7 +174,8 @@ int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const 
 int pnde_solve_ensemble_to_host(pnde_handle* h, int64_t n_traj, const double* u0, const double* p, double* mean,
                                 double* cov, double* t_final, double* loglik);
 
-/* Split form, so that inputs can stay resident in HBM across runs. */
+/* Split form, so that inputs can stay resident in HBM across runs.  pnde_upload returns after the copies have
+ * completed: u0 / p may be reused or freed immediately. */
 int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* p);
 int pnde_run(pnde_handle* h);         /* initialize! + the whole solve! loop, asynchronous.  PNDE_ALG_IEKS: every
                                          pnde_run after the first one since pnde_upload linearises at the solution

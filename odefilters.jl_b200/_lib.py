@@ -8,7 +8,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PNDE_LIB") or os.path.join(_HERE, "libpnde.so")  # PNDE_LIB: experiment builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+MAX_DEVICES = 16
+FLAG_REFERENCE_QUIRKS = 1
 ALG_EK0, ALG_EK1, ALG_IEKS = 0, 1, 2
 DIFFUSIONS = {"dynamic": 0, "fixed": 1, "fixedMAP": 2, "dynamicMV": 3, "fixedMV": 4}
 VF_KINDS = {"fhn_readme": 0, "fhn_lib": 1, "lotka_volterra": 2, "vanderpol": 3, "linear2": 4, "logistic": 5,
@@ -17,7 +19,8 @@ VF_DIMS = {"fhn_readme": (2, 3), "fhn_lib": (2, 4), "lotka_volterra": (2, 4), "v
            "logistic": (1, 1), "linear1": (1, 1)}
 SAVE_FINAL, SAVE_EVERY, SAVE_STRIDE = 0, 1, 2
 HIST_FILTERED, HIST_SMOOTHED = 0, 1
-RETCODES = {0: "Success", 1: "MaxIters", 2: "DtNaN", 3: "Unstable", 4: "HistoryFull", 5: "DtLessThanMin"}
+RETCODES = {0: "Success", 1: "MaxIters", 2: "DtNaN", 3: "Unstable", 4: "HistoryFull", 5: "DtLessThanMin",
+            6: "ZeroResidual"}
 
 
 class PndeConfig(C.Structure):
@@ -29,6 +32,7 @@ class PndeConfig(C.Structure):
         ("qmin", C.c_double), ("qmax", C.c_double), ("gamma", C.c_double), ("qsteady_min", C.c_double),
         ("qsteady_max", C.c_double), ("qoldinit", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
         ("dtmin", C.c_double), ("dtmax", C.c_double), ("maxiters", C.c_int64), ("max_saved", C.c_int64),
+        ("n_devices", C.c_int32), ("flags", C.c_int32), ("device_list", C.c_int32 * MAX_DEVICES),
     ]
 
 

@@ -124,7 +124,30 @@ class EnsembleProblem:
 
 
 class EnsembleB200:
-    """Ensemble algorithm: all trajectories in one device launch (stands where EnsembleThreads does)."""
+    """Ensemble algorithm: all trajectories in one device launch (stands where EnsembleThreads does).
+
+    ``devices``: CUDA device ordinals to shard the ensemble over inside the ONE library call (contiguous blocks, one
+    host thread + stream per GPU, results written into disjoint slices of the output arrays).  None: the
+    current device.  ``EnsembleB200(devices="all")`` uses every visible GPU."""
+
+    def __init__(self, devices=None):
+        self.devices = devices
+
+
+def device_count() -> int:
+    """Number of visible CUDA devices (cudaGetDeviceCount through the runtime the library links)."""
+    import ctypes.util
+
+    for name in ("libcudart.so.12", "libcudart.so", ctypes.util.find_library("cudart")):
+        if not name:
+            continue
+        try:
+            rt = C.CDLL(name)
+        except OSError:
+            continue
+        n = C.c_int(0)
+        return int(n.value) if rt.cudaGetDeviceCount(C.byref(n)) == 0 else 0
+    return 0
 
 
 def shard_range(n: int, rank: int, world: int):
@@ -326,6 +349,7 @@ class FilterSolver:
 
     def __init__(self, prob: ODEProblem, alg: _EK, *, abstol=1e-6, reltol=1e-3, adaptive=True, dt=None,
                  save_everystep=True, save_stride=None, smooth=None, maxiters=100000, max_saved=0, device=-1,
+                 devices=None, reference_quirks=False,
                  dtmin=0.0, dtmax=None, qmin=None, qmax=None, gamma=None, beta1=None, beta2=None):
         if not adaptive and dt is None:
             raise ValueError("Fixed timestep methods require a choice of dt")  # test/errors.jl:16-20
@@ -340,6 +364,17 @@ class FilterSolver:
         cfg.save_mode = L.SAVE_EVERY if save_everystep else (L.SAVE_STRIDE if save_stride else L.SAVE_FINAL)
         cfg.save_stride = int(save_stride or 1)
         cfg.device = device
+        if isinstance(devices, str) and devices == "all":
+            devices = list(range(device_count()))
+        if devices is not None:
+            devices = [int(x) for x in devices]
+            if not 1 <= len(devices) <= L.MAX_DEVICES:
+                raise ValueError(f"devices must list 1..{L.MAX_DEVICES} CUDA ordinals")
+            cfg.n_devices = len(devices)
+            for i, dv in enumerate(devices):
+                cfg.device_list[i] = dv
+        cfg.flags = L.FLAG_REFERENCE_QUIRKS if reference_quirks else 0
+        self.devices = devices
         cfg.ieks_iterations = int(alg.iterations)
         cfg.abstol, cfg.reltol = float(abstol), float(reltol)
         cfg.dt = float(dt) if dt is not None else 0.0
@@ -594,7 +629,7 @@ def solve_ieks(prob, alg: _EK, *args, iterations: int = 10, **kwargs):
 
 def solve(prob, alg: _EK, ensemblealg: Optional[EnsembleB200] = None, *, trajectories: Optional[int] = None,
           abstol=1e-6, reltol=1e-3, adaptive=True, dt=None, dense=None, save_everystep=None, save_stride=None,
-          maxiters=100000, max_saved=0, device=-1, balance_by=None, **ctrl):
+          maxiters=100000, max_saved=0, device=-1, devices=None, balance_by=None, **ctrl):
     """solve(prob, EK0/EK1(order=q); abstol, reltol, adaptive, dt) -> ProbODESolution, or
     solve(EnsembleProblem, alg, EnsembleB200(); trajectories=N, ...) -> EnsembleSolution.
 
@@ -606,6 +641,8 @@ def solve(prob, alg: _EK, ensemblealg: Optional[EnsembleB200] = None, *, traject
     if dense is not None and bool(dense) != bool(alg.smooth):
         raise ValueError("`dense` and `smooth` should have the same value! ")
     ensemble = isinstance(prob, EnsembleProblem)
+    if devices is None and ensemblealg is not None:
+        devices = getattr(ensemblealg, "devices", None)
     if save_everystep is None:
         save_everystep = not ensemble
     perm = None
@@ -627,7 +664,7 @@ def solve(prob, alg: _EK, ensemblealg: Optional[EnsembleB200] = None, *, traject
     while True:
         solver = FilterSolver(base, alg, abstol=abstol, reltol=reltol, adaptive=adaptive, dt=dt,
                               save_everystep=save_everystep, save_stride=save_stride, maxiters=maxiters,
-                              max_saved=max_saved, device=device, **ctrl)
+                              max_saved=max_saved, device=device, devices=devices, **ctrl)
         solver.solve_ensemble(u0, p)
         counts = solver.counts()
         if (counts["retcode"] == 4).any() and not user_cap and max_saved < maxiters + 1:

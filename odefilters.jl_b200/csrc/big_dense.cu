@@ -322,7 +322,7 @@ __global__ void pack_cov_kernel(const double* full, int D, double cal, double* o
 
 __global__ void write_outputs_kernel(StepCtx c, double* mean, double* t_final, double* loglik, double* final_diff,
                                      int* retcode, int* naccept, int* nreject, int* nf, int* njacs, int* n_saved,
-                                     long long n, long long tr, double t, int is_static) {
+                                     long long n, long long tr, double t, int is_static, int truncated) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c.D) mean[(long long)i * n + tr] = c.m[i];
   if (i == 0) {
@@ -332,7 +332,8 @@ __global__ void write_outputs_kernel(StepCtx c, double* mean, double* t_final, d
     t_final[tr] = t;
     loglik[tr] = ll;
     final_diff[tr] = sc->global_saved;
-    retcode[tr] = sc->nonfinite ? RET_NONFINITE : RET_SUCCESS;
+    // a loop cut short by maxiters is reported as such (filter_kernel / lorenz96_kernel do the same)
+    retcode[tr] = sc->nonfinite ? RET_NONFINITE : (truncated ? RET_MAXITERS : RET_SUCCESS);
     naccept[tr] = sc->nacc;
     nreject[tr] = 0;
     nf[tr] = sc->nacc;
@@ -362,6 +363,22 @@ size_t big_work_bytes(int d, int q) {
     if (e__ != cudaSuccess) return e__; \
   } while (0)
 
+// RAII owner of the auxiliary high-priority stream and its events: released on every exit path of big_run
+struct AuxGuard {
+  QrWork& wk;
+  explicit AuxGuard(QrWork& w) : wk(w) {
+    wk.aux = nullptr;
+    for (int i = 0; i < 2; ++i) wk.ev_narrow[i] = wk.ev_panel[i] = nullptr;
+  }
+  ~AuxGuard() {
+    for (int i = 0; i < 2; ++i) {
+      if (wk.ev_narrow[i]) cudaEventDestroy(wk.ev_narrow[i]);
+      if (wk.ev_panel[i]) cudaEventDestroy(wk.ev_panel[i]);
+    }
+    if (wk.aux) cudaStreamDestroy(wk.aux);
+  }
+};
+
 cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
   const int d = A.d, q = A.q, D = d * (q + 1);
   char* base = reinterpret_cast<char*>(A.work);
@@ -387,6 +404,7 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
   c.E = (double*)take((size_t)D * D * 8);
   c.R = (double*)take((size_t)D * D * 8);
   QrWork wk;
+  AuxGuard guard(wk);
   wk.W = (double*)take((size_t)NB * D * 8);
   wk.v0 = (double*)take(2 * NB * 8);
   wk.T = (double*)take(2 * NB * NB * 8);
@@ -449,8 +467,12 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
     };
     // (capturing the ~650 launches of a step into a CUDA graph was measured: 23.5 ms/step either way -- the panel
     // chain is bound by the kernels themselves, not by launch gaps -- so the plain launches stay)
+    bool truncated = false;
     while (t < A.K.t1) {
-      if (++iter > A.K.maxiters) break;
+      if (++iter > A.K.maxiters) {
+        truncated = true;
+        break;
+      }
       const double h = fmin(A.K.dt, A.K.t1 - t);
       BCK(step_body(h));
       const double ttmp = t + h;
@@ -458,7 +480,7 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
     }
     write_outputs_kernel<<<(D + TB - 1) / TB, TB, 0, s>>>(c, A.mean, A.t_final, A.loglik, A.final_diff, A.retcode,
                                                           A.naccept, A.nreject, A.nf, A.njacs, A.n_saved, A.n, tr, t,
-                                                          is_static ? 1 : 0);
+                                                          is_static ? 1 : 0, truncated ? 1 : 0);
     ++*launches;
     if (A.cov) {
       // Sigma = S' S over the factor columns (rows of S): full D x D by the same DMMA kernel, then packed
@@ -478,11 +500,6 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
     }
   }
   cudaError_t fin = cudaStreamSynchronize(s);  // the auxiliary stream's work is ordered before this point
-  for (int i = 0; i < 2; ++i) {
-    cudaEventDestroy(wk.ev_narrow[i]);
-    cudaEventDestroy(wk.ev_panel[i]);
-  }
-  cudaStreamDestroy(wk.aux);
   if (fin != cudaSuccess) return fin;
   return cudaGetLastError();
 }

@@ -24,7 +24,9 @@ namespace pnde {
 
 enum { DIFF_DYNAMIC = 0, DIFF_FIXED = 1, DIFF_FIXED_MAP = 2, DIFF_DYNAMIC_MV = 3, DIFF_FIXED_MV = 4 };
 enum { SAVE_FINAL = 0, SAVE_EVERY = 1, SAVE_STRIDE = 2 };
-enum { RET_SUCCESS = 0, RET_MAXITERS = 1, RET_DTNAN = 2, RET_NONFINITE = 3, RET_HISTORY_FULL = 4, RET_DTMIN = 5 };
+enum { RET_SUCCESS = 0, RET_MAXITERS = 1, RET_DTNAN = 2, RET_NONFINITE = 3, RET_HISTORY_FULL = 4, RET_DTMIN = 5,
+       RET_ZERO_RESIDUAL = 6 };
+enum { FLAG_REFERENCE_QUIRKS = 1 };
 
 struct CtrlParams {
   double abstol, reltol, dt, t0, t1;
@@ -63,6 +65,7 @@ struct FilterParams {
   double* hist;  // [max_saved][REC][n]
   long long max_saved;
   int save_mode, save_stride, diffusion;
+  int flags;  // FLAG_*
   IwpConsts C;
   CtrlParams K;
   LinParams lin;
@@ -97,15 +100,41 @@ __device__ __forceinline__ void precond_scales(double h, double (&P)[q + 1], dou
 
 // Step-size factor of the PI controller (OrdinaryDiffEq stepsize_controller!):
 //   qc = clamp(EEst^beta1 / qold^beta2 / gamma, 1/qmax, 1/qmin),  qc = 1/qmax for EEst == 0.
-// Through exp/log with log qold carried by the caller: one log and one exp per attempted step instead of two pow
-// calls (2-3 ulp instead of <= 2, a third of the instructions).  lE = log EEst (-inf for EEst == 0) is returned for the
-// caller's qold update (accept) or q11 = EEst^beta1 = exp(beta1 lE) (reject).
-__device__ __forceinline__ double controller_factor(double EEst, const CtrlParams& K, double lqold, double& lE) {
+// Two arithmetic variants, selected at build time:
+//   PNDE_CTRL_POW = 1  two pow calls, the way the reference evaluates it (Julia's ^ is the libm pow);
+//   PNDE_CTRL_POW = 0  exp/log with log qold carried by the caller: one log and one exp per attempted step (2-3 ulp
+//                      instead of <= 2, a third of the instructions).
+// The carried state `qs` is qold (pow) or log qold (exp/log); `lE` is scratch for the second variant.  Which one ships
+// was decided by the ensemble-scale count statistics of tests/test_gpu_parity.py::test_adaptive_ensemble_count_parity
+// (DESIGN.md section 2).
+#ifndef PNDE_CTRL_POW
+#define PNDE_CTRL_POW 0
+#endif
+__device__ __forceinline__ double ctrl_state_init(const CtrlParams& K) {
+  return PNDE_CTRL_POW ? K.qoldinit : log(K.qoldinit);
+}
+__device__ __forceinline__ double controller_factor(double EEst, const CtrlParams& K, double qs, double& lE) {
   lE = __longlong_as_double(0xfff0000000000000LL);
   if (EEst == 0.0) return 1.0 / K.qmax;
+#if PNDE_CTRL_POW
+  const double qc = pow(EEst, K.beta1) / pow(qs, K.beta2);
+#else
   lE = log(EEst);
-  const double qc = exp(K.beta1 * lE - K.beta2 * lqold);
+  const double qc = exp(K.beta1 * lE - K.beta2 * qs);
+#endif
   return fmax(1.0 / K.qmax, fmin(1.0 / K.qmin, qc / K.gamma));
+}
+// qold = max(EEst, qoldinit) after an accepted step
+__device__ __forceinline__ double ctrl_state_accept(double EEst, double lE, double qs0, const CtrlParams& K) {
+  return PNDE_CTRL_POW ? fmax(EEst, K.qoldinit) : fmax(lE, qs0);
+}
+// q11 = EEst^beta1, formed only after a rejection
+__device__ __forceinline__ double ctrl_q11(double EEst, double lE, const CtrlParams& K) {
+#if PNDE_CTRL_POW
+  return pow(EEst, K.beta1);
+#else
+  return exp(K.beta1 * lE);
+#endif
 }
 
 __device__ __forceinline__ double ulp_of(double x) {  // Julia eps(x)
@@ -510,7 +539,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
   } else {
     dt = K.dt;
   }
-  const double lqold0 = log(K.qoldinit);
+  const double lqold0 = ctrl_state_init(K);
   double dtpropose = dt, lqold = lqold0, q11 = 1.0;
   bool accepted_prev = true;
   double hcur = -1.0;  // fixed-step mode: the h the state is currently preconditioned with (<0: natural)
@@ -643,6 +672,10 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
       ret = RET_NONFINITE;  // OrdinaryDiffEq check_error!: unstable_check
       break;
     }
+    if (diffusion == DIFF_FIXED && quad == 0.0 && (prm.flags & FLAG_REFERENCE_QUIRKS)) {
+      ret = RET_ZERO_RESIDUAL;  // the reference throws here (src/diffusions.jl:18-20)
+      break;
+    }
     // ---- loopfooter! ----
     const double ttmp = t + dt;
     if (ADAPTIVE) {
@@ -651,13 +684,13 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
       if (accept) {
         ++nacc;
         if (K.qsteady_min <= qc && qc <= K.qsteady_max) qc = 1.0;
-        lqold = fmax(lE, lqold0);  // qold = max(EEst, qoldinit)
+        lqold = ctrl_state_accept(EEst, lE, lqold0, K);  // qold = max(EEst, qoldinit)
         const double dtnew = dt / qc;
         t = (fabs(ttmp - K.t1) < 10.0 * ulp_of(fmax(t, K.t1))) ? K.t1 : ttmp;
         dtpropose = fmax(K.dtmin, fmin(K.dtmax, dtnew));
       } else {
         ++nrej;
-        q11 = exp(K.beta1 * lE);
+        q11 = ctrl_q11(EEst, lE, K);
       }
     } else {
       ++nacc;

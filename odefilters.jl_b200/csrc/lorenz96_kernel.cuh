@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(LORENZ_THREADS) lorenz96_kernel(const LorenzPa
   } else {
     dt = K.dt;
   }
-  const double lqold0 = log(K.qoldinit);
+  const double lqold0 = ctrl_state_init(K);
   double dtpropose = dt, lqold = lqold0, q11 = 1.0, hcur = -1.0;
   bool accepted_prev = true;
 
@@ -342,12 +342,12 @@ __global__ void __launch_bounds__(LORENZ_THREADS) lorenz96_kernel(const LorenzPa
       if (accept) {
         ++nacc;
         if (K.qsteady_min <= qc && qc <= K.qsteady_max) qc = 1.0;
-        lqold = fmax(lE, lqold0);  // qold = max(EEst, qoldinit)
+        lqold = ctrl_state_accept(EEst, lE, lqold0, K);  // qold = max(EEst, qoldinit)
         t = (fabs(ttmp - K.t1) < 10.0 * ulp_of(fmax(t, K.t1))) ? K.t1 : ttmp;
         dtpropose = fmax(K.dtmin, fmin(K.dtmax, dt / qc));
       } else {
         ++nrej;
-        q11 = exp(K.beta1 * lE);
+        q11 = ctrl_q11(EEst, lE, K);
       }
     } else {
       ++nacc;

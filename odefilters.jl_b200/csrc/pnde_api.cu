@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pnde.h"
@@ -107,6 +108,13 @@ struct pnde_handle {
   DevBuf u0, p, mean, cov, t_final, loglik, final_diff, retcode, naccept, nreject, nf, njacs, n_saved, hist, smooth,
       sstatus, scratch_off, scratch_out, bigwork, prev_hist, prev_smooth, prev_n_saved, prev_final_diff;
   std::string err;
+  // multi-device handle (cfg.n_devices > 1): one single-device child per GPU, trajectories in contiguous shards
+  // [kid_lo[k], kid_lo[k+1]); the parent owns no device memory.  SURVEY 8(e): no exchange step, results are written
+  // straight into disjoint slices of the caller's arrays.
+  std::vector<pnde_handle*> kids;
+  std::vector<long long> kid_lo;
+  long long global_lo = 0;  // child: index of its first trajectory in the parent's ensemble (keys the sampler)
+  bool multi() const { return !kids.empty(); }
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -157,6 +165,8 @@ int pnde_default_config(pnde_config* cfg, int32_t alg, int32_t order, int32_t vf
   cfg->dtmax = 0.0;  // <= 0: t1 - t0
   cfg->maxiters = 100000;
   cfg->max_saved = 0;
+  cfg->n_devices = 0;
+  cfg->flags = 0;
   return PNDE_OK;
 }
 
@@ -314,6 +324,16 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
       return PNDE_ERR_ARG;
     }
     owns = true;
+    // adaptive kernels park the pre-step state in shared memory (STATE_LEN x 128 doubles per CTA): refuse what
+    // cannot be launched now instead of failing at the first pnde_run with an opaque "invalid value"
+    const size_t stash = (size_t)(ops->rec - 1 - ops->nd) * 128 * sizeof(double);
+    if (cfg->adaptive && stash > 227 * 1024) {
+      rtc_destroy(ops);
+      g_create_error = "adaptive steps with d = " + std::to_string(custom->d) + ", order = " + std::to_string(cfg->order) +
+                       " need " + std::to_string(stash) + " B of shared memory per CTA for the pre-step state (limit 232448): "
+                       "use a lower order or fixed steps";
+      return PNDE_ERR_UNSUPPORTED;
+    }
   }
   pnde_handle* h = new pnde_handle();
   h->cfg = *cfg;
@@ -338,6 +358,7 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
   h->cfg.d = h->d;
   h->device = dev;
   if (!build_iwp(cfg->order, h->C)) {
+    if (owns) rtc_destroy(ops);
     delete h;
     g_create_error = "IWP process-noise Cholesky failed";
     return PNDE_ERR_ARG;
@@ -352,6 +373,10 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
   if (e != cudaSuccess) {
     g_create_error = std::string("stream/event creation: ") + cudaGetErrorString(e);
+    for (int i = 0; i < 4; ++i)
+      if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (owns) rtc_destroy(ops);
     delete h;
     return PNDE_ERR_CUDA;
   }
@@ -359,7 +384,59 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
   return PNDE_OK;
 }
 
-int pnde_create(const pnde_config* cfg, pnde_handle** out) { return create_impl(cfg, out, nullptr); }
+// cfg.n_devices > 1: one child handle per listed device under a parent that owns no device memory
+static int create_any(const pnde_config* cfg, pnde_handle** out, const CustomVf* custom) {
+  if (!cfg || !out || cfg->abi_version != PNDE_ABI_VERSION || cfg->n_devices <= 1) {
+    if (cfg && out && cfg->abi_version == PNDE_ABI_VERSION && cfg->n_devices == 1) {
+      pnde_config c1 = *cfg;
+      c1.device = cfg->device_list[0];
+      c1.n_devices = 0;
+      return create_impl(&c1, out, custom);
+    }
+    return create_impl(cfg, out, custom);
+  }
+  *out = nullptr;
+  if (cfg->n_devices > PNDE_MAX_DEVICES) {
+    g_create_error = "n_devices exceeds PNDE_MAX_DEVICES";
+    return PNDE_ERR_ARG;
+  }
+  for (int i = 0; i < cfg->n_devices; ++i)
+    for (int j = 0; j < i; ++j)
+      if (cfg->device_list[i] == cfg->device_list[j]) {
+        g_create_error = "device_list holds a device twice";
+        return PNDE_ERR_ARG;
+      }
+  pnde_handle* parent = new pnde_handle();
+  for (int i = 0; i < cfg->n_devices; ++i) {
+    pnde_config ck = *cfg;
+    ck.device = cfg->device_list[i];
+    ck.n_devices = 0;
+    pnde_handle* kid = nullptr;
+    const int rc = create_impl(&ck, &kid, custom);
+    if (rc != PNDE_OK) {
+      for (pnde_handle* k : parent->kids) pnde_destroy(k);
+      delete parent;
+      return rc;
+    }
+    parent->kids.push_back(kid);
+  }
+  const pnde_handle* k0 = parent->kids[0];
+  parent->cfg = k0->cfg;
+  parent->cfg.n_devices = cfg->n_devices;
+  parent->d = k0->d;
+  parent->D = k0->D;
+  parent->np = k0->np;
+  parent->nd = k0->nd;
+  parent->ncov = k0->ncov;
+  parent->lorenz = k0->lorenz;
+  parent->ieks = k0->ieks;
+  parent->ops = k0->ops;  // dimension helpers only; never launched through the parent
+  parent->device = k0->device;
+  *out = parent;
+  return PNDE_OK;
+}
+
+int pnde_create(const pnde_config* cfg, pnde_handle** out) { return create_any(cfg, out, nullptr); }
 
 int pnde_create_custom(const pnde_config* cfg, int32_t d, int32_t n_params, const char* f_body, const char* jac_body,
                        pnde_handle** out) {
@@ -368,7 +445,7 @@ int pnde_create_custom(const pnde_config* cfg, int32_t d, int32_t n_params, cons
     g_create_error = "pnde_create_custom: cfg.vf_kind must be PNDE_VF_CUSTOM";
     return PNDE_ERR_ARG;
   }
-  return create_impl(cfg, out, &c);
+  return create_any(cfg, out, &c);
 }
 
 int pnde_check_custom(int32_t alg, int32_t order, int32_t diffusion, int32_t d, int32_t n_params, const char* f_body,
@@ -386,6 +463,11 @@ int pnde_check_custom(int32_t alg, int32_t order, int32_t diffusion, int32_t d, 
 
 int pnde_destroy(pnde_handle* h) {
   if (!h) return PNDE_OK;
+  if (h->multi()) {
+    for (pnde_handle* k : h->kids) pnde_destroy(k);
+    delete h;
+    return PNDE_OK;
+  }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->u0,      &h->p,      &h->mean,  &h->cov,     &h->t_final, &h->loglik,
@@ -424,9 +506,53 @@ static long long derive_max_saved(const pnde_handle* h) {
   return steps + 1;
 }
 
-int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* p) {
+}  // extern "C"  (templates below)
+
+// Runs fn(kid index) for every child that holds trajectories, one host thread per device, and returns the first
+// failure (its text is copied into the parent's error slot).
+template <class Fn>
+static int for_each_kid(pnde_handle* h, Fn fn) {
+  const size_t nk = h->kids.size();
+  std::vector<int> rc(nk, PNDE_OK);
+  std::vector<std::thread> th;
+  for (size_t k = 0; k < nk; ++k) {
+    if (h->kid_lo.size() == nk + 1 && h->kid_lo[k + 1] <= h->kid_lo[k]) continue;  // empty shard
+    th.emplace_back([&, k] { rc[k] = fn((int)k); });
+  }
+  for (auto& t : th) t.join();
+  for (size_t k = 0; k < nk; ++k)
+    if (rc[k] != PNDE_OK) {
+      h->err = "device " + std::to_string(h->kids[k]->device) + ": " + h->kids[k]->err;
+      return rc[k];
+    }
+  return PNDE_OK;
+}
+
+extern "C" {
+
+// contiguous block partition, remainder spread over the first shards (|shard sizes| differ by at most one)
+static void partition(pnde_handle* h, long long n) {
+  const long long nk = (long long)h->kids.size();
+  h->kid_lo.assign((size_t)nk + 1, 0);
+  for (long long k = 0; k < nk; ++k) {
+    h->kid_lo[(size_t)k + 1] = h->kid_lo[(size_t)k] + n / nk + (k < n % nk ? 1 : 0);
+    h->kids[(size_t)k]->global_lo = h->kid_lo[(size_t)k];
+  }
+}
+
+// src_pitch: elements between consecutive rows of the caller's [rows][n_total] arrays (== n_traj for a whole ensemble)
+static int upload_impl(pnde_handle* h, int64_t n_traj, const double* u0, const double* p, int64_t src_pitch) {
   if (!h) return PNDE_ERR_ARG;
   if (n_traj <= 0 || !u0 || (!p && h->np > 0)) return h->fail(PNDE_ERR_ARG, "pnde_upload: bad arguments");
+  if (h->multi()) {
+    partition(h, n_traj);
+    h->n = n_traj;
+    h->ran = h->smoothed = false;
+    return for_each_kid(h, [&](int k) {
+      const long long lo = h->kid_lo[(size_t)k], cnt = h->kid_lo[(size_t)k + 1] - lo;
+      return upload_impl(h->kids[(size_t)k], cnt, u0 + lo, p ? p + lo : nullptr, src_pitch);
+    });
+  }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   struct { int d, np, D, nd, rec; } dims = {h->d, h->np, h->D, h->nd, h->ops ? h->ops->rec : 0};
   const auto* o = &dims;
@@ -457,13 +583,21 @@ int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* 
       return PNDE_ERR_ALLOC;
     }
   }
-  CK(cudaMemcpyAsync(h->u0.p, u0, n * o->d * 8, cudaMemcpyHostToDevice, h->stream), "H2D u0");
-  if (o->np > 0) CK(cudaMemcpyAsync(h->p.p, p, n * o->np * 8, cudaMemcpyHostToDevice, h->stream), "H2D p");
+  CK(cudaMemcpy2DAsync(h->u0.p, n * 8, u0, (size_t)src_pitch * 8, n * 8, (size_t)o->d, cudaMemcpyHostToDevice, h->stream), "H2D u0");
+  if (o->np > 0)
+    CK(cudaMemcpy2DAsync(h->p.p, n * 8, p, (size_t)src_pitch * 8, n * 8, (size_t)o->np, cudaMemcpyHostToDevice, h->stream), "H2D p");
+  // with page-locked inputs the copies above are truly asynchronous: wait, so that the caller may reuse or free
+  // u0 / p as soon as this call returns (the kernel cannot start before they have arrived anyway)
+  CK(cudaStreamSynchronize(h->stream), "H2D synchronize");
   h->n = n_traj;
   h->ran = false;
   h->smoothed = false;
   h->have_prev = false;
   return PNDE_OK;
+}
+
+int pnde_upload(pnde_handle* h, int64_t n_traj, const double* u0, const double* p) {
+  return upload_impl(h, n_traj, u0, p, n_traj);
 }
 
 static void fill_filter_params(pnde_handle* h, FilterParams& fp) {
@@ -490,6 +624,7 @@ static void fill_filter_params(pnde_handle* h, FilterParams& fp) {
   fp.save_mode = c.save_mode;
   fp.save_stride = c.save_stride > 0 ? c.save_stride : 1;
   fp.diffusion = c.diffusion;
+  fp.flags = c.flags;
   fp.C = h->C;
   fp.K.abstol = c.abstol;
   fp.K.reltol = c.reltol;
@@ -512,6 +647,17 @@ static void fill_filter_params(pnde_handle* h, FilterParams& fp) {
 int pnde_run(pnde_handle* h) {
   if (!h) return PNDE_ERR_ARG;
   if (h->n <= 0) return h->fail(PNDE_ERR_STATE, "pnde_run: nothing uploaded");
+  if (h->multi()) {
+    // asynchronous launches: one thread suffices, every device works on its own stream
+    for (size_t k = 0; k < h->kids.size(); ++k) {
+      if (h->kid_lo[k + 1] <= h->kid_lo[k]) continue;
+      const int rc = pnde_run(h->kids[k]);
+      if (rc != PNDE_OK) return h->fail(rc, h->kids[k]->err);
+    }
+    h->ran = true;
+    h->smoothed = false;
+    return PNDE_OK;
+  }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   const pnde_config& c = h->cfg;
   if (h->ieks && h->ran) {
@@ -621,6 +767,15 @@ int pnde_smooth(pnde_handle* h) {
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "pnde_smooth: run the filter first");
   if (h->cfg.save_mode != PNDE_SAVE_EVERY)
     return h->fail(PNDE_ERR_STATE, "pnde_smooth needs save_mode = PNDE_SAVE_EVERY");
+  if (h->multi()) {
+    for (size_t k = 0; k < h->kids.size(); ++k) {
+      if (h->kid_lo[k + 1] <= h->kid_lo[k]) continue;
+      const int rc = pnde_smooth(h->kids[k]);
+      if (rc != PNDE_OK) return h->fail(rc, h->kids[k]->err);
+    }
+    h->smoothed = true;
+    return PNDE_OK;
+  }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   const ModelOps* o = h->ops;
   cudaError_t e = h->smooth.ensure((size_t)h->n * (size_t)h->max_saved * o->srec * 8);
@@ -653,6 +808,13 @@ int pnde_smooth(pnde_handle* h) {
 
 int pnde_synchronize(pnde_handle* h) {
   if (!h) return PNDE_ERR_ARG;
+  if (h->multi()) {
+    for (pnde_handle* k : h->kids) {
+      const int rc = pnde_synchronize(k);
+      if (rc != PNDE_OK) return h->fail(rc, k->err);
+    }
+    return PNDE_OK;
+  }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   CK(cudaStreamSynchronize(h->stream), "stream synchronize");
   return PNDE_OK;
@@ -661,6 +823,20 @@ int pnde_synchronize(pnde_handle* h) {
 int pnde_last_run_ms(pnde_handle* h, double* filter_ms, double* smooth_ms) {
   if (!h) return PNDE_ERR_ARG;
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  if (h->multi()) {  // the devices work concurrently: max over shards
+    double f = 0.0, s = 0.0;
+    for (size_t k = 0; k < h->kids.size(); ++k) {
+      if (h->kid_lo[k + 1] <= h->kid_lo[k]) continue;
+      double fk = 0.0, sk = 0.0;
+      const int rc = pnde_last_run_ms(h->kids[k], &fk, &sk);
+      if (rc != PNDE_OK) return h->fail(rc, h->kids[k]->err);
+      f = std::max(f, fk);
+      s = std::max(s, sk);
+    }
+    if (filter_ms) *filter_ms = f;
+    if (smooth_ms) *smooth_ms = s;
+    return PNDE_OK;
+  }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   CK(cudaStreamSynchronize(h->stream), "stream synchronize");
   float ms = 0.f;
@@ -675,10 +851,29 @@ int pnde_last_run_ms(pnde_handle* h, double* filter_ms, double* smooth_ms) {
   return PNDE_OK;
 }
 
-int64_t pnde_last_launch_count(const pnde_handle* h) { return h ? h->launches : 0; }
+int64_t pnde_last_launch_count(const pnde_handle* h) {
+  if (!h) return 0;
+  if (!h->multi()) return h->launches;
+  int64_t tot = 0;
+  for (size_t k = 0; k < h->kids.size(); ++k)
+    if (h->kid_lo.size() > k + 1 && h->kid_lo[k + 1] > h->kid_lo[k]) tot += h->kids[k]->launches;
+  return tot;
+}
 
-int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const double* p) {
-  int rc = pnde_upload(h, n_traj, u0, p);
+static int solve_ensemble_impl(pnde_handle* h, int64_t n_traj, const double* u0, const double* p, int64_t src_pitch) {
+  if (h && h->multi()) {
+    if (n_traj <= 0 || !u0 || (!p && h->np > 0)) return h->fail(PNDE_ERR_ARG, "pnde_solve_ensemble: bad arguments");
+    partition(h, n_traj);
+    h->n = n_traj;
+    const int rc = for_each_kid(h, [&](int k) {
+      const long long lo = h->kid_lo[(size_t)k], cnt = h->kid_lo[(size_t)k + 1] - lo;
+      return solve_ensemble_impl(h->kids[(size_t)k], cnt, u0 + lo, p ? p + lo : nullptr, src_pitch);
+    });
+    h->ran = (rc == PNDE_OK);
+    h->smoothed = h->ran && h->cfg.smooth;
+    return rc;
+  }
+  int rc = upload_impl(h, n_traj, u0, p, src_pitch);
   if (rc != PNDE_OK) return rc;
   const int iterations = h->ieks ? (h->cfg.ieks_iterations > 0 ? h->cfg.ieks_iterations : 10) : 1;
   for (int it = 0; it < iterations; ++it) {
@@ -692,18 +887,39 @@ int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const 
   return pnde_synchronize(h);
 }
 
+int pnde_solve_ensemble(pnde_handle* h, int64_t n_traj, const double* u0, const double* p) {
+  return solve_ensemble_impl(h, n_traj, u0, p, n_traj);
+}
+
+static int get_final_impl(pnde_handle* h, double* mean, double* cov, double* t_final, double* loglik, int64_t dst_pitch);
+
 // Pipelined variant of solve + get_final for the thread-per-trajectory models: the ensemble is cut into slices;
 // the device-to-host copy of slice k (auxiliary stream) overlaps the filter kernel of slice k+1.
-int pnde_solve_ensemble_to_host(pnde_handle* h, int64_t n_traj, const double* u0, const double* p, double* mean,
-                                double* cov, double* t_final, double* loglik) {
+// pitch: elements between consecutive rows of the caller's input AND output arrays (the total ensemble size)
+static int solve_to_host_impl(pnde_handle* h, int64_t n_traj, const double* u0, const double* p, double* mean,
+                              double* cov, double* t_final, double* loglik, int64_t pitch_n) {
   if (!h) return PNDE_ERR_ARG;
+  if (h->multi()) {
+    if (n_traj <= 0 || !u0 || (!p && h->np > 0)) return h->fail(PNDE_ERR_ARG, "pnde_solve_ensemble_to_host: bad arguments");
+    partition(h, n_traj);
+    h->n = n_traj;
+    const int rc = for_each_kid(h, [&](int k) {
+      const long long lo = h->kid_lo[(size_t)k], cnt = h->kid_lo[(size_t)k + 1] - lo;
+      return solve_to_host_impl(h->kids[(size_t)k], cnt, u0 + lo, p ? p + lo : nullptr, mean ? mean + lo : nullptr,
+                                cov ? cov + lo : nullptr, t_final ? t_final + lo : nullptr,
+                                loglik ? loglik + lo : nullptr, pitch_n);
+    });
+    h->ran = (rc == PNDE_OK);
+    h->smoothed = h->ran && h->cfg.smooth;
+    return rc;
+  }
   if (!h->ops || h->cfg.smooth || h->cfg.save_mode != PNDE_SAVE_FINAL) {
     // models without slices (Lorenz-96 paths) or runs that keep history: plain sequence
-    int rc = pnde_solve_ensemble(h, n_traj, u0, p);
+    int rc = solve_ensemble_impl(h, n_traj, u0, p, pitch_n);
     if (rc != PNDE_OK) return rc;
-    return pnde_get_final(h, mean, cov, t_final, loglik);
+    return get_final_impl(h, mean, cov, t_final, loglik, pitch_n);
   }
-  int rc = pnde_upload(h, n_traj, u0, p);
+  int rc = upload_impl(h, n_traj, u0, p, pitch_n);
   if (rc != PNDE_OK) return rc;
   if (!h->copy_stream) {
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), "copy stream");
@@ -730,11 +946,11 @@ int pnde_solve_ensemble_to_host(pnde_handle* h, int64_t n_traj, const double* u0
     ++launches;
     CK(cudaEventRecord(h->slice_ev[k & 1], cs), "slice event record");
     CK(cudaStreamWaitEvent(h->copy_stream, h->slice_ev[k & 1], 0), "slice wait");
-    const size_t w = (size_t)(hi - lo) * 8, pitch = (size_t)n * 8;
+    const size_t w = (size_t)(hi - lo) * 8, pitch = (size_t)n * 8, dpitch = (size_t)pitch_n * 8;
     if (mean)
-      CK(cudaMemcpy2DAsync(mean + lo, pitch, h->mean.as<double>() + lo, pitch, w, h->D, cudaMemcpyDeviceToHost, h->copy_stream), "D2H mean");
+      CK(cudaMemcpy2DAsync(mean + lo, dpitch, h->mean.as<double>() + lo, pitch, w, h->D, cudaMemcpyDeviceToHost, h->copy_stream), "D2H mean");
     if (cov)
-      CK(cudaMemcpy2DAsync(cov + lo, pitch, h->cov.as<double>() + lo, pitch, w, h->ncov, cudaMemcpyDeviceToHost, h->copy_stream), "D2H cov");
+      CK(cudaMemcpy2DAsync(cov + lo, dpitch, h->cov.as<double>() + lo, pitch, w, h->ncov, cudaMemcpyDeviceToHost, h->copy_stream), "D2H cov");
     if (t_final) CK(cudaMemcpyAsync(t_final + lo, h->t_final.as<double>() + lo, w, cudaMemcpyDeviceToHost, h->copy_stream), "D2H t");
     if (loglik) CK(cudaMemcpyAsync(loglik + lo, h->loglik.as<double>() + lo, w, cudaMemcpyDeviceToHost, h->copy_stream), "D2H loglik");
   }
@@ -750,6 +966,11 @@ int pnde_solve_ensemble_to_host(pnde_handle* h, int64_t n_traj, const double* u0
   return PNDE_OK;
 }
 
+int pnde_solve_ensemble_to_host(pnde_handle* h, int64_t n_traj, const double* u0, const double* p, double* mean,
+                                double* cov, double* t_final, double* loglik) {
+  return solve_to_host_impl(h, n_traj, u0, p, mean, cov, t_final, loglik, n_traj);
+}
+
 static int fetch_i32(pnde_handle* h, const DevBuf& b, std::vector<int>& out) {
   out.resize((size_t)h->n);
   CK(cudaMemcpyAsync(out.data(), b.p, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream), "D2H counts");
@@ -760,6 +981,20 @@ static int fetch_i32(pnde_handle* h, const DevBuf& b, std::vector<int>& out) {
 int pnde_query_sizes(pnde_handle* h, int64_t* n_saved_total, int64_t* max_saved) {
   if (!h) return PNDE_ERR_ARG;
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  if (h->multi()) {
+    int64_t tot = 0, mx = 0;
+    for (size_t k = 0; k < h->kids.size(); ++k) {
+      if (h->kid_lo[k + 1] <= h->kid_lo[k]) continue;
+      int64_t tk = 0, mk = 0;
+      const int rc = pnde_query_sizes(h->kids[k], &tk, &mk);
+      if (rc != PNDE_OK) return h->fail(rc, h->kids[k]->err);
+      tot += tk;
+      mx = std::max(mx, mk);
+    }
+    if (n_saved_total) *n_saved_total = tot;
+    if (max_saved) *max_saved = mx;
+    return PNDE_OK;
+  }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   std::vector<int> ns;
   int rc = fetch_i32(h, h->n_saved, ns);
@@ -779,6 +1014,13 @@ int pnde_get_counts(pnde_handle* h, int64_t* naccept, int64_t* nreject, int64_t*
                     int64_t* n_saved) {
   if (!h) return PNDE_ERR_ARG;
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  if (h->multi())
+    return for_each_kid(h, [&](int k) {
+      const long long lo = h->kid_lo[(size_t)k];
+      return pnde_get_counts(h->kids[(size_t)k], naccept ? naccept + lo : nullptr, nreject ? nreject + lo : nullptr,
+                             nf ? nf + lo : nullptr, njacs ? njacs + lo : nullptr, retcode ? retcode + lo : nullptr,
+                             n_saved ? n_saved + lo : nullptr);
+    });
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   std::vector<int> tmp;
   struct {
@@ -798,24 +1040,68 @@ int pnde_get_counts(pnde_handle* h, int64_t* naccept, int64_t* nreject, int64_t*
   return PNDE_OK;
 }
 
-int pnde_get_final(pnde_handle* h, double* mean, double* cov, double* t_final, double* loglik) {
+static int get_final_impl(pnde_handle* h, double* mean, double* cov, double* t_final, double* loglik, int64_t dst_pitch) {
   if (!h) return PNDE_ERR_ARG;
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  if (h->multi())
+    return for_each_kid(h, [&](int k) {
+      const long long lo = h->kid_lo[(size_t)k];
+      return get_final_impl(h->kids[(size_t)k], mean ? mean + lo : nullptr, cov ? cov + lo : nullptr,
+                            t_final ? t_final + lo : nullptr, loglik ? loglik + lo : nullptr, dst_pitch);
+    });
   CK(cudaSetDevice(h->device), "cudaSetDevice");
-  const size_t n = (size_t)h->n;
-  if (mean) CK(cudaMemcpyAsync(mean, h->mean.p, n * h->D * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
-  if (cov) CK(cudaMemcpyAsync(cov, h->cov.p, n * (size_t)h->ncov * 8, cudaMemcpyDeviceToHost, h->stream), "D2H cov");
+  const size_t n = (size_t)h->n, dp = (size_t)dst_pitch * 8;
+  if (mean) CK(cudaMemcpy2DAsync(mean, dp, h->mean.p, n * 8, n * 8, (size_t)h->D, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
+  if (cov) CK(cudaMemcpy2DAsync(cov, dp, h->cov.p, n * 8, n * 8, (size_t)h->ncov, cudaMemcpyDeviceToHost, h->stream), "D2H cov");
   if (t_final) CK(cudaMemcpyAsync(t_final, h->t_final.p, n * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
   if (loglik) CK(cudaMemcpyAsync(loglik, h->loglik.p, n * 8, cudaMemcpyDeviceToHost, h->stream), "D2H loglik");
   CK(cudaStreamSynchronize(h->stream), "stream synchronize");
   return PNDE_OK;
 }
 
+int pnde_get_final(pnde_handle* h, double* mean, double* cov, double* t_final, double* loglik) {
+  return get_final_impl(h, mean, cov, t_final, loglik, h ? h->n : 0);
+}
+
+}  // extern "C"  (template below)
+
+// Multi-device form of the CSR getters: the trajectory range is cut at the shard boundaries, every child writes its
+// part of the flat outputs (trajectory order is shard order), offsets are rebased.  `call(kid, lo, hi, offs, base)`
+// runs the child getter for its local range with output pointers advanced by `base` saved states.
+template <class Fn>
+static int multi_csr(pnde_handle* h, int64_t tb, int64_t te, int64_t* offsets, Fn call) {
+  if (tb < 0 || te > h->n || tb >= te || !offsets) return h->fail(PNDE_ERR_ARG, "bad trajectory range");
+  int64_t base = 0;
+  offsets[0] = 0;
+  std::vector<int64_t> offs;
+  for (size_t k = 0; k < h->kids.size(); ++k) {
+    const int64_t lo = std::max<int64_t>(tb, h->kid_lo[k]), hi = std::min<int64_t>(te, h->kid_lo[k + 1]);
+    if (lo >= hi) continue;
+    offs.assign((size_t)(hi - lo) + 1, 0);
+    const int rc = call(h->kids[k], lo - h->kid_lo[k], hi - h->kid_lo[k], offs.data(), base);
+    if (rc != PNDE_OK) return h->fail(rc, h->kids[k]->err);
+    for (int64_t i = 0; i <= hi - lo; ++i) offsets[lo - tb + i] = base + offs[(size_t)i];
+    base += offs[(size_t)(hi - lo)];
+  }
+  return PNDE_OK;
+}
+
+extern "C" {
+
 static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t te, int64_t* offsets, double* t,
                             double* mean, double* cov, double* diffusion, bool marginals) {
   if (!h) return PNDE_ERR_ARG;
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
   if (h->cfg.save_mode == PNDE_SAVE_FINAL) return h->fail(PNDE_ERR_STATE, "no history was saved (save_mode = final)");
+  if (h->multi()) {
+    const int64_t DM = marginals ? h->d : h->D, NC = DM * (DM + 1) / 2;
+    const int df0 = h->cfg.diffusion;
+    const int64_t ndo = (df0 == PNDE_DIFF_DYNAMIC_MV || df0 == PNDE_DIFF_FIXED_MV) ? h->d : 1;
+    return multi_csr(h, tb, te, offsets, [&](pnde_handle* kid, int64_t lo, int64_t hi, int64_t* offs, int64_t base) {
+      return get_history_impl(kid, which, lo, hi, offs, t ? t + base : nullptr, mean ? mean + base * DM : nullptr,
+                              cov ? cov + base * NC : nullptr, diffusion ? diffusion + base * ndo : nullptr, marginals);
+    });
+  }
   if (which == PNDE_HIST_SMOOTHED && !h->smoothed) return h->fail(PNDE_ERR_STATE, "history has not been smoothed");
   if (which != PNDE_HIST_FILTERED && which != PNDE_HIST_SMOOTHED) return h->fail(PNDE_ERR_ARG, "bad 'which'");
   if (tb < 0 || te > h->n || tb >= te || !offsets) return h->fail(PNDE_ERR_ARG, "bad trajectory range");
@@ -855,6 +1141,9 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   cp.final_diff = h->final_diff.as<double>();
   cp.which = which;
   cp.calibrate = (df == PNDE_DIFF_FIXED || df == PNDE_DIFF_FIXED_MAP || df == PNDE_DIFF_FIXED_MV);
+  // PNDE_FLAG_REFERENCE_QUIRKS (a): sol.pu of an un-smoothed solve keeps the uncalibrated covariances
+  if (marginals && which == PNDE_HIST_FILTERED && !h->cfg.smooth && (h->cfg.flags & PNDE_FLAG_REFERENCE_QUIRKS))
+    cp.calibrate = 0;
   cp.is_mv = is_mv;
   cp.marginals = marginals ? 1 : 0;
   cp.t = dt_;
@@ -887,6 +1176,14 @@ int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint6
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
   if (h->cfg.save_mode != PNDE_SAVE_EVERY) return h->fail(PNDE_ERR_STATE, "pnde_sample needs save_mode = PNDE_SAVE_EVERY");
   if (tb < 0 || te > h->n || tb >= te || !offsets || n_samples < 1) return h->fail(PNDE_ERR_ARG, "bad arguments");
+  if (h->multi()) {
+    // the generator is keyed by the trajectory index: children are handed their global offset so that the draws do
+    // not depend on how the ensemble was sharded
+    return multi_csr(h, tb, te, offsets, [&](pnde_handle* kid, int64_t lo, int64_t hi, int64_t* offs, int64_t base) {
+      return pnde_sample(kid, lo, hi, n_samples, seed, offs, t ? t + base : nullptr,
+                         samples ? samples + base * n_samples * h->D : nullptr);
+    });
+  }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   const ModelOps* o = h->ops;
   std::vector<int> ns;
@@ -935,6 +1232,7 @@ int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint6
   sp.is_mv = (df == PNDE_DIFF_DYNAMIC_MV || df == PNDE_DIFF_FIXED_MV);
   sp.n_samples = n_samples;
   sp.seed = seed;
+  sp.key_offset = h->global_lo;
   sp.out = dout;
   sp.C = h->C;
   CK(o->launch_sample(o, sp, h->stream), "sample kernel launch");
@@ -952,6 +1250,18 @@ int pnde_eval_dense(pnde_handle* h, int32_t which, int64_t tb, int64_t te, int64
   if (which == PNDE_HIST_SMOOTHED && !h->smoothed) return h->fail(PNDE_ERR_STATE, "history has not been smoothed");
   if (which != PNDE_HIST_FILTERED && which != PNDE_HIST_SMOOTHED) return h->fail(PNDE_ERR_ARG, "bad 'which'");
   if (tb < 0 || te > h->n || tb >= te || n_t < 1 || !t) return h->fail(PNDE_ERR_ARG, "bad arguments");
+  if (h->multi()) {
+    const int64_t NC = (int64_t)h->D * (h->D + 1) / 2;
+    for (size_t k = 0; k < h->kids.size(); ++k) {
+      const int64_t lo = std::max<int64_t>(tb, h->kid_lo[k]), hi = std::min<int64_t>(te, h->kid_lo[k + 1]);
+      if (lo >= hi) continue;
+      const int64_t o = (lo - tb) * n_t;
+      const int rc = pnde_eval_dense(h->kids[k], which, lo - h->kid_lo[k], hi - h->kid_lo[k], n_t, t,
+                                     mean ? mean + o * h->D : nullptr, cov ? cov + o * NC : nullptr);
+      if (rc != PNDE_OK) return h->fail(rc, h->kids[k]->err);
+    }
+    return PNDE_OK;
+  }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   const ModelOps* o = h->ops;
   const size_t ntr = (size_t)(te - tb), NC = (size_t)(o->D * (o->D + 1) / 2);

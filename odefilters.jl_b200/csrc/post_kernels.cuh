@@ -67,6 +67,7 @@ struct SampleParams {
   const double* final_diff;
   int calibrate, is_mv, n_samples;
   unsigned long long seed;
+  long long key_offset;  // added to the trajectory index in the generator key (shards of a multi-device ensemble)
   double* out;  // [total][n_samples][D]
   IwpConsts C;
 };
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams sp) {
 #pragma unroll
       for (int c = 0; c < R; c += 2) {
         double a, b;
-        rng.normal2((uint32_t)tr, (uint32_t)smp, (uint32_t)(ns - 1), (uint32_t)(rep * 64 + c), a, b);
+        rng.normal2((uint32_t)(tr + sp.key_offset), (uint32_t)smp, (uint32_t)(ns - 1), (uint32_t)(rep * 64 + c), a, b);
 #pragma unroll
         for (int k = 0; k < DCOV; ++k) {
           s[PT::idx(rep, k)] = fma(cs * cols[c][k], a, s[PT::idx(rep, k)]);
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams sp) {
 #pragma unroll
           for (int c = 0; c < R; c += 2) {
             double a, b;
-            rng.normal2((uint32_t)tr, (uint32_t)smp, (uint32_t)i, (uint32_t)(rep * 64 + c), a, b);
+            rng.normal2((uint32_t)(tr + sp.key_offset), (uint32_t)smp, (uint32_t)i, (uint32_t)(rep * 64 + c), a, b);
 #pragma unroll
             for (int k = 0; k < DCOV; ++k) {
               acc[k] = fma(ys * cols[c][k], a, acc[k]);

@@ -41,13 +41,66 @@ def gpu_solve(name, alg, **kw):
     return B.solve(prob, alg, **kw)
 
 
+# distance between two correct FP64 implementations of the reference's recursion (chol-first vs
+# QR-only arithmetic, FHN, dt = 0.01), relative to the block max-norm: {q: [(n_steps, mean_full, cov_full), ...]}.
+# q = 2 was measured at 2000 steps only (used for every n), q = 4 not at all (geometric mean of q = 3 and q = 5).
+_C2_FLOOR = {
+    1: [(100, 2e-15, 6e-15), (2000, 2e-15, 6e-15)],
+    2: [(100, 3e-14, 2e-10), (2000, 3e-14, 2e-10)],
+    3: [(100, 5e-13, 2e-10), (1000, 1e-10, 2e-10), (2000, 3e-10, 3e-8)],
+    5: [(100, 2e-10, 3e-8), (1000, 7e-6, 2e-6), (2000, 7e-6, 3e-5)],
+}
+_SAFETY = 100.0  # this kernel is a third algorithm (one QR in measurement-aligned coordinates) on other problems too
+
+
+def _floor(q, n, col):
+    if q == 4:
+        return float(np.sqrt(_floor(3, n, col) * _floor(5, n, col)))
+    if q > 5:
+        return _floor(5, n, col) * 100.0 ** (q - 5)
+    tab = _C2_FLOOR[q]
+    ns = np.log([r[0] for r in tab])
+    vs = np.log([r[col] for r in tab])
+    return float(np.exp(np.interp(np.log(max(n, 1)), ns, vs)))  # log-log interpolation, clamped at the ends
+
+
 def cov_tol(q, n):
-    # SURVEY App. C.2 noise floor between two correct FP64 implementations
-    return {1: 1e-10, 2: 1e-7, 3: 1e-5, 4: 1e-3, 5: 1e-2}[q]
+    """Tolerance on covariance blocks as a function of (order, number of steps): SURVEY C.2 floor x 100."""
+    return max(_SAFETY * _floor(q, n, 2), 1e-12)
 
 
 def mean_tol(q, n):
-    return {1: 1e-11, 2: 1e-10, 3: 1e-7, 4: 1e-5, 5: 1e-3}[q]
+    return max(_SAFETY * _floor(q, n, 1), 1e-13)
+
+
+def assert_state_blocks(mu_g, Sig_g, mu_o, Sig_o, d, q, n, what=""):
+    """ALL mean blocks and the FULL covariance, block by block, relative to the max-norm of the oracle's block."""
+    worst = {"mean": 0.0, "cov": 0.0}
+    for k in range(q + 1):
+        e = rel(mu_g[..., k * d:(k + 1) * d], mu_o[..., k * d:(k + 1) * d])
+        worst["mean"] = max(worst["mean"], e)
+        assert e < mean_tol(q, n), (what, "mean block", k, e, mean_tol(q, n))
+        for l in range(k + 1):
+            bo = Sig_o[..., k * d:(k + 1) * d, l * d:(l + 1) * d]
+            if np.max(np.abs(bo)) == 0.0:
+                assert np.max(np.abs(Sig_g[..., k * d:(k + 1) * d, l * d:(l + 1) * d])) == 0.0
+                continue
+            e = rel(Sig_g[..., k * d:(k + 1) * d, l * d:(l + 1) * d], bo)
+            worst["cov"] = max(worst["cov"], e)
+            assert e < cov_tol(q, n), (what, "cov block", (k, l), e, cov_tol(q, n))
+    report("state_blocks", what=what, q=q, n=n, **worst, mean_tol=mean_tol(q, n), cov_tol=cov_tol(q, n))
+    return worst
+
+
+def report(kind, **vals):
+    """Measured parity numbers are appended to $PNDE_PARITY_REPORT (a .jsonl file) when it is set."""
+    import json
+    import os
+
+    path = os.environ.get("PNDE_PARITY_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps(dict(kind=kind, **vals), default=float) + "\n")
 
 
 @pytest.mark.parametrize("name", ["fhn_readme", "lotka_volterra", "fhn_lib"])
@@ -68,9 +121,8 @@ def test_fixed_step_filter_history(name, q, kind):
     mo = np.array([g.mu for g in so.x_filt])
     co = np.array([g.Sigma.mat for g in so.x_filt])
     n = len(so.t)
-    for k in range(q + 1):  # per derivative block, relative to the block max-norm
-        assert rel(sg.x_filt.mu[:, k * d:(k + 1) * d], mo[:, k * d:(k + 1) * d]) < mean_tol(q, n)
-    assert rel(sg.x_filt.Sigma[:, :d, :d], co[:, :d, :d]) < cov_tol(q, n)
+    # every mean block and the full covariance (all (q+1)^2 blocks), tolerances from (q, n)
+    assert_state_blocks(sg.x_filt.mu, sg.x_filt.Sigma, mo, co, d, q, n, what=f"fixed-{name}-{kind}{q}")
     assert rel(sg.diffusions, np.asarray(so.diffusions)) < cov_tol(q, n)
     assert sg.destats["naccept"] == so.naccept and sg.destats["nf"] == so.nf
     assert sg.x_filt.Sigma[0].max() == 0.0  # exact initial state (test/solution.jl:38-41)
@@ -119,7 +171,8 @@ def test_diffusion_models(kind, diffusion):
     d = 2
     assert rel(sg.x_filt.mu[:, :d], np.array([g.mu[:d] for g in so.x_filt])) < 1e-10
     co = np.array([g.Sigma.mat for g in so.x_filt])
-    assert rel(sg.x_filt.Sigma[:, :d, :d], co[:, :d, :d]) < 1e-5
+    mo = np.array([g.mu for g in so.x_filt])
+    assert_state_blocks(sg.x_filt.mu, sg.x_filt.Sigma, mo, co, d, q, len(so.t), what=f"diffusion-{kind}-{diffusion}")
     do = np.array([np.asarray(x)[:d] if np.ndim(x) else x for x in so.diffusions], dtype=float)
     assert rel(sg.diffusions, do) < 1e-5
     if diffusion.startswith("fixed"):
@@ -145,7 +198,10 @@ def test_smoother(name, kind, q, adaptive):
     mo = np.array([g.mu for g in so.x_smooth])
     co = np.array([g.Sigma.mat for g in so.x_smooth])
     assert rel(sg.x_smooth.mu[:, :d], mo[:, :d]) < 1e-9
-    assert rel(sg.x_smooth.Sigma[:, :d, :d], co[:, :d, :d]) < cov_tol(q, len(so.t))
+    if not adaptive:  # full smoothed state, all blocks (adaptive grids differ at the t-grid noise floor)
+        assert_state_blocks(sg.x_smooth.mu, sg.x_smooth.Sigma, mo, co, d, q, 10 * len(so.t), what=f"smooth-{name}-{kind}{q}")
+    else:
+        assert rel(sg.x_smooth.Sigma[:, :d, :d], co[:, :d, :d]) < 1e-5
     assert rel(sg.u, np.array(so.u)) < 1e-9                      # sol.u := smoothed means
     assert np.array_equal(sg.x_smooth.mu[-1], sg.x_filt.mu[-1])  # test/smoothing.jl:39
     assert np.array_equal(sg.x_smooth.mu[0], sg.x_filt.mu[0])    # first state is never smoothed
@@ -522,13 +578,61 @@ def test_full_size_config2_properties():
     assert es.converged and np.all(es.destats["naccept"] == 2000) and np.all(es.t_final == 20.0)
     assert np.all(np.isfinite(es.mean)) and np.all(np.isfinite(es.cov))
     assert np.array_equal(es.mean[n - 1], es.mean[0]) and np.array_equal(es.cov[123457], es.cov[77])
-    idx = rng.choice(n, 32, replace=False)
-    ref = R.solve_ensemble("fhn_readme", "EK1", 3, np.tile([-1.0, 1.0], (32, 1)), P[idx], (0.0, 20.0), adaptive=False,
-                           dt=0.01, want_cov=False)
+    m = 4096
+    idx = rng.choice(n, m, replace=False)
+    ref = R.solve_ensemble("fhn_readme", "EK1", 3, np.tile([-1.0, 1.0], (m, 1)), P[idx], (0.0, 20.0), adaptive=False,
+                           dt=0.01, want_cov=True)
     # 2000 steps through relaxation jumps: the FP64 noise floor of the recursion itself is ~5e-10 on the stiffer
     # draws (oracle/arbiter_mpmath.py fhn: numpy oracle 4.1e-10, C restatement 5.4e-10, this kernel's model
-    # 4.2e-10 away from the 60-digit recursion), so two FP64 implementations agree to ~1e-8, not 1e-10
-    assert rel(es.mean[idx][:, :2], ref["mean"][:, :2]) < 1e-7
+    # 4.2e-10 away from the 60-digit recursion), so two FP64 implementations agree to a few 1e-9 at worst
+    per = np.abs(es.mean[idx][:, :2] - ref["mean"][:, :2]).max(axis=1) / np.abs(ref["mean"][:, :2]).max(axis=1)
+    report("config2_full", n=m, max_rel_u=per.max(), median_rel_u=np.median(per), p99_rel_u=np.quantile(per, 0.99))
+    assert per.max() < 5e-9 and np.median(per) < 1e-11
+    # full final state of the same sample: every mean block and the whole covariance at the (q, n) tolerance
+    Sg = B.api._unpack_lower(es.cov[idx], 8)
+    assert_state_blocks(es.mean[idx], Sg, ref["mean"], ref["cov"], 2, 3, 2000, what="config2-full-size")
+
+
+@pytest.mark.parametrize("name", ["fhn_adaptive_ek1q3", "config3_vdp_ek1q5"])
+def test_adaptive_ensemble_count_parity(name):
+    """SURVEY 8c protocol (iii) at ensemble scale: 1e4 seeded trajectories on the GPU and through the C restatement
+    of the reference's dense arithmetic (oracle/pnde_ref.c): the fraction with identical (naccept, nreject).
+
+    Measured (r2, printed by the test and by benchmarks/parity_ensemble.py, both controller variants):
+      FHN sweep, EK1(3), (0, 20), defaults:     0.9998 identical (2 of 1e4 differ by one rejected step), with the
+                                                exp/log controller AND with pow -- so exp/log stays the default;
+      config 3 (VdP mu ~ 1e3, EK1(5)):          0.037 identical (pow: 0.034).  That is not a kernel defect: the
+        reference's own FP64 arithmetic reproduces the EXACT recursion's counts (60-digit mpmath, tests/golden/
+        arbiter_config3.npz) on 1 of 32 trajectories.  Accept/reject decisions of this stiff q = 5 run sit below
+        the FP64 noise floor of the recursion, so the meaningful statement is the distance to the
+        exact recursion, asserted below: the kernel is as close to it as the reference arithmetic is."""
+    from ensembles import count_parity
+
+    stats, raw = count_parity(name, 10_000)
+    report("adaptive_ensemble", **stats)
+    print(stats)
+    assert stats["all_success_gpu"] and stats["all_success_ref"]
+    if name == "fhn_adaptive_ek1q3":
+        assert stats["frac_identical_counts"] >= 0.999
+        assert stats["max_abs_dnaccept"] <= 1 and stats["max_abs_dnreject"] <= 1
+        assert stats["median_rel_u"] < 1e-10
+        return
+    # config 3: ensemble statistics agree, individual decisions are noise
+    assert abs(stats["mean_naccept_gpu"] / stats["mean_naccept_ref"] - 1) < 1e-3
+    assert abs(stats["mean_nreject_gpu"] - stats["mean_nreject_ref"]) < 0.15
+    assert stats["max_abs_dnaccept"] <= 0.06 * stats["mean_naccept_ref"]
+    assert stats["max_rel_u_all"] < 2e-5
+    g = _g("arbiter_config3.npz")
+    k = len(g["index"])
+    cg, ref = raw["gpu_counts"], raw["ref"]
+    dist = lambda c: (np.abs(c["naccept"][:k] - g["naccept"]).mean(), np.abs(c["nreject"][:k] - g["nreject"]).mean())  # noqa: E731
+    (ga, gr), (ra, rr) = dist(cg), dist(ref)
+    sc = np.abs(g["u1"]).max(axis=1)
+    gu = (np.abs(raw["gpu_mean"][:k, :2] - g["u1"]).max(axis=1) / sc).max()
+    ru = (np.abs(ref["mean"][:k, :2] - g["u1"]).max(axis=1) / sc).max()
+    report("arbiter_config3", gpu_dnaccept=ga, gpu_dnreject=gr, ref_dnaccept=ra, ref_dnreject=rr, gpu_u1=gu, ref_u1=ru)
+    # no farther from the exact recursion than the reference's own FP64 arithmetic (up to sampling noise on 32 draws)
+    assert ga <= 1.5 * ra + 0.5 and gr <= 1.5 * rr + 0.5 and gu <= 2.0 * ru
 
 
 def test_marginals_getter_matches_history():
@@ -788,3 +892,89 @@ def test_balanced_ensemble_order_returns_results_in_caller_order():
     assert np.array_equal(a.retcode, b.retcode) and np.array_equal(a.t_final, b.t_final)
     for i in (0, 17, n - 1):
         assert np.array_equal(a[i].t, b[i].t) and np.array_equal(a[i].u, b[i].u)
+
+
+# ---- one call, several GPUs (needs a box with >= 2 devices: gpurun --gpus 2) ------------------
+def _need_devices(k):
+    import odefilters_b200 as B
+
+    if B.api.device_count() < k:
+        pytest.skip(f"needs {k} CUDA devices")
+
+
+@pytest.mark.parametrize("ndev", [2, 4, 8])
+def test_multi_device_single_call_is_bitwise_the_single_device_result(ndev):
+    """cfg.n_devices > 1: contiguous shards, one host thread + stream per GPU inside the call, results written into
+    disjoint slices of the caller's arrays.  Every getter of the multi-device handle must return exactly what the
+    single-device handle returns for the same ensemble (ragged adaptive histories included)."""
+    _need_devices(ndev)
+    import odefilters_b200 as B
+
+    rng = np.random.default_rng(17)
+    n = 1003  # not a multiple of the shard count
+    P = np.array([1.5, 1.0, 3.0, 1.0]) * (1 + 0.2 * rng.uniform(-1, 1, (n, 4)))
+    U = np.ones((n, 2)) * (1 + 0.05 * rng.standard_normal((n, 1)))
+    prob = B.ODEProblem("lotka_volterra", [1.0, 1.0], (0.0, 2.0), P[0])
+    mk = lambda dev: B.FilterSolver(prob, B.EK1(order=3, smooth=True), max_saved=256, devices=dev)  # noqa: E731
+    a, b = mk(None), mk(list(range(ndev)))
+    a.solve_ensemble(U, P)
+    b.solve_ensemble(U, P)
+    ca, cb = a.counts(), b.counts()
+    for k in ca:
+        assert np.array_equal(ca[k], cb[k]), k
+    assert len(set(ca["n_saved"].tolist())) > 1  # ragged
+    for x, y in zip(a.final(), b.final()):
+        assert np.array_equal(x, y, equal_nan=True)
+    for which in (0, 1):
+        for lo, hi in ((0, n), (n // ndev - 3, n // ndev + 5), (n - 7, n)):  # whole, across a shard boundary, tail
+            for marg in (False, True):
+                ha, hb = a.history(which, lo, hi, marginals=marg), b.history(which, lo, hi, marginals=marg)
+                for x, y in zip(ha, hb):
+                    assert (x is None and y is None) or np.array_equal(x, y)
+    tq = np.array([0.1, 0.77, 1.9])
+    lo, hi = n // ndev - 2, n // ndev + 2
+    for x, y in zip(a.dense(1, lo, hi, tq), b.dense(1, lo, hi, tq)):
+        assert np.array_equal(x, y)
+    for x, y in zip(a.sample(lo, hi, 3, seed=5), b.sample(lo, hi, 3, seed=5)):
+        assert np.array_equal(x, y)  # the generator is keyed by the GLOBAL trajectory index
+    # pipelined host-to-host entry point and the high-level API
+    pf = B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 1.0), (0.2, 0.2, 3.0))
+    Pf = np.stack([rng.uniform(0.1, 0.3, 70001), rng.uniform(0.1, 0.3, 70001), rng.uniform(2, 4, 70001)], axis=1)
+    Uf = np.tile([-1.0, 1.0], (70001, 1))
+    s1 = B.FilterSolver(pf, B.EK1(order=3, smooth=False), adaptive=False, dt=0.01, save_everystep=False)
+    sN = B.FilterSolver(pf, B.EK1(order=3, smooth=False), adaptive=False, dt=0.01, save_everystep=False,
+                        devices=list(range(ndev)))
+    for x, y in zip(s1.solve_to_host(Uf, Pf), sN.solve_to_host(Uf, Pf)):
+        assert np.array_equal(x, y)
+    es = B.solve(B.EnsembleProblem(pf, p=Pf[:999]), B.EK1(order=3, smooth=False), B.EnsembleB200(devices="all"),
+                 adaptive=False, dt=0.01)
+    assert es.converged and np.array_equal(es.mean, s1.final()[0][:999])
+    # fewer trajectories than devices: empty shards are skipped
+    sN.solve_ensemble(Uf[:1], Pf[:1])
+    assert np.array_equal(sN.final()[0], s1.final()[0][:1]) and sN.counts()["naccept"].shape == (1,)
+
+
+def test_reference_quirk_flag():
+    """PNDE_FLAG_REFERENCE_QUIRKS (include/pnde.h): (a) static diffusion + smooth = false leaves sol.pu uncalibrated
+    (src/integrator_utils.jl:43-45 runs before :4-18); (b) FixedDiffusion with an exactly zero residual ends the
+    trajectory (the reference throws, src/diffusions.jl:18-20).  Default: calibrated marginals, sigma^2 = 0."""
+    import odefilters_b200 as B
+
+    prob = B.ODEProblem("lotka_volterra", [1.0, 1.0], (0.0, 1.0), (1.5, 1.0, 3.0, 1.0))
+    out = {}
+    for quirk in (False, True):
+        s = B.FilterSolver(prob, B.EK1(order=2, diffusionmodel="fixed", smooth=False), adaptive=False, dt=0.02,
+                           reference_quirks=quirk)
+        s.solve_ensemble(prob.u0[None], prob.p[None])
+        out[quirk] = (s.history(0, 0, 1, marginals=True), s.history(0, 0, 1), s.counts())
+    g = out[False][1][4][-1, 0]  # final global diffusion
+    assert np.array_equal(out[True][1][3], out[False][1][3])          # x_filt calibrated either way
+    assert np.allclose(out[True][0][3] * g, out[False][0][3], rtol=1e-13)  # pu: uncalibrated vs calibrated
+    assert g != 1.0
+    # (b) du = p u with u0 = 0: the residual is exactly zero at every step
+    z = B.ODEProblem("linear1", [0.0], (0.0, 1.0), (1.0,))
+    for quirk, want in ((False, "Success"), (True, "ZeroResidual")):
+        s = B.FilterSolver(z, B.EK1(order=2, diffusionmodel="fixed", smooth=False), adaptive=False, dt=0.1,
+                           reference_quirks=quirk)
+        s.solve_ensemble(z.u0[None], z.p[None])
+        assert B._lib.RETCODES[int(s.counts()["retcode"][0])] == want

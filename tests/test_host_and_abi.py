@@ -27,9 +27,10 @@ def test_config_struct_layout_matches_header():
     cfg = _lib.PndeConfig()
     lib = _lib.load()
     assert lib.pnde_default_config(C.byref(cfg), _lib.ALG_EK1, 3, 0) == 0
-    assert (cfg.abi_version, cfg.alg, cfg.order, cfg.adaptive) == (1, 1, 3, 1)
+    assert (cfg.abi_version, cfg.alg, cfg.order, cfg.adaptive) == (2, 1, 3, 1)
     assert (cfg.abstol, cfg.reltol, cfg.qmax, cfg.gamma, cfg.qoldinit) == (1e-6, 1e-3, 10.0, 0.9, 1e-4)
-    assert cfg.maxiters == 100000 and C.sizeof(cfg) == 12 * 4 + 15 * 8 + 2 * 8
+    assert cfg.maxiters == 100000 and C.sizeof(cfg) == 12 * 4 + 15 * 8 + 2 * 8 + (2 + 16) * 4
+    assert (cfg.n_devices, cfg.flags) == (0, 0)
 
 
 def test_create_argument_errors_are_reported_without_a_gpu():
