@@ -30,6 +30,8 @@ N_TRAJ_PER_GPU = 1_000_000
 T1, DT, ORDER = 20.0, 0.01, 3
 STEPS_PER_TRAJ = 2000
 FLOP_PER_STEP = 1.9e3      # F_filt(d=2, q=3), the algorithmic figure
+# flops the kernel EXECUTES per step: 610 DFMA + 181 DMUL + 59 DADD (profiles/r1_filter_kernel_loop_instruction_mix.csv)
+FLOP_EXECUTED_PER_STEP = 2 * 610 + 181 + 59
 BYTES_IN_PER_TRAJ = 5 * 8  # u0 (2) + p (3)
 BYTES_OUT_PER_TRAJ = (8 + 36 + 2) * 8  # final mean, packed covariance, t, log-likelihood
 SEED = 20260118
@@ -91,19 +93,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(n, threads=0):
-    """One pass of the reference-faithful CPU restatement over n trajectories; returns steps/s."""
+def cpu_reference_run(n, threads=0, inputs=None):
+    """One pass of the reference-faithful CPU restatement over n trajectories (the first n of `inputs` when given);
+    returns steps/s, steps, seconds, threads, and the final means [n, D]."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import pnde_ref as R
 
-    u0, p = make_inputs(n)
+    u0, p = inputs if inputs is not None else make_inputs(n)
+    u0, p = u0[:, :n], p[:, :n]
     t0 = time.perf_counter()
     out = R.solve_ensemble("fhn_readme", "EK1", ORDER, u0.T, p.T, (0.0, T1), adaptive=False, dt=DT,
                            nthreads=threads, want_cov=False)
     dt = time.perf_counter() - t0
     steps = int(np.sum(out["naccept"] + out["nreject"]))
-    return steps / dt, steps, dt, R.max_threads()
+    return steps / dt, steps, dt, R.max_threads(), out["mean"]
 
 
 def run_reference(args):
@@ -119,7 +123,7 @@ def run_reference(args):
         cpu_reference_run(max(64, n // 8))
     tot_steps, tot_t = 0, 0.0
     for _ in range(args.steps):
-        _, steps, dt, _ = cpu_reference_run(n)
+        _, steps, dt, _, _ = cpu_reference_run(n)
         tot_steps += steps
         tot_t += dt
     value = tot_steps / tot_t
@@ -147,6 +151,98 @@ def workload_config(n_gpus):
             "l2": "flushed between timed steps (256 MiB memset); outputs (368 MB) exceed L2"}
 
 
+def run_config5(args):
+    """BASELINE configs[4]: Lotka-Volterra ensemble, 1e6 trajectories IN TOTAL sharded over the GPUs (strong scaling),
+    EK1(order=3), fixed dt = 0.05 on (0, 10) => 200 steps, filter with every step saved + RTS smoother over the full
+    grid, processed in waves of 250 k trajectories per GPU (history: 201 x 288 B + smoothed 201 x 352 B per
+    trajectory).  One bench step = filter + smoother over the rank's whole shard; value = filter steps / time."""
+    import numpy as np
+    import torch
+
+    import odefilters_b200 as B
+
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    total, wave, nsteps = 1_000_000, 250_000, 200
+    lo, hi = B.shard_range(total, rank, world)
+    rng = np.random.default_rng(SEED)
+    p_all = np.array([1.5, 1.0, 3.0, 1.0]) * (1 + 0.1 * rng.uniform(-1, 1, (total, 4)))
+    p_np = np.ascontiguousarray(p_all[lo:hi].T)
+    u0_np = np.ones((2, hi - lo))
+    prob = B.ODEProblem("lotka_volterra", [1.0, 1.0], (0.0, 10.0), (1.5, 1.0, 3.0, 1.0))
+    solver = B.FilterSolver(prob, B.EK1(order=3, smooth=True), adaptive=False, dt=0.05, save_everystep=True, device=local)
+    waves = [(a, min(a + wave, hi - lo)) for a in range(0, hi - lo, wave)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_pass():
+        f = s = 0.0
+        for a, b in waves:
+            solver.upload(np.ascontiguousarray(u0_np[:, a:b]), np.ascontiguousarray(p_np[:, a:b]), soa=True)
+            solver.run(sync=False)
+            solver.smooth(sync=True)
+            fm, sm = solver.last_run_ms()
+            f += fm
+            s += sm
+        return f, s
+
+    for _ in range(args.warmup):
+        one_pass()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    w0 = time.perf_counter()
+    fms = sms = 0.0
+    for _ in range(args.steps):
+        f, s = one_pass()
+        fms += f
+        sms += s
+    barrier()
+    wall = time.perf_counter() - w0
+    clocks = sampler.stop()
+    c = solver.counts()
+    assert (c["retcode"] == 0).all() and (c["naccept"] == nsteps).all()
+    t_dev = (fms + sms) * 1e-3
+    if world > 1:
+        t = torch.tensor([t_dev, fms, sms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, fms, sms = (float(x) for x in t.tolist())
+    if rank == 0:
+        steps_total = total * nsteps * args.steps
+        flop = 1.9e3 + 8.6e3  # SURVEY App. D: F_filt(2,3) + F_smooth(2,3)
+        line = {
+            "metric": METRIC, "value": steps_total / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Lotka-Volterra ensemble, EK1(order=3), dt=0.05 on (0,10), filter (every step saved) + "
+                                   "RTS smoother over the full grid (BASELINE configs[4])",
+                       "trajectories_total": total, "trajectories_per_gpu": hi - lo, "wave": wave,
+                       "steps_per_trajectory": nsteps, "parallelism": f"ensemble-shard x{world}",
+                       "l2": "history per 250 k wave (14.5 GB filtered + 17.7 GB smoothed) far exceeds L2"},
+            "filter_ms_per_step": fms / args.steps, "smoother_ms_per_step": sms / args.steps,
+            "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
+            "gpu_launches": args.steps * 2 * len(waves) * world,
+            "roofline": {"bound": "fp64", "kernel": "filter_kernel + smoother_kernel (DenseEK1<VfLotkaVolterra,3>)",
+                         "achieved": flop * steps_total / t_dev / world / 1e12, "peak": 33.8, "unit": "TFLOP/s",
+                         "frac": flop * steps_total / t_dev / world / 1e12 / 33.8, "flop_per_unit": flop,
+                         "peak_source": "DFMA micro-benchmark of round 1 (33.8 TFLOP/s)", "traffic": None},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -155,7 +251,11 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--trajectories", type=int, default=N_TRAJ_PER_GPU, help="per GPU (default: the BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, help="2: the headline (BASELINE configs[1]); 5: Lotka-Volterra "
+                    "filter + RTS smoother, 1e6 trajectories sharded over the GPUs (BASELINE configs[4])")
     args = ap.parse_args()
+    if args.config == 5:
+        return run_config5(args)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -257,6 +357,28 @@ def main():
     barrier()
     clocks = sampler.stop()
     e2e_value = total_steps / t_e2e
+    # ---- strong scaling: the BASELINE ensemble (1e6 trajectories in total) split over the ranks ----------------
+    strong = None
+    if world > 1:
+        n_s = N_TRAJ_PER_GPU // world + (1 if rank < N_TRAJ_PER_GPU % world else 0)
+        solver.n = n_s
+        solver._check(lib.pnde_upload(h, n_s, u0_pin[:, :n_s].contiguous().data_ptr(), p_pin[:, :n_s].contiguous().data_ptr()),
+                      "pnde_upload")
+        for _ in range(2):
+            solver.run()
+        barrier()
+        s_ms = []
+        for _ in range(args.steps):
+            flush_buf.zero_()
+            torch.cuda.synchronize()
+            solver.run()
+            s_ms.append(solver.last_run_ms()[0])
+        barrier()
+        t_s = max_over_ranks(sum(s_ms) * 1e-3)
+        strong = {"trajectories_total": N_TRAJ_PER_GPU, "trajectories_per_gpu": N_TRAJ_PER_GPU // world,
+                  "value": N_TRAJ_PER_GPU * STEPS_PER_TRAJ * args.steps / t_s, "unit": UNIT,
+                  "ms_per_step": 1e3 * t_s / args.steps,
+                  "note": "same kernel, 1e6 trajectories in total: device time, max over ranks"}
 
     if rank == 0:
         peak = C.c_double()
@@ -275,6 +397,11 @@ def main():
             "bound": "fp64", "kernel": "filter_kernel<DenseEK1<VfFhnReadme,3>,false>",
             "achieved": achieved_tf, "peak": fp64_peak if fp64_peak else nominal, "unit": "TFLOP/s",
             "frac": achieved_tf / (fp64_peak if fp64_peak else nominal),
+            # the same with the flops the kernel actually executes (fewer than the survey's algorithmic count)
+            "flop_executed_per_unit": FLOP_EXECUTED_PER_STEP,
+            "achieved_executed": achieved_tf * FLOP_EXECUTED_PER_STEP / FLOP_PER_STEP,
+            "frac_executed": achieved_tf * FLOP_EXECUTED_PER_STEP / FLOP_PER_STEP / (fp64_peak if fp64_peak else nominal),
+            "frac_of_nominal": achieved_tf / nominal,
             "peak_source": "DFMA micro-benchmark measured in this run (pnde_measure_fp64_peak); MEASURED_PEAKS.json "
                            "has no FP64 entry" if fp64_peak else "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz",
             "nominal_peak": nominal, "flop_per_unit": FLOP_PER_STEP, "units_per_launch": steps_per_launch,
@@ -288,16 +415,24 @@ def main():
                     "note": "state lives in registers across the time loop: HBM is touched once per trajectory"},
         }
         cpu = None
+        parity = None
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import pnde_ref as R
 
             cores = R.max_threads()
-            n_cpu = max(256, 1500 * cores)
-            v, steps, dt_cpu, _ = cpu_reference_run(n_cpu)
+            n_cpu = min(n, max(256, 1500 * cores))
+            v, steps, dt_cpu, _, ref_mean = cpu_reference_run(n_cpu, inputs=(u0_np, p_np))
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n_cpu} of {n} trajectories x {STEPS_PER_TRAJ} steps ({dt_cpu:.1f} s), "
+                   "sample": f"the first {n_cpu} of the {n} trajectories x {STEPS_PER_TRAJ} steps ({dt_cpu:.1f} s), "
                              "oracle/pnde_ref.c (reference-faithful dense algorithm, pthreads)"}
+            # the CPU sample is the same inputs the GPU just solved: check u(t1) of every one of them
+            got = mean_pin[:2, :n_cpu].numpy().T
+            per = np.abs(got - ref_mean[:, :2]).max(axis=1) / np.abs(ref_mean[:, :2]).max(axis=1)
+            parity = {"n": int(n_cpu), "max_rel_u": float(per.max()), "median_rel_u": float(np.median(per)),
+                      "against": "oracle/pnde_ref.c on the same inputs, full 2000 steps", "tolerance": 5e-9,
+                      "ok": bool(per.max() < 5e-9)}
+            assert parity["ok"], parity
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
@@ -310,6 +445,8 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity": parity,
+            "strong": strong,
         }
         print(json.dumps(line))
     if world > 1:
