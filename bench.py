@@ -362,8 +362,8 @@ def main():
     if world > 1:
         n_s = N_TRAJ_PER_GPU // world + (1 if rank < N_TRAJ_PER_GPU % world else 0)
         solver.n = n_s
-        solver._check(lib.pnde_upload(h, n_s, u0_pin[:, :n_s].contiguous().data_ptr(), p_pin[:, :n_s].contiguous().data_ptr()),
-                      "pnde_upload")
+        u0_s, p_s = u0_pin[:, :n_s].contiguous(), p_pin[:, :n_s].contiguous()  # keep alive across the call
+        solver._check(lib.pnde_upload(h, n_s, u0_s.data_ptr(), p_s.data_ptr()), "pnde_upload")
         for _ in range(2):
             solver.run()
         barrier()
@@ -426,12 +426,24 @@ def main():
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"the first {n_cpu} of the {n} trajectories x {STEPS_PER_TRAJ} steps ({dt_cpu:.1f} s), "
                              "oracle/pnde_ref.c (reference-faithful dense algorithm, pthreads)"}
-            # the CPU sample is the same inputs the GPU just solved: check u(t1) of every one of them
+            # the CPU sample is the same inputs the GPU just solved: check u(t1) of every one of them.  The yardstick
+            # is the reference arithmetic's own sensitivity: the same CPU code on inputs moved by one ulp (a few
+            # draws of this sweep have condition numbers of 1e9 over 2000 steps; tests/test_gpu_parity.py)
             got = mean_pin[:2, :n_cpu].numpy().T
-            per = np.abs(got - ref_mean[:, :2]).max(axis=1) / np.abs(ref_mean[:, :2]).max(axis=1)
+            sc = np.abs(ref_mean[:, :2]).max(axis=1)
+            per = np.abs(got - ref_mean[:, :2]).max(axis=1) / sc
+            n_own = min(n_cpu, 8000)
+            rng = np.random.default_rng(1)
+            p_ulp = p_np[:, :n_own] * (1 + 2.2e-16 * rng.choice([-1.0, 0.0, 1.0], (3, n_own)))
+            own_mean = cpu_reference_run(n_own, inputs=(u0_np[:, :n_own], p_ulp))[4]
+            own = np.abs(own_mean[:, :2] - ref_mean[:n_own, :2]).max(axis=1) / sc[:n_own]
+            qs = lambda x: {"median": float(np.median(x)), "p99": float(np.quantile(x, 0.99)), "max": float(x.max())}  # noqa: E731
             parity = {"n": int(n_cpu), "max_rel_u": float(per.max()), "median_rel_u": float(np.median(per)),
-                      "against": "oracle/pnde_ref.c on the same inputs, full 2000 steps", "tolerance": 5e-9,
-                      "ok": bool(per.max() < 5e-9)}
+                      "p99_rel_u": float(np.quantile(per, 0.99)),
+                      "against": "oracle/pnde_ref.c on the same inputs, full 2000 steps",
+                      "reference_vs_itself_inputs_moved_1ulp": dict(n=int(n_own), **qs(own)),
+                      "criterion": "median < 1e-11 and max < 5 x the reference arithmetic's own 1-ulp sensitivity",
+                      "ok": bool(np.median(per) < 1e-11 and per.max() < 5 * max(own.max(), 1e-9))}
             assert parity["ok"], parity
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -97,6 +97,10 @@ extern "C" {
    (b) FixedDiffusion with z == 0 exactly: the reference returns one value where two are destructured and throws
        (src/diffusions.jl:18-20) -- the trajectory ends with PNDE_RET_ZERO_RESIDUAL instead of sigma^2 = 0. */
 
+#define PNDE_FLAG_ONE_THREAD 2 /* dense EK1 with d (q+1) >= 10 normally runs with two lanes of a warp per trajectory
+   (wide_filter.cuh); this flag selects the one-thread-per-trajectory kernel instead (A/B measurements; the two
+   kernels perform the same operations in the same order and return identical results) */
+
 /* which states pnde_get_history returns */
 #define PNDE_HIST_FILTERED 0
 #define PNDE_HIST_SMOOTHED 1

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("PNDE_LIB") or os.path.join(_HERE, "libpnde.so")  # PN
 ABI_VERSION = 2
 MAX_DEVICES = 16
 FLAG_REFERENCE_QUIRKS = 1
+FLAG_ONE_THREAD = 2
 ALG_EK0, ALG_EK1, ALG_IEKS = 0, 1, 2
 DIFFUSIONS = {"dynamic": 0, "fixed": 1, "fixedMAP": 2, "dynamicMV": 3, "fixedMV": 4}
 VF_KINDS = {"fhn_readme": 0, "fhn_lib": 1, "lotka_volterra": 2, "vanderpol": 3, "linear2": 4, "logistic": 5,

@@ -349,7 +349,7 @@ class FilterSolver:
 
     def __init__(self, prob: ODEProblem, alg: _EK, *, abstol=1e-6, reltol=1e-3, adaptive=True, dt=None,
                  save_everystep=True, save_stride=None, smooth=None, maxiters=100000, max_saved=0, device=-1,
-                 devices=None, reference_quirks=False,
+                 devices=None, reference_quirks=False, one_thread=False,
                  dtmin=0.0, dtmax=None, qmin=None, qmax=None, gamma=None, beta1=None, beta2=None):
         if not adaptive and dt is None:
             raise ValueError("Fixed timestep methods require a choice of dt")  # test/errors.jl:16-20
@@ -373,7 +373,7 @@ class FilterSolver:
             cfg.n_devices = len(devices)
             for i, dv in enumerate(devices):
                 cfg.device_list[i] = dv
-        cfg.flags = L.FLAG_REFERENCE_QUIRKS if reference_quirks else 0
+        cfg.flags = (L.FLAG_REFERENCE_QUIRKS if reference_quirks else 0) | (L.FLAG_ONE_THREAD if one_thread else 0)
         self.devices = devices
         cfg.ieks_iterations = int(alg.iterations)
         cfg.abstol, cfg.reltol = float(abstol), float(reltol)

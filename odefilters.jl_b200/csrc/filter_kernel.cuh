@@ -26,7 +26,7 @@ enum { DIFF_DYNAMIC = 0, DIFF_FIXED = 1, DIFF_FIXED_MAP = 2, DIFF_DYNAMIC_MV = 3
 enum { SAVE_FINAL = 0, SAVE_EVERY = 1, SAVE_STRIDE = 2 };
 enum { RET_SUCCESS = 0, RET_MAXITERS = 1, RET_DTNAN = 2, RET_NONFINITE = 3, RET_HISTORY_FULL = 4, RET_DTMIN = 5,
        RET_ZERO_RESIDUAL = 6 };
-enum { FLAG_REFERENCE_QUIRKS = 1 };
+enum { FLAG_REFERENCE_QUIRKS = 1, FLAG_ONE_THREAD = 2 };
 
 struct CtrlParams {
   double abstol, reltol, dt, t0, t1;

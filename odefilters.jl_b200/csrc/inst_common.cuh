@@ -4,6 +4,7 @@
 #include "convert_kernel.cuh"
 #include "post_kernels.cuh"
 #include "smoother_kernel.cuh"
+#include "wide_filter.cuh"
 
 namespace pnde {
 
@@ -21,6 +22,26 @@ cudaError_t launch_filter_t(const ModelOps*, const FilterParams& prm, bool adapt
     filter_kernel<M, true><<<(unsigned)grid, block, smem, s>>>(prm);
   } else
     filter_kernel<M, false><<<(unsigned)grid, block, 0, s>>>(prm);
+  return cudaGetLastError();
+}
+
+// Dense EK1 at D >= 10: G = 2 lanes per trajectory (wide_filter.cuh) unless the handle asks for one thread per trajectory
+// (PNDE_FLAG_ONE_THREAD: A/B measurements and the bitwise-equality test of the two kernels).
+template <class VF, int Q>
+cudaError_t launch_filter_wide_t(const ModelOps* self, const FilterParams& prm, bool adaptive, cudaStream_t s) {
+  using W = WideEK1<VF, Q, 2>;
+  if (prm.flags & FLAG_ONE_THREAD) return launch_filter_t<DenseEK1<VF, Q>>(self, prm, adaptive, s);
+  const int block = PNDE_WIDE_BLOCK;
+  const long long grid = (prm.count * W::G + block - 1) / block;
+  const size_t scr = (size_t)(block / W::G) * W::SCR * sizeof(double);
+  const size_t smem = scr + (adaptive ? (size_t)W::STATE_LEN * block * sizeof(double) : 0);
+  cudaError_t e = adaptive ? cudaFuncSetAttribute(wide_filter_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(wide_filter_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (adaptive)
+    wide_filter_kernel<W, true><<<(unsigned)grid, block, smem, s>>>(prm);
+  else
+    wide_filter_kernel<W, false><<<(unsigned)grid, block, smem, s>>>(prm);
   return cudaGetLastError();
 }
 
@@ -85,10 +106,23 @@ const ModelOps* make_ops() {
   return &ops;
 }
 
+template <class VF, int Q>
+const ModelOps* make_ops_ek1() {
+  using M = DenseEK1<VF, Q>;
+  if constexpr (M::D >= 10 && VF::d % 2 == 0) {
+    static const ModelOps ops = {M::d, M::q, M::D, M::ND, M::REC, SmoothModel<M>::SREC, M::VF::np, true,
+                                 &launch_filter_wide_t<VF, Q>, &launch_convert_t<M>, &launch_smooth_t<M>,
+                                 &launch_sample_t<M>, &launch_dense_t<M>};
+    return &ops;
+  } else {
+    return make_ops<M>();
+  }
+}
+
 // q = 1..QINST for every algorithm
 #define PNDE_QCASE(VF, Q)                                                     \
   case Q:                                                                     \
-    if (alg == 1) return make_ops<DenseEK1<VF, Q>>();                         \
+    if (alg == 1) return make_ops_ek1<VF, Q>();                               \
     return mvdyn ? make_ops<KronEK0<VF, Q, true>>() : make_ops<KronEK0<VF, Q, false>>();
 
 #define PNDE_DEFINE_OPS(NAME, VF)                             \
