@@ -217,6 +217,13 @@ int pnde_get_final(pnde_handle* h, double* mean, double* cov, double* t_final, d
 int pnde_get_history(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end,
                      int64_t* offsets, double* t, double* mean, double* cov, double* diffusion);
 
+/* The square roots of the same states (SRMatrix.squareroot, src/squarerootmatrix.jl:10-16; consumed e.g. by
+ * src/solution_sampling.jl:6-12): sqrt [total][D][D] row-major with Sigma = S S'.  Filtered states return the
+ * rank-(D - d) factor the kernels carry, padded with d zero columns; smoothed states the lower-triangular factor of
+ * the smoother.  No factorisation happens on the way out: these ARE the device-side representations. */
+int pnde_get_history_sqrt(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end, int64_t* offsets,
+                          double* sqrt);
+
 /* sol.pu (src/integrator_utils.jl:45): marginals of the solution block, same CSR layout:
  * u [total][d], cov_u [total][d(d+1)/2]. */
 int pnde_get_marginals(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end,
@@ -229,6 +236,19 @@ int pnde_get_marginals(pnde_handle* h, int32_t which, int64_t traj_begin, int64_
  * components).  offsets is an output. */
 int pnde_sample(pnde_handle* h, int64_t traj_begin, int64_t traj_end, int32_t n_samples, uint64_t seed,
                 int64_t* offsets, double* t, double* samples);
+
+/* perform_step! (src/perform_step.jl:27-93) applied once to n caller-supplied states: the entry a step!/callback
+ * driver needs, and the teacher-forced unit of the parity protocol.  Stateless with respect to the
+ * handle's ensemble; uses the handle's algorithm, order, diffusion model and tolerances.
+ *   in : mean [D][n], sqrt [D*D][n] (entry (i,j) of S at (i*D + j)*n + traj, Sigma = S S'; must be a state the filter
+ *        can be in: zero or a filter posterior -- anything else yields status 1), t [n] (may be NULL: autonomous
+ *        fields), dt [n], p [n_params][n], uprev [d][n] (integ.u before the step, for EEst; NULL: EEst = 0)
+ *   out: mean_out [D][n], cov_out [D(D+1)/2][n] packed lower (x_filt), sigma2 [nd][n] (local diffusion),
+ *        eest [n] (src/perform_step.jl:84), u_out [d][n], quad_logdet [2][n] (z' S^-1 z, log det S of :66),
+ *        status [n] (0 ok, 1 not representable, 2 non-finite).  Any output except status may be NULL. */
+int pnde_step_from_state(pnde_handle* h, int64_t n, const double* mean, const double* sqrt, const double* t,
+                         const double* dt, const double* p, const double* uprev, double* mean_out, double* cov_out,
+                         double* sigma2, double* eest, double* u_out, double* quad_logdet, int32_t* status);
 
 /* Dense output sol(t) (GaussianODEFilterPosterior, src/solution.jl:165-215) of every trajectory in
  * [traj_begin, traj_end) at the n_t query times t[]: predict from the left filtered neighbour and, when

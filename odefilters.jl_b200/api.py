@@ -172,12 +172,13 @@ def shard_strided(n: int, rank: int, world: int) -> np.ndarray:
 # Result containers (src/squarerootmatrix.jl, GaussianDistributions.Gaussian, src/solution.jl:8-24)
 # --------------------------------------------------------------------------------------------
 class SRMatrix:
-    """PSD matrix with a square-root factor (src/squarerootmatrix.jl:9-16).  ``mat`` comes from the
-    device; ``squareroot`` (any S with S S' = mat, not unique in the reference either) is derived lazily."""
+    """PSD matrix with a square-root factor (src/squarerootmatrix.jl:9-16).  ``mat`` and ``squareroot`` both come from
+    the device (pnde_get_history / pnde_get_history_sqrt: the factor the kernels carry, S S' = mat; like the
+    reference's, it is not unique).  Only an SRMatrix built from a bare matrix derives a factor on the host."""
 
-    def __init__(self, mat: np.ndarray):
+    def __init__(self, mat: np.ndarray, squareroot: Optional[np.ndarray] = None):
         self.mat = mat
-        self._sr = None
+        self._sr = squareroot
 
     @property
     def squareroot(self) -> np.ndarray:
@@ -237,14 +238,14 @@ def _unpack_lower(packed: np.ndarray, D: int) -> np.ndarray:
 class _GaussianList:
     """StructArray{Gaussian} over SoA buffers (src/solution.jl:60-64): ``.mu`` [N, D], ``.Sigma`` [N, D, D]."""
 
-    def __init__(self, mu: np.ndarray, cov: np.ndarray):
-        self.mu, self.Sigma = mu, cov
+    def __init__(self, mu: np.ndarray, cov: np.ndarray, sqrt: Optional[np.ndarray] = None):
+        self.mu, self.Sigma, self.sqrt = mu, cov, sqrt  # sqrt: [N, rows, D] factors from the device, or None
 
     def __len__(self):
         return self.mu.shape[0]
 
     def __getitem__(self, i) -> Gaussian:
-        return Gaussian(self.mu[i], SRMatrix(self.Sigma[i]))
+        return Gaussian(self.mu[i], SRMatrix(self.Sigma[i], None if self.sqrt is None else self.sqrt[i]))
 
 
 def mean(x):
@@ -539,6 +540,37 @@ class FilterSolver:
                                               mean.ctypes.data, cov.ctypes.data, diff.ctypes.data), "pnde_get_history")
         return offsets, t, mean, cov, diff
 
+    def history_sqrt(self, which: int, lo: int, hi: int):
+        """pnde_get_history_sqrt: (offsets, S [total, D, D]) with Sigma = S S' (SRMatrix.squareroot) -- the factors the
+        kernels carry, no factorisation on the way out."""
+        total = int(self.counts()["n_saved"][lo:hi].sum())
+        offsets = np.zeros(hi - lo + 1, dtype=np.int64)
+        S = np.empty((total, self.D, self.D))
+        self._check(self.lib.pnde_get_history_sqrt(self._h, which, lo, hi, offsets.ctypes.data, S.ctypes.data),
+                    "pnde_get_history_sqrt")
+        return offsets, S
+
+    def step_from_state(self, mean, sqrt, dt, p, t=None, uprev=None) -> dict:
+        """pnde_step_from_state: perform_step! (src/perform_step.jl:27-93) once from n given states.
+        mean [n, D], sqrt [n, D, D] (Sigma = S S'), dt [n], p [n, n_params], uprev [n, d] (for EEst)."""
+        mean = np.asarray(mean, dtype=np.float64)
+        n, D, d = mean.shape[0], self.D, self.d
+        soa = lambda a, k: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(n, k).T)  # noqa: E731
+        m_, s_, dt_, p_ = soa(mean, D), soa(sqrt, D * D), soa(dt, 1), soa(p, max(self.npar, 1))
+        t_ = soa(t, 1) if t is not None else None
+        up_ = soa(uprev, d) if uprev is not None else None
+        nd = d if (self.alg.kind == L.ALG_EK0) else 1
+        out = dict(mean=np.empty((D, n)), cov=np.empty((D * (D + 1) // 2, n)), sigma2=np.empty((nd, n)), eest=np.empty(n),
+                   u=np.empty((d, n)), ql=np.empty((2, n)), status=np.zeros(n, dtype=np.int32))
+        ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
+        self._check(self.lib.pnde_step_from_state(self._h, n, ptr(m_), ptr(s_), ptr(t_), ptr(dt_), ptr(p_), ptr(up_),
+                                                  ptr(out["mean"]), ptr(out["cov"]), ptr(out["sigma2"]), ptr(out["eest"]),
+                                                  ptr(out["u"]), ptr(out["ql"]), ptr(out["status"])),
+                    "pnde_step_from_state")
+        return dict(mean=out["mean"].T.copy(), cov=_unpack_lower(out["cov"].T.copy(), D), sigma2=out["sigma2"].T.copy(),
+                    eest=out["eest"], u=out["u"].T.copy(), quad=out["ql"][0].copy(), logdet=out["ql"][1].copy(),
+                    status=out["status"])
+
     def sample(self, lo: int, hi: int, n_samples: int, seed: int = 0):
         """pnde_sample for trajectories [lo, hi): (offsets, t [total], samples [total, n_samples, D])."""
         cnt = self.counts()["n_saved"][lo:hi]
@@ -584,15 +616,17 @@ class FilterSolver:
             llv = ll[i]
         else:
             _, t, mean, cov, diffs = self.history(L.HIST_FILTERED, i, i + 1)
-            xf = _GaussianList(mean, _unpack_lower(cov, D))
+            xf = _GaussianList(mean, _unpack_lower(cov, D), self.history_sqrt(L.HIST_FILTERED, i, i + 1)[1])
             xs = None
             if smoothed:
                 _, _, ms, cs, _ = self.history(L.HIST_SMOOTHED, i, i + 1)
-                xs = _GaussianList(ms, _unpack_lower(cs, D))
+                xs = _GaussianList(ms, _unpack_lower(cs, D), self.history_sqrt(L.HIST_SMOOTHED, i, i + 1)[1])
             diffs = diffs[1:]  # entry 0 belongs to no interval
             llv = (final or self.final())[3][i]
         src = xs if xs is not None else xf
-        pu = _GaussianList(src.mu[:, :d].copy(), src.Sigma[:, :d, :d].copy())
+        # sol.pu = SolProj * x: the factor of the marginal is E0 S, d x D (src/squarerootmatrix.jl:38-39)
+        pu = _GaussianList(src.mu[:, :d].copy(), src.Sigma[:, :d, :d].copy(),
+                           None if src.sqrt is None else src.sqrt[:, :d, :].copy())
         return ProbODESolution(
             t=t, u=pu.mu, pu=pu, x_filt=xf, x_smooth=xs,
             diffusions=diffs if self.is_mv else diffs[:, 0],

@@ -52,6 +52,43 @@ __global__ void __launch_bounds__(128) convert_kernel(const ConvertParams c) {
     const double* sb = c.smooth + (slot * SREC) * n + tr;
     SmoothModel<M>::load_cov(sb, n, mean, cov);
   }
+  if (c.sqrt) {
+    // D x D square root, row major: filtered states are the reduced-rank factor [W | Lz] padded with d zero columns
+    // (calibrated), smoothed states the lower-triangular factor of the smoother
+    double* o2 = c.sqrt + o * (D * D);
+    for (int i = 0; i < D * D; ++i) o2[i] = 0.0;
+    using SMd = SmoothModel<M>;
+    using SC = typename SMd::SC;
+    constexpr int DC = SMd::DC, NF = SMd::NF, DCOV = DC * (q + 1);
+    if (c.which == 0) {
+      typename M::State st;
+      M::load(st, base + (long long)(1 + ND) * n, n);
+      for (int rep = 0; rep < D / DCOV; ++rep) {  // dense EK1: one factor; Kronecker: one replica per dimension
+        const Factor<DC, q>* F;
+        if constexpr (M::IS_EK1) F = &st.F; else F = &st.F[NF > 1 ? rep : 0];
+        const double gs = sqrt(M::IS_EK1 ? dimscale[0] : dimscale[rep < d ? rep : 0]);
+        double cols[SC::R][DCOV];
+        SC::cols_from_factor(*F, cols);
+        for (int cc = 0; cc < SC::R; ++cc)
+          for (int k = 0; k < DCOV; ++k) {
+            const int row = M::IS_EK1 ? k : k * d + rep, col = M::IS_EK1 ? cc : cc * d + rep;
+            o2[row * D + col] = gs * cols[cc][k];
+          }
+      }
+    } else {
+      const double* sb = c.smooth + (slot * SREC) * n + tr;
+      for (int rep = 0; rep < D / DCOV; ++rep) {
+        const int f = NF > 1 ? rep : 0;
+        double ds = 1.0;
+        if constexpr (!M::IS_EK1) ds = sqrt(sb[(long long)(D + NF * SC::NP + rep) * n]);
+        for (int k = 0; k < DCOV; ++k)
+          for (int cc = 0; cc <= k; ++cc) {
+            const int row = M::IS_EK1 ? k : k * d + rep, col = M::IS_EK1 ? cc : cc * d + rep;
+            o2[row * D + col] = ds * sb[(long long)(D + f * SC::NP + SC::tri(k, cc)) * n];
+          }
+      }
+    }
+  }
   if (!c.marginals) {
     if (c.mean)
       for (int i = 0; i < D; ++i) c.mean[o * D + i] = mean[i];

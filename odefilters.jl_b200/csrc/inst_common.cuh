@@ -5,6 +5,7 @@
 #include "post_kernels.cuh"
 #include "smoother_kernel.cuh"
 #include "wide_filter.cuh"
+#include "step_kernel.cuh"
 
 namespace pnde {
 
@@ -89,6 +90,14 @@ cudaError_t launch_dense_t(const ModelOps*, const DenseParams& dp, cudaStream_t 
 }
 
 template <class M>
+cudaError_t launch_step_t(const ModelOps*, const StepParams& sp, cudaStream_t s) {
+  const int block = 64;
+  if (sp.n <= 0) return cudaSuccess;
+  step_kernel<M><<<(unsigned)((sp.n + block - 1) / block), block, 0, s>>>(sp);
+  return cudaGetLastError();
+}
+
+template <class M>
 const ModelOps* make_ops() {
   static const ModelOps ops = {M::d,
                                M::q,
@@ -102,7 +111,8 @@ const ModelOps* make_ops() {
                                &launch_convert_t<M>,
                                &launch_smooth_t<M>,
                                &launch_sample_t<M>,
-                               &launch_dense_t<M>};
+                               &launch_dense_t<M>,
+                               &launch_step_t<M>};
   return &ops;
 }
 
@@ -112,7 +122,7 @@ const ModelOps* make_ops_ek1() {
   if constexpr (M::D >= 10 && VF::d % 2 == 0) {
     static const ModelOps ops = {M::d, M::q, M::D, M::ND, M::REC, SmoothModel<M>::SREC, M::VF::np, true,
                                  &launch_filter_wide_t<VF, Q>, &launch_convert_t<M>, &launch_smooth_t<M>,
-                                 &launch_sample_t<M>, &launch_dense_t<M>};
+                                 &launch_sample_t<M>, &launch_dense_t<M>, &launch_step_t<M>};
     return &ops;
   } else {
     return make_ops<M>();

@@ -27,6 +27,7 @@ struct ConvertParams {
   double* cov;               // [total][D(D+1)/2] or [total][d(d+1)/2]
   double* diffusion;         // [total][nd_out]
   int nd_out;
+  double* sqrt;              // [total][D][D] row-major square root S, Sigma = S S' (SRMatrix.squareroot), or null
 };
 
 struct SmoothParams {
@@ -44,6 +45,7 @@ struct SmoothParams {
 
 struct SampleParams;
 struct DenseParams;
+struct StepParams;
 
 #ifndef __CUDACC_RTC__
 // `self` lets run-time compiled models (rtc_model.cu) carry their CUfunction handles
@@ -55,6 +57,7 @@ struct ModelOps {
   cudaError_t (*launch_smooth)(const ModelOps* self, const SmoothParams&, cudaStream_t);
   cudaError_t (*launch_sample)(const ModelOps* self, const SampleParams&, cudaStream_t);
   cudaError_t (*launch_dense)(const ModelOps* self, const DenseParams&, cudaStream_t);
+  cudaError_t (*launch_step)(const ModelOps* self, const StepParams&, cudaStream_t);  // null: not built (NVRTC models)
 };
 
 // defined in inst_*.cu

@@ -16,6 +16,7 @@
 #include "lorenz96_kernel.cuh"
 #include "post_kernels.cuh"
 #include "rtc_model.h"
+#include "step_kernel.cuh"
 
 using namespace pnde;
 
@@ -1089,7 +1090,7 @@ static int multi_csr(pnde_handle* h, int64_t tb, int64_t te, int64_t* offsets, F
 extern "C" {
 
 static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t te, int64_t* offsets, double* t,
-                            double* mean, double* cov, double* diffusion, bool marginals) {
+                            double* mean, double* cov, double* diffusion, bool marginals, double* sqrt_out = nullptr) {
   if (!h) return PNDE_ERR_ARG;
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
   if (h->cfg.save_mode == PNDE_SAVE_FINAL) return h->fail(PNDE_ERR_STATE, "no history was saved (save_mode = final)");
@@ -1099,7 +1100,8 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
     const int64_t ndo = (df0 == PNDE_DIFF_DYNAMIC_MV || df0 == PNDE_DIFF_FIXED_MV) ? h->d : 1;
     return multi_csr(h, tb, te, offsets, [&](pnde_handle* kid, int64_t lo, int64_t hi, int64_t* offs, int64_t base) {
       return get_history_impl(kid, which, lo, hi, offs, t ? t + base : nullptr, mean ? mean + base * DM : nullptr,
-                              cov ? cov + base * NC : nullptr, diffusion ? diffusion + base * ndo : nullptr, marginals);
+                              cov ? cov + base * NC : nullptr, diffusion ? diffusion + base * ndo : nullptr, marginals,
+                              sqrt_out ? sqrt_out + base * h->D * h->D : nullptr);
     });
   }
   if (which == PNDE_HIST_SMOOTHED && !h->smoothed) return h->fail(PNDE_ERR_STATE, "history has not been smoothed");
@@ -1121,8 +1123,9 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   const int nd_out = is_mv ? o->d : 1;
   const int DM = marginals ? o->d : o->D;
   const size_t nm = (size_t)total * DM, nc = (size_t)total * (size_t)(DM * (DM + 1) / 2), ndif = (size_t)total * nd_out;
+  const size_t nsq = sqrt_out ? (size_t)total * o->D * o->D : 0;
   CK(h->scratch_off.ensure(((size_t)ntr + 1) * 8), "alloc offsets");
-  CK(h->scratch_out.ensure(((size_t)total + nm + nc + ndif) * 8 + 64), "alloc history staging");
+  CK(h->scratch_out.ensure(((size_t)total + nm + nc + ndif + nsq) * 8 + 64), "alloc history staging");
   CK(cudaMemcpyAsync(h->scratch_off.p, off.data(), ((size_t)ntr + 1) * 8, cudaMemcpyHostToDevice, h->stream), "H2D offsets");
   double* dt_ = h->scratch_out.as<double>();
   double* dmean = dt_ + total;
@@ -1151,7 +1154,14 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   cp.cov = dcov;
   cp.diffusion = ddif;
   cp.nd_out = nd_out;
+  cp.sqrt = sqrt_out ? ddif + ndif : nullptr;
+  if (sqrt_out) {  // only the factor was asked for
+    cp.mean = nullptr;
+    cp.cov = nullptr;
+    cp.diffusion = nullptr;
+  }
   CK(o->launch_convert(o, cp, h->stream), "convert kernel launch");
+  if (sqrt_out) CK(cudaMemcpyAsync(sqrt_out, cp.sqrt, nsq * 8, cudaMemcpyDeviceToHost, h->stream), "D2H sqrt");
   if (t) CK(cudaMemcpyAsync(t, dt_, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
   if (mean) CK(cudaMemcpyAsync(mean, dmean, nm * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
   if (cov) CK(cudaMemcpyAsync(cov, dcov, nc * 8, cudaMemcpyDeviceToHost, h->stream), "D2H cov");
@@ -1163,6 +1173,12 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
 int pnde_get_history(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end, int64_t* offsets, double* t,
                      double* mean, double* cov, double* diffusion) {
   return get_history_impl(h, which, traj_begin, traj_end, offsets, t, mean, cov, diffusion, false);
+}
+
+int pnde_get_history_sqrt(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end, int64_t* offsets,
+                          double* sqrt_out) {
+  if (!sqrt_out) return h ? h->fail(PNDE_ERR_ARG, "pnde_get_history_sqrt: null output") : PNDE_ERR_ARG;
+  return get_history_impl(h, which, traj_begin, traj_end, offsets, nullptr, nullptr, nullptr, nullptr, false, sqrt_out);
 }
 
 int pnde_get_marginals(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end, int64_t* offsets, double* t,
@@ -1238,6 +1254,74 @@ int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint6
   CK(o->launch_sample(o, sp, h->stream), "sample kernel launch");
   if (t) CK(cudaMemcpyAsync(t, dt_, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
   if (samples) CK(cudaMemcpyAsync(samples, dout, nout * 8, cudaMemcpyDeviceToHost, h->stream), "D2H samples");
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  return PNDE_OK;
+}
+
+int pnde_step_from_state(pnde_handle* h, int64_t n, const double* mean, const double* sqrt_in, const double* t,
+                         const double* dt, const double* p, const double* uprev, double* mean_out, double* cov_out,
+                         double* sigma2, double* eest, double* u_out, double* quad_logdet, int32_t* status) {
+  if (!h) return PNDE_ERR_ARG;
+  if (n <= 0 || !mean || !sqrt_in || !dt || (!p && h->np > 0) || !status)
+    return h->fail(PNDE_ERR_ARG, "pnde_step_from_state: bad arguments");
+  if (h->multi()) {
+    h->kid_lo.assign(h->kids.size() + 1, 0);  // a stateless call: run it on the first device
+    return pnde_step_from_state(h->kids[0], n, mean, sqrt_in, t, dt, p, uprev, mean_out, cov_out, sigma2, eest, u_out,
+                                quad_logdet, status);
+  }
+  if (!h->ops || !h->ops->launch_step)
+    return h->fail(PNDE_ERR_UNSUPPORTED, "pnde_step_from_state is built for the catalogue models (thread-per-trajectory paths)");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const ModelOps* o = h->ops;
+  const size_t N = (size_t)n, D = (size_t)o->D, NC = D * (D + 1) / 2, npar = (size_t)(o->np > 0 ? o->np : 1);
+  // one staging block: inputs then outputs
+  const size_t in_len = D + D * D + 2 + npar + (size_t)o->d, out_len = D + NC + (size_t)o->nd + 1 + (size_t)o->d + 2;
+  CK(h->scratch_out.ensure((in_len + out_len) * N * 8 + N * 4 + 64), "alloc step staging");
+  double* b = h->scratch_out.as<double>();
+  double *dmean = b, *dsq = dmean + D * N, *dt_ = dsq + D * D * N, *ddt = dt_ + N, *dp = ddt + N, *dup = dp + npar * N;
+  double *omean = dup + (size_t)o->d * N, *ocov = omean + D * N, *osig = ocov + NC * N, *oee = osig + (size_t)o->nd * N,
+         *ou = oee + N, *oql = ou + (size_t)o->d * N;
+  int* ost = reinterpret_cast<int*>(oql + 2 * N);
+  auto up = [&](double* dst, const double* src, size_t len) {
+    return cudaMemcpyAsync(dst, src, len * 8, cudaMemcpyHostToDevice, h->stream);
+  };
+  CK(up(dmean, mean, D * N), "H2D mean");
+  CK(up(dsq, sqrt_in, D * D * N), "H2D sqrt");
+  if (t) CK(up(dt_, t, N), "H2D t");
+  CK(up(ddt, dt, N), "H2D dt");
+  if (o->np > 0) CK(up(dp, p, npar * N), "H2D p");
+  if (uprev) CK(up(dup, uprev, (size_t)o->d * N), "H2D uprev");
+  StepParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.n = n;
+  sp.mean = dmean;
+  sp.sqrt = dsq;
+  sp.t = dt_;
+  sp.dt = ddt;
+  sp.p = dp;
+  sp.uprev = uprev ? dup : nullptr;
+  sp.mean_out = omean;
+  sp.cov_out = ocov;
+  sp.sigma2 = osig;
+  sp.eest = oee;
+  sp.u_out = ou;
+  sp.quad_logdet = oql;
+  sp.status = ost;
+  sp.diffusion = h->cfg.diffusion;
+  sp.abstol = h->cfg.abstol;
+  sp.reltol = h->cfg.reltol;
+  sp.C = h->C;
+  CK(o->launch_step(o, sp, h->stream), "step kernel launch");
+  auto down = [&](void* dst, const void* src, size_t bytes) {
+    return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream) : cudaSuccess;
+  };
+  CK(down(mean_out, omean, D * N * 8), "D2H mean");
+  CK(down(cov_out, ocov, NC * N * 8), "D2H cov");
+  CK(down(sigma2, osig, (size_t)o->nd * N * 8), "D2H sigma2");
+  CK(down(eest, oee, N * 8), "D2H eest");
+  CK(down(u_out, ou, (size_t)o->d * N * 8), "D2H u");
+  CK(down(quad_logdet, oql, 2 * N * 8), "D2H quad/logdet");
+  CK(down(status, ost, N * 4), "D2H status");
   CK(cudaStreamSynchronize(h->stream), "stream synchronize");
   return PNDE_OK;
 }

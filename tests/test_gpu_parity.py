@@ -1041,3 +1041,89 @@ def test_lane_group_kernel_equals_one_thread_kernel(name, q, adaptive):
         for x, y in zip(s1, s2):
             assert np.array_equal(x, y)
     assert (c2["retcode"] == 0).all()
+
+
+# ---- teacher-forced unit parity (SURVEY 8c protocol (i); test/filtering.jl:10-124) -------------------------------
+@pytest.mark.parametrize("name,kind,q,diffusion", [
+    ("fhn_readme", "EK1", 3, "dynamic"), ("lotka_volterra", "EK1", 2, "fixed"), ("vanderpol", "EK1", 3, "dynamic"),
+    ("lotka_volterra", "EK0", 3, "dynamic"), ("fhn_lib", "EK1", 1, "fixedMAP"), ("lotka_volterra", "EK1", 5, "dynamic"),
+    ("fhn_readme", "EK0", 2, "fixedMV"), ("logistic", "EK1", 4, "dynamic"),
+])
+def test_teacher_forced_single_step(name, kind, q, diffusion):
+    """One perform_step! (src/perform_step.jl:27-93) from IDENTICAL inputs: mid-trajectory oracle states (mu, S) are
+    handed to the device through pnde_step_from_state and to the oracle's perform_step; predicted-and-updated mean,
+    the FULL covariance, the local diffusion, EEst and the log-likelihood terms must agree to 1e-12 (relative to the
+    block max-norm).  This is the per-step claim behind every trajectory-level tolerance."""
+    import odefilters_b200 as B
+
+    u0, p = PROBLEMS[name]
+    d = len(u0)
+    alg_o = O.Alg(kind, q, diffusion, False)
+    prob_o = O.Problem(O.CATALOGUE[name], list(u0), (0.0, 1.5), list(p))
+    so = O.solve_ivp(prob_o, alg_o, abstol=1e-7, reltol=1e-4)
+    n = len(so.t)
+    picks = sorted(set([0, 1, 2, n // 3, n // 2, (2 * n) // 3, n - 2]))
+    cases = []
+    for i in picks:
+        h = so.t[i + 1] - so.t[i]
+        for dt in (h, 0.6 * h):
+            cases.append((i, dt))
+    mu = np.array([so.x_filt[i].mu for i, _ in cases])
+    S = np.array([so.x_filt[i].Sigma.squareroot for i, _ in cases])
+    dts = np.array([dt for _, dt in cases])
+    uprev = np.array([np.asarray(so.u[i], dtype=float) for i, _ in cases])
+    # oracle: one perform_step per case from exactly these states
+    ref = []
+    for (i, dt), m_, S_, up in zip(cases, mu, S, uprev):
+        cache = O._Cache(prob_o, alg_o, float)
+        cache.x = O.Gaussian(m_.copy(), O.SRMatrix(S_.copy()))
+        sol = O.Solution(d=cache.d, q=q, A=cache.A, Q=cache.Q)
+        sol.diffusions = [1.0] * 3  # static models: success_iter = 3 with previous global value 1 (local value is compared)
+        e, uf = O.perform_step(cache, prob_o, alg_o, sol, so.t[i], dt, True, 1e-7, 1e-4, up, 3)
+        ref.append((cache.x_filt.mu, cache.x_filt.Sigma.mat, cache.local_diffusion, e, uf, cache.log_likelihood))
+    algB = (B.EK1 if kind == "EK1" else B.EK0)(order=q, diffusionmodel=diffusion, smooth=False)
+    s = B.FilterSolver(B.ODEProblem(name, u0, (0.0, 1.5), p), algB, abstol=1e-7, reltol=1e-4, save_everystep=False)
+    out = s.step_from_state(mu, S, dts, np.tile(p, (len(cases), 1)), t=np.array([so.t[i] for i, _ in cases]), uprev=uprev)
+    assert (out["status"] == 0).all()
+    worst = dict(mean=0.0, cov=0.0, sigma2=0.0, eest=0.0, u=0.0, ll=0.0)
+    for k, (m_o, C_o, loc, e, uf, ll) in enumerate(ref):
+        for b in range(q + 1):
+            worst["mean"] = max(worst["mean"], rel(out["mean"][k, b * d:(b + 1) * d], m_o[b * d:(b + 1) * d]))
+            for c in range(b + 1):
+                bo = C_o[b * d:(b + 1) * d, c * d:(c + 1) * d]
+                if np.abs(bo).max() > 0:
+                    worst["cov"] = max(worst["cov"], rel(out["cov"][k, b * d:(b + 1) * d, c * d:(c + 1) * d], bo))
+        lo = np.atleast_1d(np.asarray(loc, dtype=float))
+        lo = lo[:d]  # MV models: kron(I_{q+1}, Sigma) diagonal, the first d entries are the per-dimension values
+        worst["sigma2"] = max(worst["sigma2"], rel(out["sigma2"][k][:len(lo)], lo))
+        worst["eest"] = max(worst["eest"], abs(out["eest"][k] - e) / e)
+        worst["u"] = max(worst["u"], rel(out["u"][k], np.asarray(uf, dtype=float)))
+        ll_g = -0.5 * (out["quad"][k] + out["logdet"][k] + d * np.log(2 * np.pi))
+        worst["ll"] = max(worst["ll"], abs(ll_g - ll) / abs(ll))
+    report("teacher_forced", name=name, kind=kind, q=q, diffusion=diffusion, cases=len(cases), **worst)
+    print(name, kind, q, diffusion, worst)
+    assert worst["mean"] < 1e-12 and worst["u"] < 1e-12
+    assert worst["cov"] < 1e-11 and worst["sigma2"] < 1e-10 and worst["eest"] < 1e-10 and worst["ll"] < 1e-10
+    # a state the filter can never be in (full-rank covariance) is refused per trajectory, not projected
+    bad = s.step_from_state(mu[:1], np.eye(d * (q + 1))[None], dts[:1], np.tile(p, (1, 1)), uprev=uprev[:1])
+    assert bad["status"][0] == 1
+
+
+def test_square_root_factors_cross_the_abi():
+    """SRMatrix.squareroot (src/squarerootmatrix.jl:10-16) comes from the device: S S' equals the covariance the
+    same call chain returns, for filtered, smoothed and marginal (sol.pu) states, dense and Kronecker models."""
+    import odefilters_b200 as B
+
+    for alg in (B.EK1(order=3, smooth=True), B.EK0(order=2, smooth=True), B.EK0(order=2, diffusionmodel="fixedMV", smooth=True),
+                B.EK1(order=2, diffusionmodel="fixed", smooth=False)):
+        sol = gpu_solve("lotka_volterra", alg, tspan=(0.0, 1.0))
+        for lst in (sol.x_filt, sol.x_smooth, sol.pu):
+            if lst is None:
+                continue
+            assert lst.sqrt is not None
+            SS = np.einsum("nij,nkj->nik", lst.sqrt, lst.sqrt)
+            scale = np.sqrt(np.einsum("nii,njj->nij", lst.Sigma, lst.Sigma)) + 1e-300
+            assert np.max(np.abs(SS - lst.Sigma) / scale) < 1e-12
+        g = sol.x_filt[len(sol) // 2]
+        assert g.Sigma.squareroot.shape == (sol.x_filt.mu.shape[1],) * 2
+        assert np.linalg.matrix_rank(g.Sigma.squareroot) <= g.Sigma.squareroot.shape[0] - 2  # R = 0: rank D - d
