@@ -11,7 +11,7 @@ if "--sort" in sys.argv:  # neighbours in a warp get similar stiffness => simila
     mu = np.sort(mu)
 u0 = np.stack([np.zeros(n), np.sqrt(3.0) * (1 + 0.01 * rng.standard_normal(n))], axis=1)
 prob = B.ODEProblem("vanderpol", [0.0, np.sqrt(3.0)], (0.0, 1.0), (1e3,))
-s = B.FilterSolver(prob, B.EK1(order=5, smooth=False), save_everystep=False)
+s = B.FilterSolver(prob, B.EK1(order=5, smooth=False), save_everystep=False, one_thread="--one-thread" in sys.argv)
 s.upload(u0, mu[:, None])
 for _ in range(2):
     s.run()

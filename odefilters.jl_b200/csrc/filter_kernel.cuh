@@ -672,10 +672,12 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
       ret = RET_NONFINITE;  // OrdinaryDiffEq check_error!: unstable_check
       break;
     }
+#ifndef PNDE_NO_QUIRK_CHECK
     if (diffusion == DIFF_FIXED && quad == 0.0 && (prm.flags & FLAG_REFERENCE_QUIRKS)) {
       ret = RET_ZERO_RESIDUAL;  // the reference throws here (src/diffusions.jl:18-20)
       break;
     }
+#endif
     // ---- loopfooter! ----
     const double ttmp = t + dt;
     if (ADAPTIVE) {

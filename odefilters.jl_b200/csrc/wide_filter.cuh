@@ -20,12 +20,12 @@
 
 namespace pnde {
 
+// G adjacent lanes; every collective below is executed by the WHOLE warp in lockstep (full mask, sub-group width G)
 template <int G>
 struct LaneGroup {
-  int g;          // this lane's index in its group
-  unsigned mask;  // the group's lanes within the warp (all shuffles synchronise only these)
-  __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(mask, v, src, G); }
-  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  int g;  // this lane's index in its group
+  __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(0xffffffffu, v, src, G); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
 template <class VF_, int q_, int G_>
@@ -143,7 +143,7 @@ struct WideEK1 {
   // Sigma = diag(sc) S S' diag(sc), packed lower.  The rows of S live in different lanes: they meet in shared memory
   // (scr: SCR = D * R + q + 1 doubles of this group) and the lanes split the D (D + 1) / 2 entries.  Once per trajectory.
   __device__ static void final_cov(const State& s, const LaneGroup<G>& gp, const double (&sc)[q + 1], double* scr,
-                                   double* cov, long long stride) {
+                                   double* cov, long long stride, bool write) {
 #pragma unroll
     for (int k = 0; k <= q; ++k)
 #pragma unroll
@@ -161,7 +161,7 @@ struct WideEK1 {
       const int j = e - i * (i + 1) / 2;
       double acc = 0.0;
       for (int r = 0; r < R; ++r) acc = fma(scr[i * R + r], scr[j * R + r], acc);
-      cov[(long long)e * stride] = acc * scr[D * R + i / d] * scr[D * R + j / d];
+      if (write) cov[(long long)e * stride] = acc * scr[D * R + i / d] * scr[D * R + j / d];
     }
     gp.sync();
   }
@@ -466,6 +466,15 @@ struct WideEK1 {
 
 // ---------------------------------------------------------------------------------------------
 // The kernel: the control flow of filter_kernel (filter_kernel.cuh), G lanes per trajectory.
+//
+// The time loop is WARP-UNIFORM: every lane iterates until the slowest trajectory of its warp is done, a finished
+// group keeps executing the loop body with its bookkeeping switched off (`alive`) -- in SIMT lockstep that costs
+// nothing, the warp runs until its slowest trajectory anyway.  This is what lets every shuffle use the full-warp mask:
+// a partial-mask __shfl_sync compiles to WARPSYNC + a convergence-barrier region per shuffle (measured on the first
+// version of this kernel: 324 WARPSYNC / 388 BSSY-BSYNC pairs per step, and slower than the one-thread kernel it was
+// meant to replace); with the full mask it is a bare SHFL.IDX.
+// The accepted state also lives in shared memory ([element][thread]): a rejected step and a finished group both
+// simply reload it.
 // ---------------------------------------------------------------------------------------------
 #ifndef PNDE_WIDE_BLOCK
 #define PNDE_WIDE_BLOCK 128
@@ -476,12 +485,11 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
   constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, G = M::G;
   const long long gth = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long lid_ = gth / G;
-  if (lid_ >= prm.count) return;  // whole groups leave together (blockDim is a multiple of G)
+  const bool exists = lid_ < prm.count;  // lanes past the end of the ensemble shadow its last trajectory, silently
   LaneGroup<G> gp;
   gp.g = (int)(threadIdx.x % G);
-  gp.mask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) / G * G);
   const bool lead = gp.g == 0;
-  const long long tid = prm.first + lid_;
+  const long long tid = prm.first + (exists ? lid_ : prm.count - 1);
   const long long n = prm.n;
   const CtrlParams& K = prm.K;
   const int diffusion = prm.diffusion;
@@ -493,8 +501,8 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
 #pragma unroll
   for (int i = 0; i < d; ++i) u0[i] = prm.u0[(long long)i * n + tid];
 
-  // shared memory: [STATE_LEN][blockDim] stash of the pre-step state (ADAPTIVE only), followed by the
-  // [blockDim / G][D * R] scratch of final_cov (groups finish at different times: the two must not alias)
+  // shared memory: [STATE_LEN][blockDim] accepted state (ADAPTIVE only), then the [blockDim / G][SCR] scratch of
+  // final_cov
   extern __shared__ double wsm[];
   typename M::State st;
   {
@@ -518,10 +526,12 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
   double one[q + 1];
 #pragma unroll
   for (int k = 0; k <= q; ++k) one[k] = 1.0;
+  bool stopped = !exists;  // left the loop through a `break` of the one-thread kernel (ret != success), or shadow lane
 
   auto save = [&](const typename M::State& sv, const double (&sc)[q + 1], double tt, const double (&g)[ND]) {
     if (nsaved >= prm.max_saved) {
       ret = RET_HISTORY_FULL;
+      stopped = true;
       return;
     }
     double* base = prm.hist + ((long long)nsaved * REC) * n + tid;
@@ -533,7 +543,7 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
     M::store(sv, gp, sc, base + (long long)(1 + ND) * n, n);
     ++nsaved;
   };
-  if (prm.save_mode != SAVE_FINAL) save(st, one, t, gsaved);
+  if (prm.save_mode != SAVE_FINAL && exists) save(st, one, t, gsaved);
 
   double dt;
   if (ADAPTIVE) {
@@ -553,43 +563,54 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
   double Pk[q + 1], PIk[q + 1];
 #pragma unroll
   for (int k = 0; k <= q; ++k) Pk[k] = PIk[k] = 1.0;
+  if (ADAPTIVE) M::stash_store(st, wsm + threadIdx.x, blockDim.x);
 
-  while (t < K.t1) {
+  while (__any_sync(0xffffffffu, !stopped && t < K.t1)) {
+    bool alive = !stopped && t < K.t1;  // this group really takes a step in this iteration
     // ---- loopheader! ----
+    double dtn = dt;
     if (iter > 0) {
       if (accepted_prev)
-        dt = dtpropose;
+        dtn = dtpropose;
       else
-        dt = dt / fmin(1.0 / K.qmin, q11 / K.gamma);
+        dtn = dt / fmin(1.0 / K.qmin, q11 / K.gamma);
     }
-    ++iter;
-    if (iter > K.maxiters) {
-      ret = RET_MAXITERS;
-      break;
+    if (alive) {
+      ++iter;
+      if (iter > K.maxiters) {
+        ret = RET_MAXITERS;
+        stopped = true;
+        alive = false;
+      }
     }
     if (ADAPTIVE) {
-      dt = fmin(dt, K.dtmax);
-      dt = fmax(dt, K.dtmin);
-      dt = fmin(dt, K.t1 - t);
+      dtn = fmin(dtn, K.dtmax);
+      dtn = fmax(dtn, K.dtmin);
+      dtn = fmin(dtn, K.t1 - t);
     } else {
-      dt = fmin(K.dt, K.t1 - t);
+      dtn = fmin(K.dt, K.t1 - t);
     }
-    if (dt != dt) {
-      ret = RET_DTNAN;
-      break;
+    if (alive) {
+      dt = dtn;
+      if (dt != dt) {
+        ret = RET_DTNAN;
+        stopped = true;
+        alive = false;
+      } else if (ADAPTIVE && iter > 1 && !accepted_prev && fabs(dt) <= fabs(K.dtmin)) {
+        ret = RET_DTMIN;
+        stopped = true;
+        alive = false;
+      }
     }
-    if (ADAPTIVE && iter > 1 && !accepted_prev && fabs(dt) <= fabs(K.dtmin)) {
-      ret = RET_DTMIN;
-      break;
-    }
+    // a group that is not alive runs the step on a harmless step size and throws the result away
+    const double h = alive ? dt : (K.t1 - K.t0);
     // ---- perform_step! ----
     if (ADAPTIVE) {
-      M::stash_store(st, wsm + threadIdx.x, blockDim.x);
-      precond_scales<q>(dt, Pk, PIk);
+      precond_scales<q>(h, Pk, PIk);
       M::scale(st, Pk);
-    } else if (dt != hcur) {
+    } else if (h != hcur) {
       double Pn[q + 1], PIn[q + 1], sc[q + 1];
-      precond_scales<q>(dt, Pn, PIn);
+      precond_scales<q>(h, Pn, PIn);
 #pragma unroll
       for (int k = 0; k <= q; ++k) {
         sc[k] = Pn[k] * PIk[k];
@@ -597,13 +618,12 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
         PIk[k] = PIn[k];
       }
       M::scale(st, sc);
-      hcur = dt;
+      hcur = h;
     }
     double unew[d], err[d], local[ND], quad, detS;
 #pragma unroll
     for (int i = 0; i < ND; ++i) local[i] = 1.0;
     M::step(st, gp, p, PIk[0], PIk[1], Pk[1], diffusion, prm.C, unew, err, local, quad, detS);
-    ++nfe;
     double gcur[ND];
     if (diffusion == DIFF_DYNAMIC) {
       gcur[0] = local[0];
@@ -630,84 +650,86 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
       EEst = sqrt(acc / double(d));
     }
 #pragma unroll
-    for (int i = 0; i < d; ++i) {
-      uprev[i] = unew[i];
-      finite = finite && (fabs(unew[i]) <= 1.79769313486231570e308);
-    }
-    const bool commit = !ADAPTIVE || (EEst < 1.0);
+    for (int i = 0; i < d; ++i) finite = finite && (fabs(unew[i]) <= 1.79769313486231570e308);
+    const bool commit = alive && (!ADAPTIVE || (EEst < 1.0));
     const bool accept = !ADAPTIVE || (EEst <= 1.0);
     if (ADAPTIVE) {
       if (commit) {
         M::scale(st, PIk);
+        M::stash_store(st, wsm + threadIdx.x, blockDim.x);
       } else {
-        M::stash_load(st, wsm + threadIdx.x, blockDim.x);
+        M::stash_load(st, wsm + threadIdx.x, blockDim.x);  // rejected, or not alive: back to the accepted state
       }
     }
-    if (commit) {
-      ll_quad += quad;
-      ++ll_n;
-      if (detS > 1e-290 && detS < 1e290) {
-        const long long bits = __double_as_longlong(detS);
-        ll_exp += ((bits >> 52) & 0x7ff) - 1023;
-        ll_mant *= __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL);
-        if (ll_mant > 1e250) {
-          ll_log += log(ll_mant);
-          ll_mant = 1.0;
-        }
-      } else {
-        ll_log += log(detS);
-      }
-    }
-    if (!finite) {
-      ret = RET_NONFINITE;
-      break;
-    }
-    if (diffusion == DIFF_FIXED && quad == 0.0 && (prm.flags & FLAG_REFERENCE_QUIRKS)) {
-      ret = RET_ZERO_RESIDUAL;
-      break;
-    }
-    // ---- loopfooter! ----
-    const double ttmp = t + dt;
-    if (ADAPTIVE) {
-      double lE;
-      double qc = controller_factor(EEst, K, lqold, lE);
-      if (accept) {
-        ++nacc;
-        if (K.qsteady_min <= qc && qc <= K.qsteady_max) qc = 1.0;
-        lqold = ctrl_state_accept(EEst, lE, lqold0, K);
-        const double dtnew = dt / qc;
-        t = (fabs(ttmp - K.t1) < 10.0 * ulp_of(fmax(t, K.t1))) ? K.t1 : ttmp;
-        dtpropose = fmax(K.dtmin, fmin(K.dtmax, dtnew));
-      } else {
-        ++nrej;
-        q11 = ctrl_q11(EEst, lE, K);
-      }
-    } else {
-      ++nacc;
-      t = (fabs(ttmp - K.t1) < 10.0 * ulp_of(fmax(t, K.t1))) ? K.t1 : ttmp;
-      dtpropose = dt;
-    }
-    accepted_prev = accept;
-    if (accept) {
+    if (alive) {
+      ++nfe;
 #pragma unroll
-      for (int i = 0; i < ND; ++i) gsaved[i] = gcur[i];
-      const bool want = (prm.save_mode == SAVE_EVERY) ||
-                        (prm.save_mode == SAVE_STRIDE && (nacc % prm.save_stride == 0 || !(t < K.t1)));
-      if (want) {
-        if (ADAPTIVE)
-          save(st, one, t, gsaved);
-        else
-          save(st, PIk, t, gsaved);
-        if (ret == RET_HISTORY_FULL) break;
+      for (int i = 0; i < d; ++i) uprev[i] = unew[i];  // integ.u .= u_filt, even when rejected (:86)
+      if (commit) {
+        ll_quad += quad;
+        ++ll_n;
+        if (detS > 1e-290 && detS < 1e290) {
+          const long long bits = __double_as_longlong(detS);
+          ll_exp += ((bits >> 52) & 0x7ff) - 1023;
+          ll_mant *= __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL);
+          if (ll_mant > 1e250) {
+            ll_log += log(ll_mant);
+            ll_mant = 1.0;
+          }
+        } else {
+          ll_log += log(detS);
+        }
+      }
+      if (!finite) {
+        ret = RET_NONFINITE;
+        stopped = true;
+      } else if (diffusion == DIFF_FIXED && quad == 0.0 && (prm.flags & FLAG_REFERENCE_QUIRKS)) {
+        ret = RET_ZERO_RESIDUAL;
+        stopped = true;
+      } else {
+        // ---- loopfooter! ----
+        const double ttmp = t + dt;
+        if (ADAPTIVE) {
+          double lE;
+          double qc = controller_factor(EEst, K, lqold, lE);
+          if (accept) {
+            ++nacc;
+            if (K.qsteady_min <= qc && qc <= K.qsteady_max) qc = 1.0;
+            lqold = ctrl_state_accept(EEst, lE, lqold0, K);
+            const double dtnew = dt / qc;
+            t = (fabs(ttmp - K.t1) < 10.0 * ulp_of(fmax(t, K.t1))) ? K.t1 : ttmp;
+            dtpropose = fmax(K.dtmin, fmin(K.dtmax, dtnew));
+          } else {
+            ++nrej;
+            q11 = ctrl_q11(EEst, lE, K);
+          }
+        } else {
+          ++nacc;
+          t = (fabs(ttmp - K.t1) < 10.0 * ulp_of(fmax(t, K.t1))) ? K.t1 : ttmp;
+          dtpropose = dt;
+        }
+        accepted_prev = accept;
+        if (accept) {
+#pragma unroll
+          for (int i = 0; i < ND; ++i) gsaved[i] = gcur[i];
+          const bool want = (prm.save_mode == SAVE_EVERY) ||
+                            (prm.save_mode == SAVE_STRIDE && (nacc % prm.save_stride == 0 || !(t < K.t1)));
+          if (want) {
+            if (ADAPTIVE)
+              save(st, one, t, gsaved);
+            else
+              save(st, PIk, t, gsaved);
+          }
+        }
       }
     }
   }
 
-  // ---- outputs ----
+  // ---- outputs (the warp is converged here) ----
   double sc[q + 1];
 #pragma unroll
   for (int k = 0; k <= q; ++k) sc[k] = (ADAPTIVE || hcur < 0.0) ? 1.0 : PIk[k];
-  if (prm.mean) M::write_mean(st, gp, sc, prm.mean + tid, n);
+  if (prm.mean && exists) M::write_mean(st, gp, sc, prm.mean + tid, n);
   double ll = -0.5 * (ll_quad + 2.0 * (ll_log + log(ll_mant) + double(ll_exp) * 0.6931471805599453) +
                       double(ll_n) * double(d) * 1.8378770664093453);
   double cal = 1.0;
@@ -720,11 +742,10 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
     const double gq = sqrt(cal);
 #pragma unroll
     for (int k = 0; k <= q; ++k) sc2[k] = sc[k] * gq;
-    // every group of the warp may arrive here at a different time: the scratch is per group, syncs are per group
     double* scr = wsm + (ADAPTIVE ? (size_t)M::STATE_LEN * blockDim.x : 0) + (size_t)(threadIdx.x / G) * M::SCR;
-    M::final_cov(st, gp, sc2, scr, prm.cov + tid, n);
+    M::final_cov(st, gp, sc2, scr, prm.cov + tid, n, exists);
   }
-  if (lead) {
+  if (lead && exists) {
     if (prm.final_diff) prm.final_diff[tid] = gsaved[0];
     if (prm.t_final) prm.t_final[tid] = t;
     if (prm.loglik) prm.loglik[tid] = ll;
