@@ -95,7 +95,9 @@ extern "C" {
        (src/integrator_utils.jl:43-45) fills it before postamble! rescales x_filt (:4-18) -- pnde_get_marginals(
        PNDE_HIST_FILTERED) then returns uncalibrated cov_u (pnde_get_history stays calibrated, like sol.x_filt);
    (b) FixedDiffusion with z == 0 exactly: the reference returns one value where two are destructured and throws
-       (src/diffusions.jl:18-20) -- the trajectory ends with PNDE_RET_ZERO_RESIDUAL instead of sigma^2 = 0. */
+       (src/diffusions.jl:18-20) -- the trajectory ends there with PNDE_RET_ZERO_RESIDUAL instead of sigma^2 = 0.
+       The test is not in the ahead-of-time kernels (it costs 2-3 % there): a handle with this flag and the fixed
+       diffusion model gets its kernels compiled at create time through NVRTC (1-3 s). */
 
 #define PNDE_FLAG_ONE_THREAD 2 /* dense EK1 with d (q+1) >= 10 normally runs with two lanes of a warp per trajectory
    (wide_filter.cuh); this flag selects the one-thread-per-trajectory kernel instead (A/B measurements; the two

@@ -672,8 +672,11 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
       ret = RET_NONFINITE;  // OrdinaryDiffEq check_error!: unstable_check
       break;
     }
-#ifndef PNDE_NO_QUIRK_CHECK
-    if (diffusion == DIFF_FIXED && quad == 0.0 && (prm.flags & FLAG_REFERENCE_QUIRKS)) {
+#ifdef PNDE_QUIRK_CHECK
+    // PNDE_FLAG_REFERENCE_QUIRKS (b).  Compiled only into the kernels that pnde_create builds through NVRTC for handles
+    // that set the flag: in the ahead-of-time kernels this test cost 3.3 % on the headline configuration as a loop
+    // exit and 2 % as a sticky flag (A/B, round 2) -- the one-thread kernel sits on the register limit.
+    if (diffusion == DIFF_FIXED && quad == 0.0) {
       ret = RET_ZERO_RESIDUAL;  // the reference throws here (src/diffusions.jl:18-20)
       break;
     }

@@ -270,7 +270,9 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
       return PNDE_ERR_ARG;
     }
   } else {
-    ops = as_ieks ? nullptr : find_ops(cfg->vf_kind, cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV);
+    // PNDE_FLAG_REFERENCE_QUIRKS (b) lives only in run-time compiled kernels (filter_kernel.cuh): take that route
+    const bool quirk_rtc = (cfg->flags & PNDE_FLAG_REFERENCE_QUIRKS) && cfg->diffusion == PNDE_DIFF_FIXED;
+    ops = (as_ieks || quirk_rtc) ? nullptr : find_ops(cfg->vf_kind, cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV);
     if (!ops) {
       // orders 6 and 7 of the catalogue, and the IEKS flavour of every order, are not instantiated at build
       // time: compile them on demand (NVRTC)
@@ -319,7 +321,8 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
     }
     std::string rerr;
     ops = rtc_build(cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV, custom->d, custom->np, custom->f_body,
-                    custom->jac_body, rerr, as_ieks, cfg->adaptive ? 1 : 0);
+                    custom->jac_body, rerr, as_ieks, cfg->adaptive ? 1 : 0,
+                    (cfg->flags & PNDE_FLAG_REFERENCE_QUIRKS) && cfg->diffusion == PNDE_DIFF_FIXED);
     if (!ops) {
       g_create_error = rerr;
       return PNDE_ERR_ARG;

