@@ -346,6 +346,7 @@ struct WideEK1 {
 #pragma unroll
         for (int al = 0; al < DL; ++al) {
           const int ps = kk * DL + al;
+          if (kk == kc && al * G + G - 1 < ac) continue;  // this slot is in front of the pivot in every lane
           // j > c ?  (decided at compile time except inside the pivot's own block)
           const bool behind = (kk > kc) || (al > ac / G) || (al == ac / G && g > oc);
           const bool is_c = (kk == kc) && (al == ac / G) && (g == oc);
@@ -362,16 +363,21 @@ struct WideEK1 {
             pnz = same_dim;
             prj = sL(kk, kc);
           }
-          const double e0 = E[first][ps];
-          double w = pnz ? fma(v[first], e0, v0 * prj) : v[first] * e0;
+          // The pivot-row entry is selected to zero where the prior row has none: w then starts from v0 * 0 = 0 and
+          // fma(a, b, 0) == a * b, fma(-s, v0, 0) == -s * v0 -- bit for bit the two code paths of cov_filter_step,
+          // without evaluating both.  Likewise a lane that has no column behind the pivot in this slot applies the
+          // reflector with s = 0 (E is unchanged exactly): no divergent branch inside the sweep, so ptxas schedules
+          // the whole column step as one block and overlaps the next column's norm chain with these updates.
+          const bool never = (c < d) && (kk < 2);  // no prior-row entry in any lane (compile time)
+          const double prj_e = pnz ? prj : 0.0;
+          double w = never ? v[first] * E[first][ps] : fma(v[first], E[first][ps], v0 * prj_e);
 #pragma unroll
           for (int i = first + 1; i < D; ++i) w = fma(v[i], E[i][ps], w);
           const double sc = beta * w;
-          double rr = pnz ? fma(-sc, v0, prj) : -sc * v0;  // R[c][j]
-          if (behind) {
+          double rr = never ? -sc * v0 : fma(-sc, v0, prj_e);  // R[c][j]
+          const double sce = behind ? sc : 0.0;
 #pragma unroll
-            for (int i = first; i < D; ++i) E[i][ps] = fma(-sc, v[i], E[i][ps]);
-          }
+          for (int i = first; i < D; ++i) E[i][ps] = fma(-sce, v[i], E[i][ps]);
           rr = is_c ? -snrm : (behind ? rr : 0.0);
           // consume the finished entry of R
           if (c < d) {
