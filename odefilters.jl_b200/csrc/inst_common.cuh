@@ -74,9 +74,14 @@ cudaError_t launch_smooth_t(const ModelOps*, const SmoothParams& sp, cudaStream_
 template <class M>
 cudaError_t launch_sample_t(const ModelOps*, const SampleParams& sp, cudaStream_t s) {
   const int block = 128;
-  const long long total = (sp.traj_end - sp.traj_begin) * sp.n_samples;
-  if (total <= 0) return cudaSuccess;
-  sample_kernel<M><<<(unsigned)((total + block - 1) / block), block, 0, s>>>(sp);
+  const long long ntr = sp.traj_end - sp.traj_begin;
+  if (ntr <= 0 || sp.n_samples <= 0) return cudaSuccess;
+  if (sp.max_saved > 1) {
+    const long long prep = ntr * (sp.max_saved - 1);
+    sample_prep_kernel<M><<<(unsigned)((prep + block - 1) / block), block, 0, s>>>(sp);
+  }
+  const long long total = ntr * sp.n_samples;
+  sample_draw_kernel<M><<<(unsigned)((total + block - 1) / block), block, 0, s>>>(sp);
   return cudaGetLastError();
 }
 
@@ -106,6 +111,7 @@ const ModelOps* make_ops() {
                                M::REC,
                                SmoothModel<M>::SREC,
                                M::VF::np,
+                               SamplePrep<M>::LEN,
                                M::IS_EK1,
                                &launch_filter_t<M>,
                                &launch_convert_t<M>,
@@ -120,7 +126,7 @@ template <class VF, int Q>
 const ModelOps* make_ops_ek1() {
   using M = DenseEK1<VF, Q>;
   if constexpr (M::D >= 10 && VF::d % 2 == 0) {
-    static const ModelOps ops = {M::d, M::q, M::D, M::ND, M::REC, SmoothModel<M>::SREC, M::VF::np, true,
+    static const ModelOps ops = {M::d, M::q, M::D, M::ND, M::REC, SmoothModel<M>::SREC, M::VF::np, SamplePrep<M>::LEN, true,
                                  &launch_filter_wide_t<VF, Q>, &launch_convert_t<M>, &launch_smooth_t<M>,
                                  &launch_sample_t<M>, &launch_dense_t<M>, &launch_step_t<M>};
     return &ops;

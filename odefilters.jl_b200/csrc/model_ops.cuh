@@ -51,6 +51,7 @@ struct StepParams;
 // `self` lets run-time compiled models (rtc_model.cu) carry their CUfunction handles
 struct ModelOps {
   int d, q, D, nd, rec, srec, np;
+  int sample_len;  // doubles of sampler scratch per (trajectory, interval): SamplePrep<M>::LEN
   bool ek1;
   cudaError_t (*launch_filter)(const ModelOps* self, const FilterParams&, bool adaptive, cudaStream_t);
   cudaError_t (*launch_convert)(const ModelOps* self, const ConvertParams&, cudaStream_t);

@@ -107,7 +107,7 @@ struct pnde_handle {
   double filter_ms = 0.0, smooth_ms = 0.0;
   long long launches = 0;
   DevBuf u0, p, mean, cov, t_final, loglik, final_diff, retcode, naccept, nreject, nf, njacs, n_saved, hist, smooth,
-      sstatus, scratch_off, scratch_out, bigwork, prev_hist, prev_smooth, prev_n_saved, prev_final_diff;
+      sstatus, scratch_off, scratch_out, sample_scratch, bigwork, prev_hist, prev_smooth, prev_n_saved, prev_final_diff;
   std::string err;
   // multi-device handle (cfg.n_devices > 1): one single-device child per GPU, trajectories in contiguous shards
   // [kid_lo[k], kid_lo[k+1]); the parent owns no device memory.  SURVEY 8(e): no exchange step, results are written
@@ -476,7 +476,7 @@ int pnde_destroy(pnde_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->u0,      &h->p,      &h->mean,  &h->cov,     &h->t_final, &h->loglik,
                     &h->final_diff, &h->retcode, &h->naccept, &h->nreject, &h->nf,      &h->njacs,
-                    &h->n_saved, &h->hist,   &h->smooth, &h->sstatus, &h->scratch_off, &h->scratch_out,
+                    &h->n_saved, &h->hist,   &h->smooth, &h->sstatus, &h->scratch_off, &h->scratch_out, &h->sample_scratch,
                     &h->bigwork, &h->prev_hist, &h->prev_smooth, &h->prev_n_saved, &h->prev_final_diff};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; ++i)
@@ -1237,14 +1237,17 @@ int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint6
   cp.t = dt_;
   cp.nd_out = 1;
   CK(o->launch_convert(o, cp, h->stream), "convert kernel launch");
+  // the per-interval backward kernels (stage-1 sweep, once per trajectory and interval) live in a scratch block;
+  // large ranges are processed in chunks of trajectories so that the block stays below 2 GiB
+  int mxs = 0;
+  for (long long i = tb; i < te; ++i) mxs = std::max(mxs, ns[(size_t)i]);
+  const size_t per_traj = (size_t)std::max(mxs - 1, 1) * (size_t)o->sample_len * 8;
+  const long long chunk = std::max<long long>(1, std::min<long long>(ntr, (long long)(((size_t)2 << 30) / per_traj)));
+  CK(h->sample_scratch.ensure((size_t)chunk * per_traj), "alloc sampler scratch");
   SampleParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.n = h->n;
-  sp.traj_begin = tb;
-  sp.traj_end = te;
-  sp.max_saved = h->max_saved;
   sp.n_saved = h->n_saved.as<int>();
-  sp.offsets = h->scratch_off.as<long long>();
   sp.hist = h->hist.as<double>();
   sp.final_diff = h->final_diff.as<double>();
   sp.calibrate = (df == PNDE_DIFF_FIXED || df == PNDE_DIFF_FIXED_MAP || df == PNDE_DIFF_FIXED_MV);
@@ -1252,9 +1255,17 @@ int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint6
   sp.n_samples = n_samples;
   sp.seed = seed;
   sp.key_offset = h->global_lo;
-  sp.out = dout;
+  sp.scratch = h->sample_scratch.as<double>();
   sp.C = h->C;
-  CK(o->launch_sample(o, sp, h->stream), "sample kernel launch");
+  for (long long c0 = tb; c0 < te; c0 += chunk) {
+    sp.traj_begin = c0;
+    sp.traj_end = std::min<long long>(te, c0 + chunk);
+    sp.max_saved = std::max(mxs, 1);  // stride of the scratch: intervals per trajectory + 1
+    sp.offsets = h->scratch_off.as<long long>() + (c0 - tb);
+    sp.out = dout;
+    CK(o->launch_sample(o, sp, h->stream), "sample kernel launch");
+    h->launches += 2;
+  }
   if (t) CK(cudaMemcpyAsync(t, dt_, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
   if (samples) CK(cudaMemcpyAsync(samples, dout, nout * 8, cudaMemcpyDeviceToHost, h->stream), "D2H samples");
   CK(cudaStreamSynchronize(h->stream), "stream synchronize");

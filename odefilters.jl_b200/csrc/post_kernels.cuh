@@ -69,6 +69,7 @@ struct SampleParams {
   unsigned long long seed;
   long long key_offset;  // added to the trajectory index in the generator key (shards of a multi-device ensemble)
   double* out;  // [total][n_samples][D]
+  double* scratch;  // [traj_end - traj_begin][max_saved - 1][SamplePrep<M>::LEN]: the per-interval backward kernels
   IwpConsts C;
 };
 
@@ -100,17 +101,102 @@ struct PostTraits {
   }
 };
 
-// one thread per (trajectory, sample)
+// Backward sampling in two kernels ("reuse the smoother gain per interval instead of N n full
+// smooth calls"):
+//   sample_prep_kernel  one thread per (trajectory, interval): the stage-1 sweep of that interval, ONCE -- the
+//                       backward kernel x_i | x_{i+1} ~ N(m + G (x_{i+1} - m^-), Y'Y) does not depend on the sample.
+//                       Writes m = P m_i, m^- = A m, R-, 1/diag(R-), X (G' = R-^-1 X) and Y to a scratch record.
+//   sample_draw_kernel  one thread per (trajectory, sample): per interval a forward substitution with R-, two
+//                       matrix-vector products with X and Y and the normals: O(D^2) per draw instead of the O(D^3) sweep.
 template <class M>
-__global__ void __launch_bounds__(128) sample_kernel(const SampleParams sp) {
+struct SamplePrep {
   using PT = PostTraits<M>;
   using SC = typename PT::SC;
+  static constexpr int D = M::D, NF = PT::NF, DCOV = PT::DCOV, R = PT::R, NP = SC::NP;
+  static constexpr int FLEN = NP + DCOV + DCOV * DCOV + R * DCOV;  // R-, rinv, X, Y of one factor
+  static constexpr int LEN = 2 * D + NF * FLEN;                     // + m, m^-
+};
+
+template <class M>
+__global__ void __launch_bounds__(128) sample_prep_kernel(const SampleParams sp) {
+  using PT = PostTraits<M>;
+  using SC = typename PT::SC;
+  using SPp = SamplePrep<M>;
+  constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, NF = PT::NF, DC = PT::DC, DCOV = PT::DCOV, R = PT::R;
+  const long long ntr = sp.traj_end - sp.traj_begin;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= ntr * (sp.max_saved - 1)) return;
+  const long long tr = sp.traj_begin + gid % ntr;  // trajectory fastest: record loads coalesce
+  const int i = (int)(gid / ntr);                  // interval t[i] -> t[i+1]
+  const long long n = sp.n;
+  const int ns = sp.n_saved[tr];
+  if (i + 1 >= ns) return;
+  auto rec = [&](int slot) { return sp.hist + ((long long)slot * REC) * n + tr; };
+  double* o = sp.scratch + ((tr - sp.traj_begin) * (sp.max_saved - 1) + i) * SPp::LEN;
+  const double* ri = rec(i);
+  const double* rn = rec(i + 1);
+  const double h = rn[0] - ri[0];
+  if (!(h > 0.0)) return;  // the draw kernel copies the sample across such an interval
+  double gfin[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) gfin[k] = sp.calibrate ? sp.final_diff[(long long)k * n + tr] : 1.0;
+  double Pk[q + 1], PIk[q + 1];
+  precond_scales<q>(h, Pk, PIk);
+  typename M::State st;
+  M::load(st, ri + (long long)(1 + ND) * n, n);
+  M::scale(st, Pk);
+  double mpred[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) mpred[k] = st.m[k];
+  apply_A<d, q>(mpred);
+  for (int k = 0; k < D; ++k) {
+    o[k] = st.m[k];
+    o[D + k] = mpred[k];
+  }
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    // dynamic models: the interval's own diffusion; static models: the final global value.  In the Kronecker form a
+    // static per-dimension scale cancels in G and multiplies Y'Y (applied by the draw kernel).
+    double g;
+    if (sp.calibrate)
+      g = M::IS_EK1 ? gfin[0] : 1.0;
+    else
+      g = rn[(long long)(1 + (NF > 1 ? f : 0)) * n];
+    const double sig = sqrt(g);
+    double cols[R][DCOV];
+    SC::cols_from_factor(PT::factor(st, f), cols);
+    if (M::IS_EK1 && sp.calibrate) {
+      const double cs = sqrt(gfin[0]);
+#pragma unroll
+      for (int c = 0; c < R; ++c)
+#pragma unroll
+        for (int k = 0; k < DCOV; ++k) cols[c][k] *= cs;
+    }
+    double Rm[SC::NP], rinv[DCOV];
+    RegMat<DCOV> X;
+    SC::template stage1<R>(cols, sig, sp.C, Rm, rinv, X);  // cols now holds Y
+    double* of = o + 2 * D + f * SPp::FLEN;
+    for (int k = 0; k < SC::NP; ++k) of[k] = Rm[k];
+    for (int k = 0; k < DCOV; ++k) of[SC::NP + k] = rinv[k];
+    for (int r = 0; r < DCOV; ++r)
+      for (int k = 0; k < DCOV; ++k) of[SC::NP + DCOV + r * DCOV + k] = X.get(r, k);
+    for (int c = 0; c < R; ++c)
+      for (int k = 0; k < DCOV; ++k) of[SC::NP + DCOV + DCOV * DCOV + c * DCOV + k] = cols[c][k];
+  }
+}
+
+// one thread per (trajectory, sample)
+template <class M>
+__global__ void __launch_bounds__(128) sample_draw_kernel(const SampleParams sp) {
+  using PT = PostTraits<M>;
+  using SC = typename PT::SC;
+  using SPp = SamplePrep<M>;
   constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, NF = PT::NF, DC = PT::DC, DCOV = PT::DCOV,
                 R = PT::R;
   const long long ntr = sp.traj_end - sp.traj_begin;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= ntr * sp.n_samples) return;
-  const int smp = (int)(gid % sp.n_samples);  // samples of one trajectory are adjacent: shared history loads hit L1
+  const int smp = (int)(gid % sp.n_samples);  // samples of one trajectory are adjacent: the scratch loads broadcast
   const long long tr = sp.traj_begin + gid / sp.n_samples;
   const long long n = sp.n;
   const int ns = sp.n_saved[tr];
@@ -123,8 +209,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams sp) {
   for (int i = 0; i < ND; ++i) gfin[i] = sp.calibrate ? sp.final_diff[(long long)i * n + tr] : 1.0;
   auto rec = [&](int slot) { return sp.hist + ((long long)slot * REC) * n + tr; };
   auto outp = [&](int slot) { return sp.out + ((sp.offsets[tr - sp.traj_begin] + slot) * sp.n_samples + smp) * D; };
-  // factor scale that calibrates a filtered covariance (static diffusion models)
-  auto calib = [&](int f, int rep) -> double {
+  auto calib = [&](int rep) -> double {  // factor scale that calibrates a filtered covariance (static models)
     if (!sp.calibrate) return 1.0;
     if (M::IS_EK1) return sqrt(gfin[0]);
     return sqrt(sp.is_mv ? gfin[rep < ND ? rep : 0] : gfin[0]);
@@ -141,7 +226,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams sp) {
       const int f = (NF > 1) ? rep : 0;
       double cols[R][DCOV];
       SC::cols_from_factor(PT::factor(st, f), cols);
-      const double cs = calib(f, rep);
+      const double cs = calib(rep);
 #pragma unroll
       for (int c = 0; c < R; c += 2) {
         double a, b;
@@ -157,65 +242,50 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams sp) {
 #pragma unroll
     for (int i = 0; i < D; ++i) o[i] = s[i];
   }
-  int status = 0;
   for (int i = ns - 2; i >= 0; --i) {
-    const double* ri = rec(i);
-    const double* rn = rec(i + 1);
-    const double h = rn[0] - ri[0];
+    const double h = rec(i + 1)[0] - rec(i)[0];
     if (h > 0.0) {
+      const double* pr = sp.scratch + ((tr - sp.traj_begin) * (sp.max_saved - 1) + i) * SPp::LEN;
       double Pk[q + 1], PIk[q + 1];
       precond_scales<q>(h, Pk, PIk);
-      typename M::State st;
-      M::load(st, ri + (long long)(1 + ND) * n, n);
-      M::scale(st, Pk);
-      double mpred[D];
-#pragma unroll
-      for (int k = 0; k < D; ++k) mpred[k] = st.m[k];
-      apply_A<d, q>(mpred);
       double snew[D];
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
-        // dynamic models: the interval's own diffusion; static models: the final global value.  In the
-        // Kronecker form a static per-dimension scale cancels in G and multiplies Y'Y.
-        double g;
-        if (sp.calibrate)
-          g = M::IS_EK1 ? gfin[0] : 1.0;
-        else
-          g = rn[(long long)(1 + (NF > 1 ? f : 0)) * n];
-        const double sig = sqrt(g);
-        double cols[R][DCOV];
-        SC::cols_from_factor(PT::factor(st, f), cols);
-        if (M::IS_EK1 && sp.calibrate) {
-          const double cs = sqrt(gfin[0]);
-#pragma unroll
-          for (int c = 0; c < R; ++c)
-#pragma unroll
-            for (int k = 0; k < DCOV; ++k) cols[c][k] *= cs;
-        }
-        double Rm[SC::NP], rinv[DCOV];
-        RegMat<DCOV> X;
-        SC::template stage1<R>(cols, sig, sp.C, Rm, rinv, X);  // cols now holds Y
-        constexpr int NR_ = (NF > 1) ? 1 : PT::NREP;           // replicas served by this factor
+        const double* pf = pr + 2 * D + f * SPp::FLEN;
+        const double* Rm = pf;
+        const double* rinv = pf + SC::NP;
+        const double* X = rinv + DCOV;
+        const double* Y = X + DCOV * DCOV;
+        constexpr int NR_ = (NF > 1) ? 1 : PT::NREP;  // replicas served by this factor
 #pragma unroll
         for (int rr = 0; rr < NR_; ++rr) {
           const int rep = (NF > 1) ? f : rr;
-          double delta[1][DCOV];
+          // y = R-^-T (P s - m^-), delta = X' y  (the gain applied without ever forming it)
+          double y[DCOV];
 #pragma unroll
-          for (int k = 0; k < DCOV; ++k)
-            delta[0][k] = fma(Pk[k / DC], s[PT::idx(rep, k)], -mpred[PT::idx(rep, k)]);
-          SC::template apply_gain<1>(Rm, rinv, X, delta);
-          const double ys = (!M::IS_EK1 && sp.calibrate) ? calib(f, rep) : 1.0;
+          for (int k = 0; k < DCOV; ++k) {
+            double acc = fma(Pk[k / DC], s[PT::idx(rep, k)], -pr[D + PT::idx(rep, k)]);
+#pragma unroll
+            for (int l = 0; l < k; ++l) acc = fma(-Rm[SC::tri(k, l)], y[l], acc);
+            y[k] = acc * rinv[k];
+          }
+          const double ys = (!M::IS_EK1 && sp.calibrate) ? calib(rep) : 1.0;
           double acc[DCOV];
 #pragma unroll
-          for (int k = 0; k < DCOV; ++k) acc[k] = st.m[PT::idx(rep, k)] + delta[0][k];
+          for (int k = 0; k < DCOV; ++k) {
+            double dl = 0.0;
+#pragma unroll
+            for (int l = 0; l < DCOV; ++l) dl = fma(X[l * DCOV + k], y[l], dl);
+            acc[k] = pr[PT::idx(rep, k)] + dl;
+          }
 #pragma unroll
           for (int c = 0; c < R; c += 2) {
             double a, b;
             rng.normal2((uint32_t)(tr + sp.key_offset), (uint32_t)smp, (uint32_t)i, (uint32_t)(rep * 64 + c), a, b);
 #pragma unroll
             for (int k = 0; k < DCOV; ++k) {
-              acc[k] = fma(ys * cols[c][k], a, acc[k]);
-              if (c + 1 < R) acc[k] = fma(ys * cols[c + 1 < R ? c + 1 : 0][k], b, acc[k]);
+              acc[k] = fma(ys * Y[c * DCOV + k], a, acc[k]);
+              if (c + 1 < R) acc[k] = fma(ys * Y[(c + 1 < R ? c + 1 : 0) * DCOV + k], b, acc[k]);
             }
           }
 #pragma unroll
@@ -229,7 +299,6 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams sp) {
 #pragma unroll
     for (int k = 0; k < D; ++k) o[k] = s[k];
   }
-  (void)status;
 }
 
 // Posterior N(mean, cov) of trajectory `tr` at time `tval` (src/solution.jl:165-215): the stored state on an exact

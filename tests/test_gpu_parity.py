@@ -343,9 +343,33 @@ def test_sampling_statistics(kind, q):
     assert smp.shape == (len(sol), 2, 10)
     outliers = np.sum(np.abs(smp - sol.u[:, :, None]) > 3 * std[:, :2, None])
     assert outliers < 0.05 * smp.size                                  # test/solution.jl:70-72
-    # cross-time structure: lag-1 sample covariance of u matches G-propagated smoothing covariance sign
-    c = np.mean((S[-2, 0] - m_emp[-2, 0]) * (S[-1, 0] - m_emp[-1, 0]))
-    assert c > 0
+    # against the ORACLE (not the GPU's own smoother): moments of the draws vs the oracle's smoothing posterior, and
+    # the cross-time law: Cov(x_i, x_{i+1}) = G_i Sigma^s_{i+1} with the smoother gain G_i = Sigma_i A' (Sigma^-)^-1
+    # (src/smoothing.jl:42-46) evaluated in numpy from the oracle's filtered states
+    so = oracle_solve("lotka_volterra", O.Alg(kind, q, "dynamic", True), tspan=(0.0, 3.0), abstol=1e-3, reltol=1e-2)
+    assert len(so.t) == len(sol)
+    mo = np.array([g.mu for g in so.x_smooth])
+    co = np.array([g.Sigma.mat for g in so.x_smooth])
+    sdo = np.sqrt(np.maximum(np.diagonal(co, axis1=1, axis2=2), 0))
+    n2 = 20000
+    S2 = sol.sample_states(n2, seed=11)
+    ok = sdo > 1e-12 * np.abs(mo).max()
+    assert np.all(np.abs(S2.mean(axis=2) - mo)[ok] < 6 * sdo[ok] / np.sqrt(n2))
+    assert np.all(np.abs(S2.std(axis=2)[ok] / sdo[ok] - 1) < 6 / np.sqrt(2 * n2))
+    worst = 0.0
+    for i in (1, len(so.t) // 2, len(so.t) - 2):
+        hstep = so.t[i + 1] - so.t[i]
+        A, Qh = O.vanilla_ibm(2, q, hstep, float(np.atleast_1d(so.diffusions[i])[0]))
+        Sf = so.x_filt[i].Sigma.mat
+        G = Sf @ A.T @ np.linalg.pinv(A @ Sf @ A.T + Qh, rcond=1e-14, hermitian=True)
+        C_exact = (G @ co[i + 1])[:2, :2]                       # Cov(u_i, u_{i+1})
+        a = S2[i, :2, :] - S2[i, :2, :].mean(axis=1, keepdims=True)
+        b = S2[i + 1, :2, :] - S2[i + 1, :2, :].mean(axis=1, keepdims=True)
+        C_emp = a @ b.T / (n2 - 1)
+        scale = np.sqrt(np.outer(np.diag(co[i])[:2], np.diag(co[i + 1])[:2]))
+        worst = max(worst, float(np.max(np.abs(C_emp - C_exact) / scale)))
+    report("sampling_lag1", alg=kind, q=q, n=n2, worst_scaled_error=worst, sampling_sd=1 / np.sqrt(n2))
+    assert worst < 6 / np.sqrt(n2)  # sampling error of a correlation coefficient ~ 1 / sqrt(n)
 
 
 # ---- BASELINE config 4: Lorenz-96, EK0 with the Kronecker-factored covariance -------------------
