@@ -5,6 +5,7 @@
 #include "post_kernels.cuh"
 #include "smoother_kernel.cuh"
 #include "wide_filter.cuh"
+#include "wide_smoother.cuh"
 #include "step_kernel.cuh"
 
 namespace pnde {
@@ -71,6 +72,20 @@ cudaError_t launch_smooth_t(const ModelOps*, const SmoothParams& sp, cudaStream_
   return cudaGetLastError();
 }
 
+// Dense EK1 at D >= 10: four lanes per trajectory (wide_smoother.cuh) unless PNDE_FLAG_ONE_THREAD
+template <class VF, int Q>
+cudaError_t launch_smooth_wide_t(const ModelOps* self, const SmoothParams& sp, cudaStream_t s) {
+  using W = WideSmooth<VF, Q>;
+  if (sp.flags & FLAG_ONE_THREAD) return launch_smooth_t<DenseEK1<VF, Q>>(self, sp, s);
+  const int block = W::ST;
+  const size_t smem = (size_t)W::SM_LEN * block * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(wide_smoother_kernel<VF, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long grid = (sp.n * W::G + block - 1) / block;
+  wide_smoother_kernel<VF, Q><<<(unsigned)grid, block, smem, s>>>(sp);
+  return cudaGetLastError();
+}
+
 template <class M>
 cudaError_t launch_sample_t(const ModelOps*, const SampleParams& sp, cudaStream_t s) {
   const int block = 128;
@@ -127,7 +142,7 @@ const ModelOps* make_ops_ek1() {
   using M = DenseEK1<VF, Q>;
   if constexpr (M::D >= 10 && VF::d % 2 == 0) {
     static const ModelOps ops = {M::d, M::q, M::D, M::ND, M::REC, SmoothModel<M>::SREC, M::VF::np, SamplePrep<M>::LEN, true,
-                                 &launch_filter_wide_t<VF, Q>, &launch_convert_t<M>, &launch_smooth_t<M>,
+                                 &launch_filter_wide_t<VF, Q>, &launch_convert_t<M>, &launch_smooth_wide_t<VF, Q>,
                                  &launch_sample_t<M>, &launch_dense_t<M>, &launch_step_t<M>};
     return &ops;
   } else {

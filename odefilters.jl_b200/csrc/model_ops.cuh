@@ -40,6 +40,7 @@ struct SmoothParams {
   int calibrate;
   int is_mv;
   int* status;               // [n] non-zero: non-finite / negative-variance flag (src/smoothing.jl:25,59)
+  int flags;                 // FLAG_ONE_THREAD: the one-thread kernel also where the lane-group smoother exists
   IwpConsts C;
 };
 

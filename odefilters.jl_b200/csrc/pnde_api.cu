@@ -801,6 +801,7 @@ int pnde_smooth(pnde_handle* h) {
   sp.calibrate = (df == PNDE_DIFF_FIXED || df == PNDE_DIFF_FIXED_MAP || df == PNDE_DIFF_FIXED_MV);
   sp.is_mv = (df == PNDE_DIFF_DYNAMIC_MV || df == PNDE_DIFF_FIXED_MV);
   sp.status = h->sstatus.as<int>();
+  sp.flags = h->cfg.flags;
   sp.C = h->C;
   CK(cudaEventRecord(h->ev[2], h->stream), "event record");
   CK(o->launch_smooth(o, sp, h->stream), "smoother kernel launch");

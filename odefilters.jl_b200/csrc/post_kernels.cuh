@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(128) sample_prep_kernel(const SampleParams sp)
   using PT = PostTraits<M>;
   using SC = typename PT::SC;
   using SPp = SamplePrep<M>;
-  constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, NF = PT::NF, DC = PT::DC, DCOV = PT::DCOV, R = PT::R;
+  constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, NF = PT::NF, DCOV = PT::DCOV, R = PT::R;
   const long long ntr = sp.traj_end - sp.traj_begin;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= ntr * (sp.max_saved - 1)) return;
@@ -191,8 +191,7 @@ __global__ void __launch_bounds__(128) sample_draw_kernel(const SampleParams sp)
   using PT = PostTraits<M>;
   using SC = typename PT::SC;
   using SPp = SamplePrep<M>;
-  constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, NF = PT::NF, DC = PT::DC, DCOV = PT::DCOV,
-                R = PT::R;
+  constexpr int q = M::q, D = M::D, ND = M::ND, REC = M::REC, NF = PT::NF, DC = PT::DC, DCOV = PT::DCOV, R = PT::R;
   const long long ntr = sp.traj_end - sp.traj_begin;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= ntr * sp.n_samples) return;

@@ -1235,3 +1235,40 @@ def test_square_root_factors_cross_the_abi():
         g = sol.x_filt[len(sol) // 2]
         assert g.Sigma.squareroot.shape == (sol.x_filt.mu.shape[1],) * 2
         assert np.linalg.matrix_rank(g.Sigma.squareroot) <= g.Sigma.squareroot.shape[0] - 2  # R = 0: rank D - d
+
+
+@pytest.mark.parametrize("name,q,adaptive", [("lotka_volterra", 5, False), ("fhn_readme", 4, False), ("lotka_volterra", 4, True),
+                                             ("vanderpol", 5, True)])
+def test_lane_group_smoother_equals_one_thread_smoother(name, q, adaptive):
+    """Dense EK1 at D >= 10: the RTS pass runs with four lanes per trajectory (wide_smoother.cuh).  Same operations
+    in the same order as the one-thread smoother: fed with the SAME filtered history, the smoothed means and factors
+    must be identical."""
+    import odefilters_b200 as B
+    from ensembles import config2_inputs, config3_inputs, config5_inputs
+
+    n = 777
+    make = {"vanderpol": config3_inputs, "lotka_volterra": config5_inputs, "fhn_readme": config2_inputs}[name]
+    u0, p = make(n)
+    prob = B.ODEProblem(name, u0[0], (0.0, 1.0), p[0])
+    kw = dict(max_saved=600) if adaptive else dict(adaptive=False, dt=0.01)
+    out = {}
+    for one in (True, False):
+        s = B.FilterSolver(prob, B.EK1(order=q, smooth=True), one_thread=one, **kw)
+        s.upload(u0, p)
+        s.run()       # the filter: one-thread in one handle, lane groups in the other ...
+        s.smooth()
+        out[one] = (s.history(0, 0, n), s.history(1, 0, n), s.history_sqrt(1, 0, n)[1], s.counts())
+        s.close()
+    (f1, s1, q1, c1), (f2, s2, q2, c2) = out[True], out[False]
+    assert np.array_equal(c1["n_saved"], c2["n_saved"]) and (c2["retcode"] == 0).all()
+    same_filter = all(np.array_equal(x, y) for x, y in zip(f1, f2))
+    dmean = rel(s2[2][:, :2], s1[2][:, :2])
+    dfac = float(np.max(np.abs(q1 - q2)) / np.max(np.abs(q1)))
+    bitwise = all(np.array_equal(x, y) for x, y in zip(s1, s2)) and np.array_equal(q1, q2)
+    report("lane_group_smoother", name=name, q=q, adaptive=adaptive, same_filter_history=same_filter, bitwise=bitwise,
+           smoothed_u_rel=dmean, factor_rel=dfac)
+    print(name, q, adaptive, "same filter history", same_filter, "bitwise", bitwise, dmean, dfac)
+    if same_filter:
+        assert bitwise  # identical input history => identical smoothed output
+    else:
+        assert dmean < 1e-9  # fixed steps: the two filter kernels differ in the last bit (see the filter test)
