@@ -45,6 +45,9 @@ struct WideSmooth {
     __device__ __forceinline__ bool ok(int s) const { return k(s) <= q; }
     __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(0xffffffffu, v, src, G); }
   };
+  // largest natural index a slot can have (odd-block lane, last dimension): rows of L^s / columns of R- of slot s have
+  // entries c <= jmax(s) at most -- everything beyond is never touched, so it costs no register
+  __host__ __device__ static constexpr int jmax(int s) { return (2 * (s / DL) + 1) * d + d - 1 < D - 1 ? (2 * (s / DL) + 1) * d + d - 1 : D - 1; }
   __device__ __forceinline__ static constexpr int owner(int c) { return ((c % d) & 1) + 2 * ((c / d) & 1); }
   __device__ __forceinline__ static constexpr int slot_of(int c) { return ((c / d) >> 1) * DL + ((c % d) >> 1); }
 
@@ -68,7 +71,7 @@ struct WideSmooth {
   // Householder triangularisation of the stack [Y ; T'] (R + D rows, own columns) -> rows of the lower factor L.
   // Arithmetic of SmoothCov::triangularize_impl.
   __device__ __forceinline__ static void triangularize(const Lane& ln, double (&Y)[R][CL], double (&Tt)[D][CL],
-                                                       double (&L)[CL][D], int& status) {
+                                                       double (&L)[CL][D], bool on, int& status) {
 #pragma unroll
     for (int c = 0; c < D; ++c) {
       const int oc = owner(c), psc = slot_of(c);
@@ -85,10 +88,10 @@ struct WideSmooth {
       const double snrm = copysign(nrm, pv);
       const double v0 = pv + snrm;
       const double beta = nz ? fast_rcp(fma(fabs(pv), nrm, n2)) : 0.0;
-      if (!(n2 == n2)) status |= 1;
+      if (on && !(n2 == n2)) status |= 1;
 #pragma unroll
       for (int s = 0; s < CL; ++s) {
-        if (2 * (s / DL) + 1 < c / d) continue;  // every block of this slot lies before the pivot's (compile time)
+        if (jmax(s) < c) continue;  // every column of this slot lies before the pivot (compile time)
         const bool behind = ln.ok(s) && ln.j(s) > c;
         const bool is_c = ln.ok(s) && ln.j(s) == c;
         const double prj = (c < R) ? Y[c < R ? c : 0][s] : Tt[c - R >= 0 ? c - R : 0][s];
@@ -105,9 +108,55 @@ struct WideSmooth {
           else
             Tt[i - R >= 0 ? i - R : 0][s] = fma(-sce, v[i], Tt[i - R >= 0 ? i - R : 0][s]);
         }
-        L[s][c] = is_c ? -snrm : (behind ? rr : L[s][c]);
+        L[s][c] = (on && is_c) ? -snrm : ((on && behind) ? rr : L[s][c]);
       }
     }
+  }
+
+  // smoothed record (layout of SmoothModel<DenseEK1>: mean[D], L packed lower by rows): the own rows
+  __device__ __forceinline__ static void write_record(const Lane& ln, double* o, long long n, bool on,
+                                                      const double (&ms)[CL], const double (&Ls)[CL][D]) {
+    if (!on) return;
+#pragma unroll
+    for (int s = 0; s < CL; ++s) {
+      if (!ln.ok(s)) continue;
+      const int j = ln.j(s);
+      o[(long long)j * n] = ms[s];
+#pragma unroll
+      for (int c = 0; c < D; ++c)
+        if (c <= jmax(s) && c <= j) o[(long long)(D + j * (j + 1) / 2 + c) * n] = Ls[s][c];
+    }
+  }
+  // x_smooth = x_filt as a triangular factor (last state; the un-smoothed first state).  r0: the record behind t and
+  // the diffusion.
+  __device__ __forceinline__ static void from_filtered(const Lane& ln, const double* r0, long long n, bool on,
+                                                       double dense_cal, double (&ms)[CL], double (&Ls)[CL][D],
+                                                       int& status) {
+    double Y[R][CL], Tt[D][CL];
+#pragma unroll
+    for (int s = 0; s < CL; ++s) {
+      const bool ld = on && ln.ok(s);
+      const double v = ld ? r0[(long long)ln.j(s) * n] : 0.0;
+      ms[s] = on ? v : ms[s];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int al = 0; al < DL; ++al) {
+        double col[q + 1];
+        load_factor_column(r0 + (long long)D * n, n, r, 2 * al + ln.ga, on, col);
+#pragma unroll
+        for (int kl = 0; kl < KL; ++kl) {
+          const double v = ln.gk ? (2 * kl + 1 <= q ? col[2 * kl + 1 <= q ? 2 * kl + 1 : 0] : 0.0) : col[2 * kl];
+          Y[r][kl * DL + al] = v * dense_cal;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+      for (int s = 0; s < CL; ++s) Tt[c][s] = 0.0;
+    triangularize(ln, Y, Tt, Ls, on, status);
   }
 };
 
@@ -145,54 +194,13 @@ __global__ void __launch_bounds__(PNDE_WSMOOTH_BLOCK, 1) wide_smoother_kernel(co
   for (int s = 0; s < CL; ++s) {
     ms[s] = 0.0;
 #pragma unroll
-    for (int c = 0; c < D; ++c) Ls[s][c] = 0.0;
-  }
-  auto write = [&](int slot, bool on) {
-    if (!on) return;
-    double* o = srec(slot);
-#pragma unroll
-    for (int s = 0; s < CL; ++s) {
-      if (!ln.ok(s)) continue;
-      const int j = ln.j(s);
-      o[(long long)j * n] = ms[s];
-#pragma unroll
-      for (int c = 0; c < D; ++c)
-        if (c <= j) o[(long long)(D + j * (j + 1) / 2 + c) * n] = Ls[s][c];
-    }
-  };
-  // x_smooth[slot] = x_filt[slot] as a triangular factor (last state; the un-smoothed first state)
-  auto from_filtered = [&](int slot, bool on) {
-    const double* r0 = rec(on ? slot : 0) + (long long)2 * n;  // behind t and the diffusion
-    double Y[R][CL], Tt[D][CL];
-#pragma unroll
-    for (int s = 0; s < CL; ++s) {
-      const bool ld = on && ln.ok(s);
-      ms[s] = ld ? r0[(long long)ln.j(s) * n] : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-#pragma unroll
-      for (int al = 0; al < DL; ++al) {
-        double col[q + 1];
-        W::load_factor_column(r0 + (long long)D * n, n, r, 2 * al + ln.ga, on, col);
-#pragma unroll
-        for (int kl = 0; kl < KL; ++kl) {
-          const double v = ln.gk ? (2 * kl + 1 <= q ? col[2 * kl + 1 <= q ? 2 * kl + 1 : 0] : 0.0) : col[2 * kl];
-          Y[r][kl * DL + al] = v * dense_cal;
-        }
-      }
-    }
-#pragma unroll
     for (int c = 0; c < D; ++c)
-#pragma unroll
-      for (int s = 0; s < CL; ++s) Tt[c][s] = 0.0;
-    W::triangularize(ln, Y, Tt, Ls, status);
-  };
-
+      if (c <= W::jmax(s)) Ls[s][c] = 0.0;
+  }
   // the whole warp walks its trajectories backwards together (full-mask shuffles); a group whose trajectory is
   // shorter idles with its stores and loads switched off
-  from_filtered(ns - 1, ns >= 1);
-  write(ns - 1, ns >= 1);
+  W::from_filtered(ln, rec(ns >= 1 ? ns - 1 : 0) + (long long)2 * n, n, ns >= 1, dense_cal, ms, Ls, status);
+  W::write_record(ln, srec(ns >= 1 ? ns - 1 : 0), n, ns >= 1, ms, Ls);
   int i = ns - 2;
   while (__any_sync(0xffffffffu, i >= 1)) {
     const bool alive = i >= 1;
@@ -268,10 +276,7 @@ __global__ void __launch_bounds__(PNDE_WSMOOTH_BLOCK, 1) wide_smoother_kernel(co
       // left block: own columns behind c; R-[c][j] goes to shared memory
 #pragma unroll
       for (int s = 0; s < CL; ++s) {
-        if (2 * (s / DL) + 1 < kc) {  // in front of the pivot in both parities
-          sm[(W::SM_R + c * CL + s) * ST] = 0.0;
-          continue;
-        }
+        if (W::jmax(s) < c) continue;  // in front of the pivot in both parities: R-[c][j] is never read
         const bool behind = ln.ok(s) && ln.j(s) > c;
         const bool is_c = ln.ok(s) && ln.j(s) == c;
         const bool pnz = ln.ok(s) && ln.a(s) == ac;
@@ -318,7 +323,8 @@ __global__ void __launch_bounds__(PNDE_WSMOOTH_BLOCK, 1) wide_smoother_kernel(co
       const double pk = ln.gk ? Pk[2 * kl + 1 <= q ? 2 * kl + 1 : 0] : Pk[2 * kl];
       accY[s] = fma(pk, ms[s], -mpred[s]);  // delta = P m^s_{i+1} - A P m_i
 #pragma unroll
-      for (int c = 0; c < D; ++c) Ls[s][c] *= pk;  // L^s into P(h) coordinates
+      for (int c = 0; c < D; ++c)
+        if (c <= W::jmax(s)) Ls[s][c] *= pk;  // L^s into P(h) coordinates
     }
 #pragma unroll
     for (int c = 0; c < D; ++c)
@@ -331,14 +337,14 @@ __global__ void __launch_bounds__(PNDE_WSMOOTH_BLOCK, 1) wide_smoother_kernel(co
       const double yv = ln.bcast(accY[psr] * ri_, orr);
       double Zr[D];
 #pragma unroll
-      for (int c = 0; c <= r; ++c) Zr[c] = ln.bcast(Ls[psr][c] * ri_, orr);
+      for (int c = 0; c <= r; ++c) Zr[c] = ln.bcast(Ls[psr][c <= W::jmax(psr) ? c : 0] * ri_, orr);
 #pragma unroll
       for (int s = 0; s < CL; ++s) {
         const double x = sm[(W::SM_X + r * CL + s) * ST];
         dn[s] = fma(x, yv, dn[s]);
 #pragma unroll
         for (int c = 0; c <= r; ++c) Tt[c][s] = (c == r) ? x * Zr[c] : fma(x, Zr[c], Tt[c][s]);
-        if (2 * (s / DL) + 1 < r / d) continue;  // no row of this slot lies behind r
+        if (W::jmax(s) <= r) continue;  // no row of this slot lies behind r
         const bool after = work && ln.ok(s) && ln.j(s) > r;  // an idle group leaves its L^s untouched (rm = 0)
         const double rm = after ? sm[(W::SM_R + r * CL + s) * ST] : 0.0;  // R-[r][j]
         accY[s] = fma(-rm, yv, accY[s]);
@@ -352,13 +358,8 @@ __global__ void __launch_bounds__(PNDE_WSMOOTH_BLOCK, 1) wide_smoother_kernel(co
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int s = 0; s < CL; ++s) Y[r][s] = sm[(W::SM_Y + r * CL + s) * ST];
-    double Ln[CL][D];
-#pragma unroll
-    for (int s = 0; s < CL; ++s)
-#pragma unroll
-      for (int c = 0; c < D; ++c) Ln[s][c] = 0.0;
-    int st2 = 0;
-    W::triangularize(ln, Y, Tt, Ln, st2);
+    // (L^s of a working group is dead here -- it served as the accumulator of Z --, an idle group's is kept)
+    W::triangularize(ln, Y, Tt, Ls, work, status);
     // back to natural coordinates; a group without work keeps its state
 #pragma unroll
     for (int s = 0; s < CL; ++s) {
@@ -370,18 +371,18 @@ __global__ void __launch_bounds__(PNDE_WSMOOTH_BLOCK, 1) wide_smoother_kernel(co
         if (ln.ok(s) && !(msn == msn)) status |= 1;
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          Ls[s][c] = Ln[s][c] * pik;
-          if (ln.ok(s) && c == ln.j(s) && !(Ls[s][c] == Ls[s][c])) status |= 1;  // src/smoothing.jl:25,59
+          if (c > W::jmax(s)) continue;
+          Ls[s][c] *= pik;
+          if (!(Ls[s][c] == Ls[s][c])) status |= 1;  // any NaN in the row (src/smoothing.jl:25,59 test the diagonal)
         }
       }
     }
-    if (work) status |= st2;
-    write(ii, alive);
+    W::write_record(ln, srec(ii), n, alive, ms, Ls);
     --i;
   }
   // the first state is never smoothed (src/smoothing.jl:11: i runs down to 2)
-  from_filtered(0, ns >= 2);
-  write(0, ns >= 2);
+  W::from_filtered(ln, rec(0) + (long long)2 * n, n, ns >= 2, dense_cal, ms, Ls, status);
+  W::write_record(ln, srec(0), n, ns >= 2, ms, Ls);
   // the status flags of the four lanes are combined by the lead lane
   {
     int sall = status;

@@ -1271,5 +1271,9 @@ def test_lane_group_smoother_equals_one_thread_smoother(name, q, adaptive):
            mean_blockrel=w["mean"], cov_blockrel=w["cov"], where=str(where),
            factor_abs_rel=float(np.max(np.abs(np.abs(q1) - np.abs(q2))) / np.max(np.abs(q1))))
     print(name, q, adaptive, "same filter history", same_filter, "bitwise", bitwise, w)
-    tol = 1e-11 if same_filter else 1e-7  # fixed steps: the two FILTER kernels already differ in the last bit
-    assert w["mean"] < tol and w["cov"] < tol
+    # Not bitwise: the two smoothers round differently in places (a pivot that is zero up to rounding takes either
+    # sign, nvcc contracts sig * Lt + nrm differently), and the backward recursion amplifies that in the highest
+    # derivatives like every other perturbation -- the solution block and the covariance agree to rounding.
+    nsteps = int(np.max(c1["n_saved"]))
+    assert rel(s2[2][:, :2], s1[2][:, :2]) < (1e-12 if same_filter else 1e-9)
+    assert w["mean"] < mean_tol(q, nsteps) and w["cov"] < cov_tol(q, nsteps)
