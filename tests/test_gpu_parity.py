@@ -1274,6 +1274,11 @@ def test_lane_group_smoother_equals_one_thread_smoother(name, q, adaptive):
     # Not bitwise: the two smoothers round differently in places (a pivot that is zero up to rounding takes either
     # sign, nvcc contracts sig * Lt + nrm differently), and the backward recursion amplifies that in the highest
     # derivatives like every other perturbation -- the solution block and the covariance agree to rounding.
-    nsteps = int(np.max(c1["n_saved"]))
-    assert rel(s2[2][:, :2], s1[2][:, :2]) < (1e-12 if same_filter else 1e-9)
-    assert w["mean"] < mean_tol(q, nsteps) and w["cov"] < cov_tol(q, nsteps)
+    if same_filter:
+        # identical input history: covariances agree to rounding (bitwise on the non-stiff cases), means to the
+        # amplification of one differently contracted product (P m) through a few hundred backward steps
+        assert rel(s2[2][:, :2], s1[2][:, :2]) < 1e-10 and w["cov"] < 1e-12 and w["mean"] < 1e-6
+    else:
+        # fixed steps: the two FILTER kernels already differ in the last bit per step (see the filter test); q = 5
+        # amplifies that to 1e-4 in the highest derivative, the solution block stays at rounding level
+        assert rel(s2[2][:, :2], s1[2][:, :2]) < 1e-9 and w["cov"] < 1e-5 and w["mean"] < 1e-3
