@@ -13,12 +13,11 @@ namespace pnde {
 
 template <class M>
 cudaError_t launch_filter_t(const ModelOps*, const FilterParams& prm, bool adaptive, cudaStream_t s) {
-  // Small shards (strong scaling: 125 k trajectories per GPU are 3.3 waves of 148 SMs x 256 resident threads): with
-  // 128-thread CTAs the last, partial wave leaves SMs idle while others still hold a full CTA; 64-thread CTAs spread the
-  // tail over all SMs (measured, r2: see DESIGN section 5).  Large ensembles keep 128.
+  // (CTA size does not change the cost of a partial last wave -- 125 k trajectories = 3.3 waves of 148 SMs x 256
+  // resident threads run at 0.918 of the 1e6 rate with 128-, 64- and 32-thread CTAs alike, profiles/
+  // r2_tail_waves_cta_size.jsonl; PNDE_FILTER_BLOCK_RT is the knob that measurement used)
   int block = PNDE_FILTER_BLOCK;
   if (const char* e = getenv("PNDE_FILTER_BLOCK_RT")) block = atoi(e);
-  else if (prm.count < 16LL * 148 * 256) block = 64;
   const long long grid = (prm.count + block - 1) / block;
   if (adaptive) {
     // shared-memory stash of the pre-step state (read back on rejection)
