@@ -145,7 +145,7 @@ int pnde_default_config(pnde_config* cfg, int32_t alg, int32_t order, int32_t vf
 /* alg_cache (src/caches.jl:42-114): validates the configuration, builds the IWP constants
  * (src/priors.jl:7-59), binds the device. */
 int pnde_create(const pnde_config* cfg, pnde_handle** out);
-/* Any autonomous user ODE (d <= 8): the vector field and its Jacobian are given as CUDA C++ statement lists and
+/* Any autonomous user ODE (d <= 8 for EK1, d <= 16 for EK0): the vector field and its Jacobian are given as CUDA C++ statement lists and
  * compiled at run time (NVRTC) into the same kernels as the catalogue.  f_body assigns du[i] from u[] and p[]
  * and must be generic in the scalar type T (it is also evaluated on truncated Taylor series for the exact
  * initial state, src/state_initialization.jl:15-42): + - * / exp log sin cos sqrt are available.  jac_body

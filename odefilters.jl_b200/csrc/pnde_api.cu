@@ -265,8 +265,11 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
       return PNDE_ERR_UNSUPPORTED;
     }
   } else if (custom) {
-    if (custom->d < 1 || custom->d > 8 || custom->np < 0 || custom->np > 64) {
-      g_create_error = "custom vector field: d must be in 1..8 and n_params in 0..64";
+    // EK1 carries a dense D x (D - d) factor per thread: d <= 8.  EK0's covariance is the (q+1) x q Kronecker factor
+    // whatever d is; only the mean grows (d (q + 1) doubles per thread): d <= 16.
+    const int dmax = (cfg->alg == PNDE_ALG_EK0) ? 16 : 8;
+    if (custom->d < 1 || custom->d > dmax || custom->np < 0 || custom->np > 64) {
+      g_create_error = "custom vector field: d must be in 1..8 (EK1) / 1..16 (EK0) and n_params in 0..64";
       return PNDE_ERR_ARG;
     }
   } else {

@@ -1282,3 +1282,23 @@ def test_lane_group_smoother_equals_one_thread_smoother(name, q, adaptive):
         # fixed steps: the two FILTER kernels already differ in the last bit per step (see the filter test); q = 5
         # amplifies that to 1e-4 in the highest derivative, the solution block stays at rounding level
         assert rel(s2[2][:, :2], s1[2][:, :2]) < 1e-9 and w["cov"] < 1e-5 and w["mean"] < 1e-3
+
+
+def test_custom_field_d12_ek0():
+    """EK0 on a user ODE with d = 12 (the Kronecker covariance does not grow with d): against the dense oracle."""
+    import odefilters_b200 as B
+
+    d = 12
+    f = "; ".join(f"du[{i}] = -p[0]*u[{i}] + p[1]*u[{(i + 1) % d}]*u[{(i + d - 1) % d}]" for i in range(d)) + ";"
+    cv = B.CustomVectorField(d=d, n_params=2, f=f, jac=None)
+    fo = lambda u, p, t: [-p[0] * u[i] + p[1] * u[(i + 1) % d] * u[(i + d - 1) % d] for i in range(d)]  # noqa: E731
+    vf = O.VectorField("ring", d, 2, fo, None)
+    rng = np.random.default_rng(4)
+    u0, p = list(1.0 + 0.3 * rng.standard_normal(d)), [0.7, 0.4]
+    so = O.solve_ivp(O.Problem(vf, u0, (0.0, 1.0), p), O.EK0(order=3, smooth=False), abstol=1e-6, reltol=1e-4)
+    sg = B.solve(B.ODEProblem(cv, u0, (0.0, 1.0), p), B.EK0(order=3, smooth=False), abstol=1e-6, reltol=1e-4)
+    assert (sg.destats["naccept"], sg.destats["nreject"]) == (so.naccept, so.nreject) and sg.retcode == "Success"
+    assert rel(sg.u, np.array([g.mu[:d] for g in so.x_filt])) < 1e-9
+    assert rel(np.diagonal(sg.x_filt.Sigma, axis1=1, axis2=2)[:, :d], np.array([np.diag(g.Sigma.mat)[:d] for g in so.x_filt])) < 1e-6
+    with pytest.raises(RuntimeError):  # EK1 stays at d <= 8 (dense factor per thread)
+        B.solve(B.ODEProblem(B.CustomVectorField(d=d, n_params=2, f=f, jac="J[0][0] = 0.0;"), u0, (0.0, 1.0), p), B.EK1(order=2))
