@@ -69,8 +69,11 @@ extern "C" {
 #define PNDE_VF_VANDERPOL 3      /* prob_ode_vanstiff ordering u=(y,x), p = (mu) */
 #define PNDE_VF_LINEAR2 4        /* du_i = p_i u_i, d = 2 (test/state_init.jl:15) */
 #define PNDE_VF_LOGISTIC 5       /* du = p u (1-u), d = 1 (test/specific_problems.jl:62) */
-#define PNDE_VF_LORENZ96 6       /* d given in the config (4..2048), p = (F); EK0 only: one CTA per trajectory,
-                                    Kronecker-factored covariance, final state only (BASELINE config 4) */
+#define PNDE_VF_LORENZ96 6       /* d given in the config (4..2048), p = (F).  EK0: one CTA per trajectory, Kronecker-
+                                    factored covariance Sigma = Ctilde (x) I_d, history / smoothing available (the
+                                    getters then return the packed Ctilde where other paths return Sigma, and
+                                    pnde_get_marginals ONE covariance entry per state, Ctilde[0][0]); EK1: dense
+                                    D = d (q+1) <= 5120, final state only (BASELINE config 4) */
 #define PNDE_VF_LINEAR1 7        /* du = p u, d = 1 (test/convergence.jl:10) */
 #define PNDE_VF_CUSTOM 100       /* user source, compiled at run time: pnde_create_custom */
 

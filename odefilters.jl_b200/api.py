@@ -529,7 +529,8 @@ class FilterSolver:
         offsets = np.zeros(hi - lo + 1, dtype=np.int64)
         t = empty(total)
         mean = empty((total, DM))
-        cov = empty((total, DM * (DM + 1) // 2))
+        # large-d Kronecker path: the packed Ctilde (Sigma = Ctilde (x) I_d); marginals: one entry, Ctilde[0][0]
+        cov = empty((total, (1 if marginals else self.ncov) if self.kron else DM * (DM + 1) // 2))
         if marginals:
             self._check(self.lib.pnde_get_marginals(self._h, which, lo, hi, offsets.ctypes.data, t.ctypes.data,
                                                     mean.ctypes.data, cov.ctypes.data), "pnde_get_marginals")
@@ -615,6 +616,8 @@ class FilterSolver:
             xs = None
             llv = ll[i]
         else:
+            if self.kron:
+                return self._kron_solution(i, counts, final)
             _, t, mean, cov, diffs = self.history(L.HIST_FILTERED, i, i + 1)
             xf = _GaussianList(mean, _unpack_lower(cov, D), self.history_sqrt(L.HIST_FILTERED, i, i + 1)[1])
             xs = None
@@ -634,6 +637,25 @@ class FilterSolver:
             destats={k: int(counts[k][i]) for k in ("naccept", "nreject", "nf", "njacs")},
             retcode=L.RETCODES.get(int(counts["retcode"][i]), "Failure"), prob=self.prob, alg=self.alg,
             _solver=self, _index=i)
+
+
+    def _kron_solution(self, i: int, counts: dict, final=None) -> ProbODESolution:
+        """Large-d Kronecker path with history: Sigma = Ctilde (x) I_d is never expanded.  x_filt / x_smooth carry the
+        means [N, D] and Ctilde [N, q+1, q+1]; sol.pu the means [N, d] and the marginal variance Ctilde[0, 0] [N]."""
+        q1 = self.alg.order + 1
+        _, t, mean, cov, diffs = self.history(L.HIST_FILTERED, i, i + 1)
+        xf = _GaussianList(mean, _unpack_lower(cov, q1))
+        xs = None
+        if self.cfg.smooth:
+            _, _, ms, cs, _ = self.history(L.HIST_SMOOTHED, i, i + 1)
+            xs = _GaussianList(ms, _unpack_lower(cs, q1))
+        src = xs if xs is not None else xf
+        pu = _GaussianList(src.mu[:, : self.d].copy(), src.Sigma[:, 0, 0].copy())
+        return ProbODESolution(
+            t=t, u=pu.mu, pu=pu, x_filt=xf, x_smooth=xs, diffusions=diffs[1:, 0],
+            log_likelihood=float((final or self.final())[3][i]),
+            destats={k: int(counts[k][i]) for k in ("naccept", "nreject", "nf", "njacs")},
+            retcode=L.RETCODES.get(int(counts["retcode"][i]), "Failure"), prob=self.prob, alg=self.alg, _solver=self, _index=i)
 
 
 # --------------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 // alg isa EK0, H = E1 PI, src/perform_step.jl:127); the reference itself is dense D x D.
 #pragma once
 #include "filter_kernel.cuh"
+#include "smoother_kernel.cuh"
 
 namespace pnde {
 
@@ -427,6 +428,255 @@ inline cudaError_t launch_lorenz(int q, const LorenzParams& prm, cudaStream_t s)
     case 5: return launch_lorenz_q<5>(prm, s);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// History of the large-d Kronecker path: RTS smoother and record conversion.
+//   filtered record  [slot][2 + LEN + D][n]:  t, diffusion, factor of Ctilde (Factor<1, q>), mean (k-major: k d + i)
+//   smoothed record  [slot][NP + 1 + D][n]:   packed lower factor of the smoothed Ctilde, calibration scale, mean
+// Reference: smooth_all! / smooth!  src/smoothing.jl:4-63 on Sigma = Ctilde (x) I_d: the gain is G~ (x) I_d, so the
+// covariance recursion is the (q+1) x (q+1) one (every thread repeats it, ~1 kflop) and the mean recursion applies the
+// same small gain to every dimension independently: no communication between the threads of the CTA at all.
+// ---------------------------------------------------------------------------------------------
+struct LorenzSmoothParams {
+  long long n;
+  int d;
+  long long max_saved;
+  const int* n_saved;
+  const double* hist;
+  double* smooth;
+  const double* final_diff;  // [n]
+  int calibrate;             // static diffusion model: sigma^2 = 1 inside, the final global value scales the output
+  int* status;
+  IwpConsts C;
+};
+
+template <int q, int DPT>
+__global__ void __launch_bounds__(LORENZ_THREADS) lorenz96_smoother_kernel(const LorenzSmoothParams sp) {
+  using Fac = Factor<1, q>;
+  using SC = SmoothCov<1, q>;
+  constexpr int REC = 2 + Fac::LEN, NP = SC::NP;
+  const int d = sp.d, D = d * (q + 1);
+  const long long n = sp.n, tr = blockIdx.x;
+  const int ns = sp.n_saved[tr];
+  if (ns <= 0) {
+    if (threadIdx.x == 0) sp.status[tr] = 0;
+    return;
+  }
+  int own[DPT];
+  bool act[DPT];
+#pragma unroll
+  for (int j = 0; j < DPT; ++j) {
+    own[j] = threadIdx.x + j * LORENZ_THREADS;
+    act[j] = own[j] < d;
+  }
+  const double gfin = sp.calibrate ? sp.final_diff[tr] : 1.0;
+  auto rec = [&](int slot) { return sp.hist + ((long long)slot * (REC + D)) * n + tr; };
+  auto srec = [&](int slot) { return sp.smooth + ((long long)slot * (NP + 1 + D)) * n + tr; };
+  int status = 0;
+  double ms[DPT][q + 1];  // smoothed mean of the own dimensions at i + 1 (natural coordinates)
+  double Ls[NP];          // smoothed factor of Ctilde at i + 1 (natural coordinates), the same in every thread
+  auto load_mean = [&](const double* r, double (&mm)[DPT][q + 1]) {
+#pragma unroll
+    for (int j = 0; j < DPT; ++j)
+#pragma unroll
+      for (int k = 0; k <= q; ++k) mm[j][k] = act[j] ? r[(long long)(REC + k * d + own[j]) * n] : 0.0;
+  };
+  auto write = [&](int slot) {
+    double* o = srec(slot);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int e = 0; e < NP; ++e) o[(long long)e * n] = Ls[e];
+      o[(long long)NP * n] = gfin;
+    }
+#pragma unroll
+    for (int j = 0; j < DPT; ++j)
+      if (act[j])
+#pragma unroll
+        for (int k = 0; k <= q; ++k) o[(long long)(NP + 1 + k * d + own[j]) * n] = ms[j][k];
+  };
+  auto from_filtered = [&](int slot) {
+    const double* r = rec(slot);
+    Fac F;
+    F.load(r + 2 * n, n);
+    load_mean(r, ms);
+    double Y[SC::R][q + 1], Tt[q + 1][q + 1];
+    SC::cols_from_factor(F, Y);
+#pragma unroll
+    for (int c = 0; c <= q; ++c)
+#pragma unroll
+      for (int k = 0; k <= q; ++k) Tt[c][k] = 0.0;
+    SC::template triangularize<SC::R>(Y, Tt, Ls, status);
+  };
+  from_filtered(ns - 1);
+  write(ns - 1);
+  for (int i = ns - 2; i >= 1; --i) {
+    const double* ri = rec(i);
+    const double* rn = rec(i + 1);
+    const double h = rn[0] - ri[0];
+    if (h != 0.0) {
+      double Pk[q + 1], PIk[q + 1];
+      precond_scales<q>(h, Pk, PIk);
+      Fac F;
+      F.load(ri + 2 * n, n);
+      F.scale_blocks(Pk);
+      const double sg = sp.calibrate ? 1.0 : sqrt(rn[n]);  // the interval's diffusion is stored with state i + 1
+      double m[DPT][q + 1], delta[DPT][q + 1];
+      load_mean(ri, m);
+#pragma unroll
+      for (int j = 0; j < DPT; ++j) {
+        double mp[q + 1];
+#pragma unroll
+        for (int k = 0; k <= q; ++k) {
+          m[j][k] *= Pk[k];
+          mp[k] = m[j][k];
+        }
+        apply_A<1, q>(mp);
+#pragma unroll
+        for (int k = 0; k <= q; ++k) delta[j][k] = fma(Pk[k], ms[j][k], -mp[k]);
+      }
+#pragma unroll
+      for (int r = 0; r <= q; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) Ls[SC::tri(r, c)] *= Pk[r];
+      SC::template step<DPT>(F, sg, sp.C, Ls, delta, status);
+#pragma unroll
+      for (int j = 0; j < DPT; ++j)
+#pragma unroll
+        for (int k = 0; k <= q; ++k) {
+          ms[j][k] = (m[j][k] + delta[j][k]) * PIk[k];
+          if (act[j] && !(ms[j][k] == ms[j][k])) status |= 1;
+        }
+#pragma unroll
+      for (int r = 0; r <= q; ++r) {
+#pragma unroll
+        for (int c = 0; c <= r; ++c) Ls[SC::tri(r, c)] *= PIk[r];
+        if (!(Ls[SC::tri(r, r)] == Ls[SC::tri(r, r)])) status |= 1;
+      }
+    }
+    write(i);
+  }
+  if (ns >= 2) {
+    from_filtered(0);  // the first state is never smoothed (src/smoothing.jl:11)
+    write(0);
+  }
+  status = __syncthreads_or(status);
+  if (threadIdx.x == 0) sp.status[tr] = status;
+}
+
+template <int q>
+cudaError_t launch_lorenz_smooth_q(const LorenzSmoothParams& sp, cudaStream_t s) {
+  const int dpt = (sp.d + LORENZ_THREADS - 1) / LORENZ_THREADS;
+  const unsigned grid = (unsigned)sp.n;
+  if (dpt <= 1) { lorenz96_smoother_kernel<q, 1><<<grid, LORENZ_THREADS, 0, s>>>(sp); return cudaGetLastError(); }
+  if (dpt <= 2) { lorenz96_smoother_kernel<q, 2><<<grid, LORENZ_THREADS, 0, s>>>(sp); return cudaGetLastError(); }
+  if (dpt <= 4) { lorenz96_smoother_kernel<q, 4><<<grid, LORENZ_THREADS, 0, s>>>(sp); return cudaGetLastError(); }
+  if (dpt <= 8) { lorenz96_smoother_kernel<q, 8><<<grid, LORENZ_THREADS, 0, s>>>(sp); return cudaGetLastError(); }
+  return cudaErrorInvalidValue;
+}
+inline cudaError_t launch_lorenz_smooth(int q, const LorenzSmoothParams& sp, cudaStream_t s) {
+  switch (q) {
+    case 1: return launch_lorenz_smooth_q<1>(sp, s);
+    case 2: return launch_lorenz_smooth_q<2>(sp, s);
+    case 3: return launch_lorenz_smooth_q<3>(sp, s);
+    case 4: return launch_lorenz_smooth_q<4>(sp, s);
+    case 5: return launch_lorenz_smooth_q<5>(sp, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// History records -> (t, mean, Ctilde packed, diffusion) in CSR order; one CTA per (slot, trajectory).
+// marginals: u [total][d] and ONE covariance entry per state, Ctilde[0][0] (Sigma_u = Ctilde[0][0] I_d).
+struct LorenzConvertParams {
+  long long n, traj_begin, traj_end, max_saved;
+  int d;
+  const int* n_saved;
+  const long long* offsets;
+  const double* hist;
+  const double* smooth;
+  const double* final_diff;
+  int which, calibrate, marginals;
+  double* t;
+  double* mean;
+  double* cov;
+  double* diffusion;
+};
+
+template <int q>
+__global__ void __launch_bounds__(256) lorenz_convert_kernel(const LorenzConvertParams c) {
+  using Fac = Factor<1, q>;
+  using SC = SmoothCov<1, q>;
+  constexpr int REC = 2 + Fac::LEN, NP = SC::NP;
+  const long long ntr = c.traj_end - c.traj_begin;
+  const long long slot = blockIdx.x / ntr;
+  const long long tr = c.traj_begin + blockIdx.x % ntr;
+  if (slot >= c.n_saved[tr]) return;
+  const int d = c.d, D = d * (q + 1);
+  const long long n = c.n;
+  const long long o = c.offsets[tr - c.traj_begin] + slot;
+  const double* fr = c.hist + (slot * (REC + D)) * n + tr;
+  const double* sr = c.which ? c.smooth + (slot * (NP + 1 + D)) * n + tr : nullptr;
+  const double* mean = c.which ? sr + (long long)(NP + 1) * n : fr + (long long)REC * n;
+  const int DM = c.marginals ? d : D;
+  if (c.mean)
+    for (int i = threadIdx.x; i < DM; i += blockDim.x) c.mean[o * DM + i] = mean[(long long)i * n];
+  if (threadIdx.x == 0) {
+    const double g = c.calibrate ? c.final_diff[tr] : fr[n];
+    if (c.t) c.t[o] = fr[0];
+    if (c.diffusion) c.diffusion[o] = g;
+    double Ct[NP];
+    if (c.which == 0) {
+      Fac F;
+      F.load(fr + 2 * n, n);
+      const double cal = c.calibrate ? g : 1.0;
+#pragma unroll
+      for (int i = 0; i <= q; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+          double v = F.W[0][i] * F.W[0][j];
+#pragma unroll
+          for (int cc = 0; cc < Fac::NZ; ++cc)
+            if (i >= 2 + cc && j >= 2 + cc) v = fma(F.Lz[Fac::lz(cc, i - 2)], F.Lz[Fac::lz(cc, j - 2)], v);
+          Ct[SC::tri(i, j)] = v * cal;
+        }
+    } else {
+      double L[NP];
+#pragma unroll
+      for (int e = 0; e < NP; ++e) L[e] = sr[(long long)e * n];
+      const double ds = sr[(long long)NP * n];
+#pragma unroll
+      for (int i = 0; i <= q; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+          double v = 0.0;
+#pragma unroll
+          for (int k = 0; k <= j; ++k) v = fma(L[SC::tri(i, k)], L[SC::tri(j, k)], v);
+          Ct[SC::tri(i, j)] = v * ds;
+        }
+    }
+    if (c.cov) {
+      if (c.marginals) {
+        c.cov[o] = Ct[0];
+      } else {
+#pragma unroll
+        for (int e = 0; e < NP; ++e) c.cov[o * NP + e] = Ct[e];
+      }
+    }
+  }
+}
+
+inline cudaError_t launch_lorenz_convert(int q, const LorenzConvertParams& c, cudaStream_t s) {
+  const long long blocks = (c.traj_end - c.traj_begin) * c.max_saved;
+  if (blocks <= 0) return cudaSuccess;
+  switch (q) {
+    case 1: lorenz_convert_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(c); break;
+    case 2: lorenz_convert_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(c); break;
+    case 3: lorenz_convert_kernel<3><<<(unsigned)blocks, 256, 0, s>>>(c); break;
+    case 4: lorenz_convert_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(c); break;
+    case 5: lorenz_convert_kernel<5><<<(unsigned)blocks, 256, 0, s>>>(c); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace pnde

@@ -260,8 +260,8 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
       g_create_error = "Lorenz-96: MV diffusion models are not built for the large-d path";
       return PNDE_ERR_UNSUPPORTED;
     }
-    if (cfg->save_mode != PNDE_SAVE_FINAL || cfg->smooth) {
-      g_create_error = "Lorenz-96: only save_mode = PNDE_SAVE_FINAL (no smoothing) is built for the large-d path";
+    if (cfg->alg == PNDE_ALG_EK1 && (cfg->save_mode != PNDE_SAVE_FINAL || cfg->smooth)) {
+      g_create_error = "Lorenz-96 EK1 (dense): only save_mode = PNDE_SAVE_FINAL (no smoothing) is built";
       return PNDE_ERR_UNSUPPORTED;
     }
   } else if (custom) {
@@ -499,7 +499,17 @@ const char* pnde_last_error(const pnde_handle* h) { return h ? h->err.c_str() : 
 
 int64_t pnde_state_dim(const pnde_handle* h) { return h ? h->D : 0; }
 int64_t pnde_n_params(const pnde_handle* h) { return h ? h->np : 0; }
-int64_t pnde_record_len(const pnde_handle* h) { return (h && h->ops) ? h->ops->rec : 0; }
+// doubles per saved state: catalogue / NVRTC models from their ops; large-d Kronecker path: t, diffusion, factor, mean
+static int lorenz_rec(const pnde_handle* h) {
+  const int q = h->cfg.order, nz = q - 1;
+  return 2 + (q + 1) + (nz > 0 ? nz * (nz + 1) / 2 : 0) + h->D;
+}
+static int lorenz_srec(const pnde_handle* h) { return (h->cfg.order + 1) * (h->cfg.order + 2) / 2 + 1 + h->D; }
+int64_t pnde_record_len(const pnde_handle* h) {
+  if (!h) return 0;
+  if (h->ops) return h->ops->rec;
+  return (h->lorenz && h->cfg.alg == PNDE_ALG_EK0) ? lorenz_rec(h) : 0;
+}
 int64_t pnde_cov_len(const pnde_handle* h) { return h ? h->ncov : 0; }
 
 static long long derive_max_saved(const pnde_handle* h) {
@@ -561,7 +571,7 @@ static int upload_impl(pnde_handle* h, int64_t n_traj, const double* u0, const d
     });
   }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
-  struct { int d, np, D, nd, rec; } dims = {h->d, h->np, h->D, h->nd, h->ops ? h->ops->rec : 0};
+  struct { int d, np, D, nd, rec; } dims = {h->d, h->np, h->D, h->nd, (int)pnde_record_len(h)};
   const auto* o = &dims;
   const size_t n = (size_t)n_traj;
   const long long ms = derive_max_saved(h);
@@ -748,10 +758,10 @@ int pnde_run(pnde_handle* h) {
     lp.nreject = fp.nreject;
     lp.nf = fp.nf;
     lp.n_saved = fp.n_saved;
-    lp.hist = nullptr;
-    lp.max_saved = 0;
-    lp.save_mode = PNDE_SAVE_FINAL;
-    lp.save_stride = 1;
+    lp.hist = fp.hist;
+    lp.max_saved = fp.max_saved;
+    lp.save_mode = fp.save_mode;
+    lp.save_stride = fp.save_stride;
     lp.diffusion = fp.diffusion;
     lp.adaptive = c.adaptive;
     lp.C = fp.C;
@@ -784,6 +794,35 @@ int pnde_smooth(pnde_handle* h) {
     return PNDE_OK;
   }
   CK(cudaSetDevice(h->device), "cudaSetDevice");
+  if (h->lorenz) {
+    if (h->cfg.alg != PNDE_ALG_EK0) return h->fail(PNDE_ERR_UNSUPPORTED, "smoothing is not built for the dense large-D EK1 path");
+    cudaError_t e2 = h->smooth.ensure((size_t)h->n * (size_t)h->max_saved * lorenz_srec(h) * 8);
+    if (e2 != cudaSuccess) {
+      h->err = std::string("smoothed-history allocation: ") + cudaGetErrorString(e2);
+      cudaGetLastError();
+      return PNDE_ERR_ALLOC;
+    }
+    CK(h->sstatus.ensure((size_t)h->n * 4), "alloc smoother status");
+    LorenzSmoothParams ls;
+    memset(&ls, 0, sizeof(ls));
+    ls.n = h->n;
+    ls.d = h->d;
+    ls.max_saved = h->max_saved;
+    ls.n_saved = h->n_saved.as<int>();
+    ls.hist = h->hist.as<double>();
+    ls.smooth = h->smooth.as<double>();
+    ls.final_diff = h->final_diff.as<double>();
+    const int dfl = h->cfg.diffusion;
+    ls.calibrate = (dfl == PNDE_DIFF_FIXED || dfl == PNDE_DIFF_FIXED_MAP);
+    ls.status = h->sstatus.as<int>();
+    ls.C = h->C;
+    CK(cudaEventRecord(h->ev[2], h->stream), "event record");
+    CK(launch_lorenz_smooth(h->cfg.order, ls, h->stream), "lorenz smoother launch");
+    CK(cudaEventRecord(h->ev[3], h->stream), "event record");
+    h->launches += 1;
+    h->smoothed = true;
+    return PNDE_OK;
+  }
   const ModelOps* o = h->ops;
   cudaError_t e = h->smooth.ensure((size_t)h->n * (size_t)h->max_saved * o->srec * 8);
   if (e != cudaSuccess) {
@@ -1102,7 +1141,8 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
   if (h->cfg.save_mode == PNDE_SAVE_FINAL) return h->fail(PNDE_ERR_STATE, "no history was saved (save_mode = final)");
   if (h->multi()) {
-    const int64_t DM = marginals ? h->d : h->D, NC = DM * (DM + 1) / 2;
+    const bool kron = h->lorenz && h->cfg.alg == PNDE_ALG_EK0;
+    const int64_t DM = marginals ? h->d : h->D, NC = kron ? (marginals ? 1 : h->ncov) : DM * (DM + 1) / 2;
     const int df0 = h->cfg.diffusion;
     const int64_t ndo = (df0 == PNDE_DIFF_DYNAMIC_MV || df0 == PNDE_DIFF_FIXED_MV) ? h->d : 1;
     return multi_csr(h, tb, te, offsets, [&](pnde_handle* kid, int64_t lo, int64_t hi, int64_t* offs, int64_t base) {
@@ -1116,6 +1156,8 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   if (tb < 0 || te > h->n || tb >= te || !offsets) return h->fail(PNDE_ERR_ARG, "bad trajectory range");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   const ModelOps* o = h->ops;
+  if (!o && !(h->lorenz && h->cfg.alg == PNDE_ALG_EK0)) return h->fail(PNDE_ERR_UNSUPPORTED, "no history on this path");
+  if (!o && sqrt_out) return h->fail(PNDE_ERR_UNSUPPORTED, "the large-d path returns Ctilde, not D x D factors");
   std::vector<int> ns;
   int rc = fetch_i32(h, h->n_saved, ns);
   if (rc != PNDE_OK) return rc;
@@ -1125,6 +1167,44 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   for (long long i = 0; i < ntr; ++i) off[(size_t)i + 1] = off[(size_t)i] + ns[(size_t)(tb + i)];
   const long long total = off[(size_t)ntr];
   for (long long i = 0; i <= ntr; ++i) offsets[i] = off[(size_t)i];
+  if (!o) {
+    // large-d Kronecker path: mean [total][D] (marginals: [total][d]), cov = packed Ctilde [total][(q+1)(q+2)/2]
+    // (marginals: ONE entry per state, Ctilde[0][0]: Sigma_u = Ctilde[0][0] I_d), diffusion [total]
+    const size_t DMl = marginals ? (size_t)h->d : (size_t)h->D, NCl = marginals ? 1 : (size_t)h->ncov;
+    const size_t nml = (size_t)total * DMl, ncl = (size_t)total * NCl;
+    CK(h->scratch_off.ensure(((size_t)ntr + 1) * 8), "alloc offsets");
+    CK(h->scratch_out.ensure(((size_t)total * 2 + nml + ncl) * 8 + 64), "alloc history staging");
+    CK(cudaMemcpyAsync(h->scratch_off.p, off.data(), ((size_t)ntr + 1) * 8, cudaMemcpyHostToDevice, h->stream), "H2D offsets");
+    double* lt = h->scratch_out.as<double>();
+    LorenzConvertParams lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.n = h->n;
+    lc.traj_begin = tb;
+    lc.traj_end = te;
+    lc.max_saved = h->max_saved;
+    lc.d = h->d;
+    lc.n_saved = h->n_saved.as<int>();
+    lc.offsets = h->scratch_off.as<long long>();
+    lc.hist = h->hist.as<double>();
+    lc.smooth = h->smooth.as<double>();
+    lc.final_diff = h->final_diff.as<double>();
+    lc.which = which;
+    const int dfl = h->cfg.diffusion;
+    lc.calibrate = (dfl == PNDE_DIFF_FIXED || dfl == PNDE_DIFF_FIXED_MAP);
+    if (marginals && which == PNDE_HIST_FILTERED && !h->cfg.smooth && (h->cfg.flags & PNDE_FLAG_REFERENCE_QUIRKS)) lc.calibrate = 0;
+    lc.marginals = marginals ? 1 : 0;
+    lc.t = lt;
+    lc.diffusion = lt + total;
+    lc.mean = lt + 2 * total;
+    lc.cov = lc.mean + nml;
+    CK(launch_lorenz_convert(h->cfg.order, lc, h->stream), "lorenz convert launch");
+    if (t) CK(cudaMemcpyAsync(t, lc.t, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
+    if (mean) CK(cudaMemcpyAsync(mean, lc.mean, nml * 8, cudaMemcpyDeviceToHost, h->stream), "D2H mean");
+    if (cov) CK(cudaMemcpyAsync(cov, lc.cov, ncl * 8, cudaMemcpyDeviceToHost, h->stream), "D2H cov");
+    if (diffusion) CK(cudaMemcpyAsync(diffusion, lc.diffusion, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H diffusion");
+    CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+    return PNDE_OK;
+  }
   const int df = h->cfg.diffusion;
   const bool is_mv = (df == PNDE_DIFF_DYNAMIC_MV || df == PNDE_DIFF_FIXED_MV);
   const int nd_out = is_mv ? o->d : 1;
@@ -1199,6 +1279,7 @@ int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint6
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
   if (h->cfg.save_mode != PNDE_SAVE_EVERY) return h->fail(PNDE_ERR_STATE, "pnde_sample needs save_mode = PNDE_SAVE_EVERY");
   if (tb < 0 || te > h->n || tb >= te || !offsets || n_samples < 1) return h->fail(PNDE_ERR_ARG, "bad arguments");
+  if (h->lorenz) return h->fail(PNDE_ERR_UNSUPPORTED, "sampling is not built for the large-d paths");
   if (h->multi()) {
     // the generator is keyed by the trajectory index: children are handed their global offset so that the draws do
     // not depend on how the ensemble was sharded
@@ -1352,6 +1433,7 @@ int pnde_eval_dense(pnde_handle* h, int32_t which, int64_t tb, int64_t te, int64
   if (which == PNDE_HIST_SMOOTHED && !h->smoothed) return h->fail(PNDE_ERR_STATE, "history has not been smoothed");
   if (which != PNDE_HIST_FILTERED && which != PNDE_HIST_SMOOTHED) return h->fail(PNDE_ERR_ARG, "bad 'which'");
   if (tb < 0 || te > h->n || tb >= te || n_t < 1 || !t) return h->fail(PNDE_ERR_ARG, "bad arguments");
+  if (h->lorenz) return h->fail(PNDE_ERR_UNSUPPORTED, "dense output is not built for the large-d paths");
   if (h->multi()) {
     const int64_t NC = (int64_t)h->D * (h->D + 1) / 2;
     for (size_t k = 0; k < h->kids.size(); ++k) {

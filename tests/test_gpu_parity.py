@@ -1302,3 +1302,47 @@ def test_custom_field_d12_ek0():
     assert rel(np.diagonal(sg.x_filt.Sigma, axis1=1, axis2=2)[:, :d], np.array([np.diag(g.Sigma.mat)[:d] for g in so.x_filt])) < 1e-6
     with pytest.raises(RuntimeError):  # EK1 stays at d <= 8 (dense factor per thread)
         B.solve(B.ODEProblem(B.CustomVectorField(d=d, n_params=2, f=f, jac="J[0][0] = 0.0;"), u0, (0.0, 1.0), p), B.EK1(order=2))
+
+
+@pytest.mark.parametrize("d,q,diffusion,adaptive", [(8, 3, "dynamic", False), (40, 2, "fixed", False), (12, 3, "dynamic", True)])
+def test_large_d_path_history_and_smoother_against_dense_oracle(d, q, diffusion, adaptive):
+    """The CTA-per-trajectory Kronecker path (Lorenz-96) with every step saved and the RTS pass: filtered and smoothed
+    means of all derivatives and Ctilde against the DENSE oracle (Sigma = Ctilde (x) I_d), src/smoothing.jl:4-63."""
+    import odefilters_b200 as B
+
+    u0 = _lorenz_inputs(d)
+    kw = dict(adaptive=False, dt=0.01) if not adaptive else dict(abstol=1e-6, reltol=1e-4)
+    so = O.solve_ivp(O.Problem(O.lorenz96(d), list(u0), (0.0, 0.3), [8.0]), O.Alg("EK0", q, diffusion, True), **kw)
+    sg = B.solve(B.ODEProblem("lorenz96", u0, (0.0, 0.3), (8.0,)), B.EK0(order=q, diffusionmodel=diffusion, smooth=True), **kw)
+    assert sg.retcode == "Success" and len(sg.t) == len(so.t)
+    assert (sg.destats["naccept"], sg.destats["nreject"]) == (so.naccept, so.nreject)
+    assert rel(sg.t, so.t) < 1e-9
+    for mine, theirs, tol in ((sg.x_filt, so.x_filt, 1e-9), (sg.x_smooth, so.x_smooth, 1e-8)):
+        mo = np.array([g.mu for g in theirs])
+        assert rel(mine.mu[:, :d], mo[:, :d]) < tol
+        for k in range(q + 1):
+            assert rel(mine.mu[:, k * d:(k + 1) * d], mo[:, k * d:(k + 1) * d]) < 1e-6
+        # Ctilde[k][l] = Sigma[(k, 0), (l, 0)]; the other dimensions repeat it
+        Co = np.array([g.Sigma.mat[0::d, 0::d] for g in theirs])
+        sd = np.sqrt(np.maximum(np.diagonal(Co, axis1=1, axis2=2).max(axis=0), 1e-300))
+        assert np.max(np.abs(mine.Sigma - Co) / np.outer(sd, sd)) < 1e-6
+    assert rel(sg.u, np.array(so.u)) < 1e-8                             # sol.u := smoothed means
+    assert np.array_equal(sg.x_smooth.mu[-1], sg.x_filt.mu[-1])          # test/smoothing.jl:39
+    assert rel(sg.diffusions, np.asarray(so.diffusions, dtype=float)) < 1e-6
+    assert rel(sg.pu.Sigma, np.array([g.Sigma.mat[0, 0] for g in so.x_smooth])) < 1e-6
+
+
+def test_large_d_path_history_d1024():
+    """d = 1024 (BASELINE config 4) with history and smoothing: sizes, the filtered end state equal to the final-only
+    run, the last smoothed state equal to the last filtered one, smoothed variances not above the filtered ones."""
+    import odefilters_b200 as B
+
+    d, q = 1024, 3
+    u0 = _lorenz_inputs(d)
+    prob = B.ODEProblem("lorenz96", u0, (0.0, 0.05), (8.0,))
+    fin = B.solve(prob, B.EK0(order=q, smooth=False), adaptive=False, dt=1e-3, save_everystep=False)
+    sg = B.solve(prob, B.EK0(order=q, smooth=True), adaptive=False, dt=1e-3)
+    assert sg.retcode == "Success" and len(sg.t) == 51 and sg.x_filt.mu.shape == (51, d * (q + 1))
+    assert np.array_equal(sg.x_filt.mu[-1], fin.x_filt.mu[0]) and np.array_equal(sg.x_smooth.mu[-1], sg.x_filt.mu[-1])
+    assert np.all(sg.x_smooth.Sigma[1:-1, 0, 0] <= sg.x_filt.Sigma[1:-1, 0, 0] * (1 + 1e-12))
+    assert np.all(np.isfinite(sg.x_smooth.mu)) and sg.pu.Sigma.shape == (51,)
