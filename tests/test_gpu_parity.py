@@ -1325,6 +1325,9 @@ def test_large_d_path_history_and_smoother_against_dense_oracle(d, q, diffusion,
         # Ctilde[k][l] = Sigma[(k, 0), (l, 0)]; the other dimensions repeat it
         Co = np.array([g.Sigma.mat[0::d, 0::d] for g in theirs])
         sd = np.sqrt(np.maximum(np.diagonal(Co, axis1=1, axis2=2).max(axis=0), 1e-300))
+        hmax = float(np.max(np.diff(so.t)))
+        for k in range(q - 1, -1, -1):  # block 1 is pinned by the measurement: floor at h s_{k+1} (see block_errors)
+            sd[k] = max(sd[k], hmax * sd[k + 1])
         assert np.max(np.abs(mine.Sigma - Co) / np.outer(sd, sd)) < 1e-6
     assert rel(sg.u, np.array(so.u)) < 1e-8                             # sol.u := smoothed means
     assert np.array_equal(sg.x_smooth.mu[-1], sg.x_filt.mu[-1])          # test/smoothing.jl:39
