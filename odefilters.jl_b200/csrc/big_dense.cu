@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <utility>
+
 #include "big_dense_api.h"
 #include "filter_kernel.cuh"
 
@@ -288,6 +290,76 @@ __global__ void finish_step_kernel(Scalars* sc, int d, int diffusion) {
   sc->ll_n += 1;
 }
 
+// Local error estimate and EEst of one attempted step (src/perform_step.jl:78-84,148-158), single CTA:
+//   err_i = sqrt(sigma^2_loc (H Q H')_ii),  r_i = dt err_i / (abstol + max(|uprev_i|, |u_i|) reltol),  EEst = rms(r).
+// integ.u is overwritten with the new solution whether or not the step is accepted (:86).
+__global__ void __launch_bounds__(1024) eest_kernel(StepCtx c, double* uprev, double dt, double abstol, double reltol,
+                                                    int dynamic, double* out) {
+  __shared__ double red[32];
+  const int d = c.d;
+  const double pi1 = c.sc->pi1;
+  const double local = dynamic ? c.sc->local : c.sc->quad / double(d);
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    double jj = 0.0;
+    for (int o = 0; o < 4; ++o) jj = fma(c.Jp[i * 4 + o], c.Jp[i * 4 + o], jj);
+    const double Bii = fma(pi1 * pi1, c.C.Qt[1][1], fma(-2.0 * pi1 * c.C.Qt[0][1], c.Jp[i * 4 + 2], c.C.Qt[0][0] * jj));
+    const double un = c.m[i];
+    const double r = dt * sqrt(local * Bii) / (abstol + fmax(fabs(uprev[i]), fabs(un)) * reltol);
+    acc = fma(r, r, acc);
+    uprev[i] = un;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    out[0] = sqrt(tot / double(d));
+  }
+}
+
+// ode_determine_initdt (Hairer) for Lorenz-96, single CTA; m holds the initial jets (m[d + i] = f(u0)_i)
+__global__ void __launch_bounds__(1024) initdt_kernel(StepCtx c, double abstol, double reltol, double dtmax, double* scratch,
+                                                      double* out) {
+  __shared__ double red[3][32];
+  const int d = c.d, q = c.q;
+  auto bsum = [&](double v, int slot) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[slot][threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[slot][w];
+    return tot;
+  };
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    const double sk = abstol + fabs(c.m[i]) * reltol;
+    const double a = c.m[i] / sk, b = c.m[d + i] / sk;
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+  }
+  const double d0 = sqrt(bsum(s0, 0) / d), d1 = sqrt(bsum(s1, 1) / d);
+  double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+  dt0 = fmin(dt0, dtmax);
+  for (int i = threadIdx.x; i < d; i += blockDim.x) scratch[i] = fma(dt0, c.m[d + i], c.m[i]);
+  __syncthreads();
+  double s2 = 0.0;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    const double f1 = (scratch[wrapi(i + 1, d)] - scratch[wrapi(i - 2, d)]) * scratch[wrapi(i - 1, d)] - scratch[i] + c.F;
+    const double sk = abstol + fabs(c.m[i]) * reltol;
+    const double cc = (f1 - c.m[d + i]) / sk;
+    s2 = fma(cc, cc, s2);
+  }
+  const double d2 = sqrt(bsum(s2, 2) / d) / dt0;
+  if (threadIdx.x == 0) {
+    const double mx = fmax(d1, d2);
+    const double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / double(q + 1));
+    out[0] = (dt0 < 10.0 * 2.220446049250313e-16) ? 1e-6 : fmin(fmin(100.0 * dt0, dt1), dtmax);
+  }
+}
+
 __global__ void init_mean_kernel(StepCtx c, const double* u0, long long n, long long tr, double* jets /* [(q+1)][d] */) {
   // Taylor-mode jets of Lorenz-96 (same recursion as lorenz96_kernel.cuh); single CTA
   const int d = c.d, q = c.q;
@@ -322,7 +394,8 @@ __global__ void pack_cov_kernel(const double* full, int D, double cal, double* o
 
 __global__ void write_outputs_kernel(StepCtx c, double* mean, double* t_final, double* loglik, double* final_diff,
                                      int* retcode, int* naccept, int* nreject, int* nf, int* njacs, int* n_saved,
-                                     long long n, long long tr, double t, int is_static, int truncated) {
+                                     long long n, long long tr, double t, int is_static, int ret_host, int nrej,
+                                     int nfe) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c.D) mean[(long long)i * n + tr] = c.m[i];
   if (i == 0) {
@@ -333,11 +406,11 @@ __global__ void write_outputs_kernel(StepCtx c, double* mean, double* t_final, d
     loglik[tr] = ll;
     final_diff[tr] = sc->global_saved;
     // a loop cut short by maxiters is reported as such (filter_kernel / lorenz96_kernel do the same)
-    retcode[tr] = sc->nonfinite ? RET_NONFINITE : (truncated ? RET_MAXITERS : RET_SUCCESS);
+    retcode[tr] = sc->nonfinite ? RET_NONFINITE : ret_host;
     naccept[tr] = sc->nacc;
-    nreject[tr] = 0;
-    nf[tr] = sc->nacc;
-    njacs[tr] = sc->nacc;
+    nreject[tr] = nrej;
+    nf[tr] = nfe;
+    njacs[tr] = sc->nacc + nrej;
     n_saved[tr] = 0;
   }
 }
@@ -350,11 +423,11 @@ double ulp_host(double x) {
 
 }  // namespace
 
-size_t big_work_bytes(int d, int q) {
+size_t big_work_bytes(int d, int q, bool adaptive) {
   const size_t D = (size_t)d * (q + 1);
-  // m, mp, Jp, fu, z, y, jets | S | E | R | W | v0, T | scalars
+  // m, mp, Jp, fu, z, y, jets | S | E | R | W | v0, T | scalars  (+ adaptive: second S, pre-step m, uprev, EEst)
   return (D * 2 + (size_t)d * 4 + (size_t)d * 3 + D) * 8 + (D - d) * D * 8 + D * D * 8 * 2 + (size_t)NB * D * 8 +
-         2 * (NB + NB * NB) * 8 + sizeof(Scalars) + 8192;
+         2 * (NB + NB * NB) * 8 + sizeof(Scalars) + 8192 + (adaptive ? (D - d) * D * 8 + (D + d + 64) * 8 + 2048 : 0);
 }
 
 #define BCK(call)                      \
@@ -420,6 +493,15 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
     BCK(cudaEventCreateWithFlags(&wk.ev_panel[i], cudaEventDisableTiming));
   }
   c.sc = (Scalars*)take(sizeof(Scalars));
+  // adaptive: a rejected step must leave (m, S) untouched -- the new factor goes to a second buffer that is swapped in
+  // on commit, the pre-step mean is kept, EEst comes back to the host controller (8 bytes per attempted step)
+  double *S2 = nullptr, *m_old = nullptr, *uprev = nullptr, *d_eest = nullptr;
+  if (A.adaptive) {
+    S2 = (double*)take((size_t)(D - d) * D * 8);
+    m_old = (double*)take((size_t)D * 8);
+    uprev = (double*)take((size_t)d * 8);
+    d_eest = (double*)take(64);
+  }
   c.diffusion = A.diffusion;
   c.C = A.C;
   const bool dynamic = (A.diffusion == DIFF_DYNAMIC);
@@ -460,27 +542,107 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
       gain_gemv_kernel<<<dim3((D - d + TB - 1) / TB, (d + 63) / 64), TB, 0, s>>>(c, jets);
       mean_update2_kernel<<<(d + TB - 1) / TB, TB, 0, s>>>(c, jets);
       ++*launches;
-      build_s_kernel<<<(unsigned)(((long long)(D - d) * d + TB - 1) / TB), TB, 0, s>>>(c);
-      finish_step_kernel<<<1, 1, 0, s>>>(c.sc, d, A.diffusion);
-      *launches += 4;
+      if (A.adaptive) {
+        StepCtx c2 = c;  // same R, Jp, scalars; the posterior factor is written next to the current one
+        c2.S = S2;
+        build_s_kernel<<<(unsigned)(((long long)(D - d) * d + TB - 1) / TB), TB, 0, s>>>(c2);
+        *launches += 3;
+      } else {
+        build_s_kernel<<<(unsigned)(((long long)(D - d) * d + TB - 1) / TB), TB, 0, s>>>(c);
+        finish_step_kernel<<<1, 1, 0, s>>>(c.sc, d, A.diffusion);
+        *launches += 4;
+      }
       return cudaGetLastError();
     };
     // (capturing the ~650 launches of a step into a CUDA graph was measured: 23.5 ms/step either way -- the panel
     // chain is bound by the kernels themselves, not by launch gaps -- so the plain launches stay)
-    bool truncated = false;
-    while (t < A.K.t1) {
-      if (++iter > A.K.maxiters) {
-        truncated = true;
-        break;
+    int ret_host = RET_SUCCESS, nrej = 0, nfe = 0;
+    if (!A.adaptive) {
+      while (t < A.K.t1) {
+        if (++iter > A.K.maxiters) {
+          ret_host = RET_MAXITERS;
+          break;
+        }
+        const double h = fmin(A.K.dt, A.K.t1 - t);
+        BCK(step_body(h));
+        ++nfe;
+        const double ttmp = t + h;
+        t = (fabs(ttmp - A.K.t1) < 10.0 * ulp_host(fmax(t, A.K.t1))) ? A.K.t1 : ttmp;
       }
-      const double h = fmin(A.K.dt, A.K.t1 - t);
-      BCK(step_body(h));
-      const double ttmp = t + h;
-      t = (fabs(ttmp - A.K.t1) < 10.0 * ulp_host(fmax(t, A.K.t1))) ? A.K.t1 : ttmp;
+    } else {
+      // OrdinaryDiffEq's loop (loopheader!, perform_step!, loopfooter!, PI controller) on the host:
+      // a step is ~18 ms of device work at D = 4096, the 8-byte read-back of EEst per attempt is free beside it
+      const CtrlParams& K = A.K;
+      double dt = K.dt;
+      BCK(cudaMemcpyAsync(uprev, c.m, (size_t)d * 8, cudaMemcpyDeviceToDevice, s));  // integ.u = u0
+      if (!(dt > 0.0)) {
+        initdt_kernel<<<1, 1024, 0, s>>>(c, K.abstol, K.reltol, K.dtmax, jets, d_eest);
+        ++*launches;
+        BCK(cudaMemcpyAsync(&dt, d_eest, 8, cudaMemcpyDeviceToHost, s));
+        BCK(cudaStreamSynchronize(s));
+        nfe += 2;
+      }
+      double dtpropose = dt, qold = K.qoldinit, q11 = 1.0;
+      bool accepted_prev = true;
+      while (t < K.t1) {
+        if (iter > 0) dt = accepted_prev ? dtpropose : dt / fmin(1.0 / K.qmin, q11 / K.gamma);
+        if (++iter > K.maxiters) {
+          ret_host = RET_MAXITERS;
+          break;
+        }
+        dt = fmin(dt, K.dtmax);
+        dt = fmax(dt, K.dtmin);
+        dt = fmin(dt, K.t1 - t);
+        if (dt != dt) {
+          ret_host = RET_DTNAN;
+          break;
+        }
+        if (iter > 1 && !accepted_prev && fabs(dt) <= fabs(K.dtmin)) {
+          ret_host = RET_DTMIN;
+          break;
+        }
+        BCK(cudaMemcpyAsync(m_old, c.m, (size_t)D * 8, cudaMemcpyDeviceToDevice, s));
+        BCK(step_body(dt));
+        ++nfe;
+        eest_kernel<<<1, 1024, 0, s>>>(c, uprev, dt, K.abstol, K.reltol, dynamic ? 1 : 0, d_eest);
+        ++*launches;
+        double EEst = 0.0;
+        BCK(cudaMemcpyAsync(&EEst, d_eest, 8, cudaMemcpyDeviceToHost, s));
+        BCK(cudaStreamSynchronize(s));
+        if (!(EEst == EEst)) {  // non-finite state: OrdinaryDiffEq's unstable check
+          ret_host = RET_NONFINITE;
+          break;
+        }
+        const bool commit = EEst < 1.0, accept = EEst <= 1.0;  // src/perform_step.jl:89 / loopfooter!
+        if (commit) {
+          std::swap(c.S, S2);
+          finish_step_kernel<<<1, 1, 0, s>>>(c.sc, d, A.diffusion);
+          ++*launches;
+        } else {
+          BCK(cudaMemcpyAsync(c.m, m_old, (size_t)D * 8, cudaMemcpyDeviceToDevice, s));
+        }
+        double qc;
+        if (EEst == 0.0) {
+          qc = 1.0 / K.qmax;
+        } else {
+          q11 = pow(EEst, K.beta1);
+          qc = fmax(1.0 / K.qmax, fmin(1.0 / K.qmin, q11 / pow(qold, K.beta2) / K.gamma));
+        }
+        const double ttmp = t + dt;
+        if (accept) {
+          if (K.qsteady_min <= qc && qc <= K.qsteady_max) qc = 1.0;
+          qold = fmax(EEst, K.qoldinit);
+          t = (fabs(ttmp - K.t1) < 10.0 * ulp_host(fmax(t, K.t1))) ? K.t1 : ttmp;
+          dtpropose = fmax(K.dtmin, fmin(K.dtmax, dt / qc));
+        } else {
+          ++nrej;
+        }
+        accepted_prev = accept;
+      }
     }
     write_outputs_kernel<<<(D + TB - 1) / TB, TB, 0, s>>>(c, A.mean, A.t_final, A.loglik, A.final_diff, A.retcode,
                                                           A.naccept, A.nreject, A.nf, A.njacs, A.n_saved, A.n, tr, t,
-                                                          is_static ? 1 : 0, truncated ? 1 : 0);
+                                                          is_static ? 1 : 0, ret_host, nrej, nfe);
     ++*launches;
     if (A.cov) {
       // Sigma = S' S over the factor columns (rows of S): full D x D by the same DMMA kernel, then packed

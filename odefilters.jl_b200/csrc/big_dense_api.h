@@ -10,6 +10,7 @@ namespace big {
 struct BigRunArgs {
   long long n;       // trajectories (processed one after the other)
   int d, q, diffusion;
+  int adaptive;      // 1: PI-controlled steps (the controller runs on the host, one 8-byte read-back per attempted step)
   const double* u0;  // [d][n] device
   const double* p;   // [1][n] device (forcing F)
   double* mean;      // [D][n]
@@ -28,7 +29,7 @@ struct BigRunArgs {
   CtrlParams K;
 };
 
-size_t big_work_bytes(int d, int q);
+size_t big_work_bytes(int d, int q, bool adaptive = false);
 cudaError_t big_run(const BigRunArgs& args, cudaStream_t stream, long long* launches);
 
 }  // namespace big

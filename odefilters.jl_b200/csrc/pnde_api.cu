@@ -245,10 +245,6 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
         g_create_error = "Lorenz-96 EK1 (dense, D >= 64): d must be a multiple of 32 with d (q+1) <= 5120";
         return PNDE_ERR_UNSUPPORTED;
       }
-      if (cfg->adaptive) {
-        g_create_error = "Lorenz-96 EK1 (dense): only fixed steps are built";
-        return PNDE_ERR_UNSUPPORTED;
-      }
     } else if (cfg->d < 4 || cfg->d > 8 * LORENZ_THREADS) {
       g_create_error = "Lorenz-96: d must be in 4..2048";
       return PNDE_ERR_ARG;
@@ -705,7 +701,7 @@ int pnde_run(pnde_handle* h) {
   }
   CK(cudaEventRecord(h->ev[0], h->stream), "event record");
   if (h->lorenz && c.alg == PNDE_ALG_EK1) {
-    cudaError_t e = h->bigwork.ensure(big::big_work_bytes(h->d, c.order));
+    cudaError_t e = h->bigwork.ensure(big::big_work_bytes(h->d, c.order, c.adaptive != 0));
     if (e != cudaSuccess) {
       h->err = std::string("work-space allocation for the dense large-D path: ") + cudaGetErrorString(e);
       cudaGetLastError();
@@ -717,6 +713,7 @@ int pnde_run(pnde_handle* h) {
     ba.d = h->d;
     ba.q = c.order;
     ba.diffusion = c.diffusion;
+    ba.adaptive = c.adaptive;
     ba.u0 = fp.u0;
     ba.p = fp.p;
     ba.mean = fp.mean;

@@ -1349,3 +1349,25 @@ def test_large_d_path_history_d1024():
     assert np.array_equal(sg.x_filt.mu[-1], fin.x_filt.mu[0]) and np.array_equal(sg.x_smooth.mu[-1], sg.x_filt.mu[-1])
     assert np.all(sg.x_smooth.Sigma[1:-1, 0, 0] <= sg.x_filt.Sigma[1:-1, 0, 0] * (1 + 1e-12))
     assert np.all(np.isfinite(sg.x_smooth.mu)) and sg.pu.Sigma.shape == (51,)
+
+
+@pytest.mark.parametrize("d,q,diffusion", [(32, 2, "dynamic"), (32, 3, "dynamic"), (64, 1, "fixed")])
+def test_large_dense_ek1_adaptive_against_oracle(d, q, diffusion):
+    """The blocked-QR dense EK1 path with PI-controlled steps (controller on the host, EEst from the device):
+    identical accept/reject counts and the final state against the dense oracle."""
+    import odefilters_b200 as B
+
+    u0 = _lorenz_inputs(d)
+    kw = dict(abstol=1e-5, reltol=1e-3)
+    so = O.solve_ivp(O.Problem(O.lorenz96(d), list(u0), (0.0, 0.1), [8.0]), O.Alg("EK1", q, diffusion, False), **kw)
+    sg = B.solve(B.ODEProblem("lorenz96", u0, (0.0, 0.1), (8.0,)), B.EK1(order=q, diffusionmodel=diffusion, smooth=False),
+                 save_everystep=False, **kw)
+    ref = so.x_filt[-1]
+    assert sg.retcode == "Success" and sg.t[-1] == 0.1
+    assert (sg.destats["naccept"], sg.destats["nreject"], sg.destats["nf"]) == (so.naccept, so.nreject, so.nf)
+    assert rel(sg.x_filt.mu[0][:d], ref.mu[:d]) < 1e-9
+    assert rel(sg.x_filt.mu[0], ref.mu) < 1e-6
+    w, _ = block_errors(sg.x_filt.mu[0], sg.x_filt.Sigma[0], ref.mu, ref.Sigma.mat, d, q, 0.1 / max(so.naccept, 1))
+    assert w["cov"] < 1e-6
+    if diffusion == "dynamic":
+        assert abs(sg.log_likelihood - so.log_likelihood) < 1e-6 * abs(so.log_likelihood)
