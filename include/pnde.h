@@ -87,7 +87,8 @@ extern "C" {
 #define PNDE_RET_MAXITERS 1
 #define PNDE_RET_DTNAN 2
 #define PNDE_RET_NONFINITE 3
-#define PNDE_RET_HISTORY_FULL 4
+#define PNDE_RET_HISTORY_FULL 4 /* more accepted steps than cfg.max_saved slots.  Adaptive thread-per-trajectory runs keep
+                                    stepping without saving: naccept + 1 is the capacity a retry needs */
 #define PNDE_RET_DTMIN 5
 #define PNDE_RET_ZERO_RESIDUAL 6 /* only with PNDE_FLAG_REFERENCE_QUIRKS: FixedDiffusion met an exactly zero residual,
                                     where the reference throws (src/diffusions.jl:18-20) */

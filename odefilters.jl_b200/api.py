@@ -717,15 +717,19 @@ def solve(prob, alg: _EK, ensemblealg: Optional[EnsembleB200] = None, *, traject
     user_cap = max_saved
     if save_everystep and adaptive and not max_saved:
         max_saved = 1024 if ensemble else 8192
-    while True:
+    for attempt in range(8):
         solver = FilterSolver(base, alg, abstol=abstol, reltol=reltol, adaptive=adaptive, dt=dt,
                               save_everystep=save_everystep, save_stride=save_stride, maxiters=maxiters,
                               max_saved=max_saved, device=device, devices=devices, **ctrl)
         solver.solve_ensemble(u0, p)
         counts = solver.counts()
-        if (counts["retcode"] == 4).any() and not user_cap and max_saved < maxiters + 1:
+        full = counts["retcode"] == 4
+        if full.any() and not user_cap and max_saved < maxiters + 1:
+            # history full: the kernels kept stepping without saving, so naccept is what the run needs -- ONE retry
+            # with the exact capacity (the large-d path stops at a full history: grow geometrically there)
+            need = int(counts["naccept"][full].max()) + 1
             solver.close()
-            max_saved = min(max_saved * 4, maxiters + 1)  # history full: grow and redo
+            max_saved = min(max(need, max_saved * 4 if need <= max_saved else need), maxiters + 1)
             continue
         break
     if not ensemble:

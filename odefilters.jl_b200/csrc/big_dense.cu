@@ -1,5 +1,5 @@
 // Host orchestration + element-wise kernels of the large-D EK1 path (see big_dense.cuh).
-// Lorenz-96 only (the one catalogue entry with large d); fixed steps; one trajectory at a time.
+// Lorenz-96 only (the one catalogue entry with large d); fixed or adaptive steps; one trajectory at a time.
 #include "big_dense.cuh"
 
 #include <math.h>

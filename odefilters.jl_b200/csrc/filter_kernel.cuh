@@ -717,7 +717,9 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
           M::scale(nat, PIk);
           save(nat, t, gsaved);
         }
-        if (ret == RET_HISTORY_FULL) break;
+        // fixed steps: the capacity is derived from the grid, a full history is a caller error: stop.  Adaptive: keep
+        // stepping WITHOUT saving so that naccept tells the caller the capacity the run needs (one retry, api.py)
+        if (!ADAPTIVE && ret == RET_HISTORY_FULL) break;
       }
     }
   }

@@ -142,10 +142,23 @@ const ModelOps* make_ops() {
   return &ops;
 }
 
+// D = 8 (q = 3, d = 2): experiment switch PNDE_WIDE_SMOOTH=1 runs the four-lane smoother instead of the one-thread one
+template <class VF, int Q>
+cudaError_t launch_smooth_try_wide_t(const ModelOps* self, const SmoothParams& sp, cudaStream_t s) {
+  static const bool wide = getenv("PNDE_WIDE_SMOOTH") && atoi(getenv("PNDE_WIDE_SMOOTH")) != 0;
+  if (wide) return launch_smooth_wide_t<VF, Q>(self, sp, s);
+  return launch_smooth_t<DenseEK1<VF, Q>>(self, sp, s);
+}
+
 template <class VF, int Q>
 const ModelOps* make_ops_ek1() {
   using M = DenseEK1<VF, Q>;
-  if constexpr (M::D >= 10 && VF::d % 2 == 0) {
+  if constexpr (M::D == 8 && VF::d == 2) {
+    static const ModelOps ops = {M::d, M::q, M::D, M::ND, M::REC, SmoothModel<M>::SREC, M::VF::np, SamplePrep<M>::LEN, true,
+                                 &launch_filter_t<M>, &launch_convert_t<M>, &launch_smooth_try_wide_t<VF, Q>,
+                                 &launch_sample_t<M>, &launch_dense_t<M>, &launch_step_t<M>};
+    return &ops;
+  } else if constexpr (M::D >= 10 && VF::d % 2 == 0) {
     static const ModelOps ops = {M::d, M::q, M::D, M::ND, M::REC, SmoothModel<M>::SREC, M::VF::np, SamplePrep<M>::LEN, true,
                                  &launch_filter_wide_t<VF, Q>, &launch_convert_t<M>, &launch_smooth_wide_t<VF, Q>,
                                  &launch_sample_t<M>, &launch_dense_t<M>, &launch_step_t<M>};

@@ -536,8 +536,8 @@ __global__ void __launch_bounds__(PNDE_WIDE_BLOCK, 1) wide_filter_kernel(const F
 
   auto save = [&](const typename M::State& sv, const double (&sc)[q + 1], double tt, const double (&g)[ND]) {
     if (nsaved >= prm.max_saved) {
-      ret = RET_HISTORY_FULL;
-      stopped = true;
+      ret = RET_HISTORY_FULL;  // adaptive runs keep stepping without saving: naccept is the capacity the run needs
+      if (!ADAPTIVE) stopped = true;
       return;
     }
     double* base = prm.hist + ((long long)nsaved * REC) * n + tid;

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(PNDE_WSMOOTH_BLOCK, 1) wide_smoother_kernel(co
   using W = WideSmooth<VF, q_>;
   using M = typename W::M;
   using SC = typename W::SC;
-  constexpr int d = W::d, q = W::q, D = W::D, R = W::R, NP = W::NP, G = W::G, CL = W::CL, DL = W::DL, KL = W::KL, ST = W::ST;
+  constexpr int d = W::d, q = W::q, D = W::D, R = W::R, G = W::G, CL = W::CL, DL = W::DL, KL = W::KL, ST = W::ST;
   constexpr int REC = M::REC, SREC = SmoothModel<M>::SREC;
   extern __shared__ double wsm[];
   if (blockDim.x != ST) __trap();
