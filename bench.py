@@ -432,7 +432,7 @@ def main():
             got = mean_pin[:2, :n_cpu].numpy().T
             sc = np.abs(ref_mean[:, :2]).max(axis=1)
             per = np.abs(got - ref_mean[:, :2]).max(axis=1) / sc
-            n_own = min(n_cpu, 8000)
+            n_own = n_cpu  # the same sample: the maximum of a heavy-tailed quantity grows with the sample size
             rng = np.random.default_rng(1)
             p_ulp = p_np[:, :n_own] * (1 + 2.2e-16 * rng.choice([-1.0, 0.0, 1.0], (3, n_own)))
             own_mean = cpu_reference_run(n_own, inputs=(u0_np[:, :n_own], p_ulp))[4]
