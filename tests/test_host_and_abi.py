@@ -178,3 +178,28 @@ def test_strided_sharding_covers_the_ensemble_once():
     assert max(len(x) for x in parts) - min(len(x) for x in parts) <= 1
     with pytest.raises(ValueError):
         B.shard_strided(n, 4, 4)
+
+
+def test_multi_device_config_errors_without_a_gpu():
+    """cfg.n_devices / device_list (ABI version 2) are validated before any device is touched."""
+    import odefilters_b200 as B
+    from odefilters_b200 import _lib
+
+    prob = B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 1.0), (0.2, 0.2, 3.0))
+    with pytest.raises(RuntimeError, match="twice"):
+        B.FilterSolver(prob, B.EK1(order=3, smooth=False), save_everystep=False, devices=[0, 0])
+    with pytest.raises(ValueError, match="devices"):
+        B.FilterSolver(prob, B.EK1(order=3, smooth=False), save_everystep=False, devices=list(range(_lib.MAX_DEVICES + 1)))
+    assert isinstance(B.api.device_count(), int)
+    assert B.EnsembleB200(devices=[0, 1]).devices == [0, 1] and B.EnsembleB200().devices is None
+
+
+def test_header_constants_match_the_python_binding():
+    from odefilters_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "pnde.h")).read()
+    get = lambda name: int(re.search(rf"#define {name} (-?\d+)", hdr).group(1))  # noqa: E731
+    assert get("PNDE_ABI_VERSION") == _lib.ABI_VERSION and get("PNDE_MAX_DEVICES") == _lib.MAX_DEVICES
+    assert get("PNDE_FLAG_REFERENCE_QUIRKS") == _lib.FLAG_REFERENCE_QUIRKS and get("PNDE_FLAG_ONE_THREAD") == _lib.FLAG_ONE_THREAD
+    assert get("PNDE_RET_ZERO_RESIDUAL") == 6 and _lib.RETCODES[6] == "ZeroResidual"
+    assert get("PNDE_ALG_IEKS") == _lib.ALG_IEKS and get("PNDE_SAVE_STRIDE") == _lib.SAVE_STRIDE
