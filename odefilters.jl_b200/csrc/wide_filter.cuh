@@ -346,7 +346,16 @@ struct WideEK1 {
 #pragma unroll
         for (int al = 0; al < DL; ++al) {
           const int ps = kk * DL + al;
-          if (kk == kc && al * G + G - 1 < ac) continue;  // this slot is in front of the pivot in every lane
+          if (kk == kc && al * G + G - 1 < ac) {  // this slot is in front of the pivot in every lane: R[c][j] = 0
+            if (c < d) {
+              RtopL[c][ps] = 0.0;
+            } else if (c < 2 * d) {
+              s.S[0 * DL + al][c - d] = 0.0;  // (kk == kc == 1)
+            } else if (nzb(kk, c - d)) {
+              s.S[kk * DL + al][c - d] = 0.0;
+            }
+            continue;
+          }
           // j > c ?  (decided at compile time except inside the pivot's own block)
           const bool behind = (kk > kc) || (al > ac / G) || (al == ac / G && g > oc);
           const bool is_c = (kk == kc) && (al == ac / G) && (g == oc);
