@@ -321,7 +321,8 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
     std::string rerr;
     ops = rtc_build(cfg->alg, cfg->order, cfg->diffusion == PNDE_DIFF_DYNAMIC_MV, custom->d, custom->np, custom->f_body,
                     custom->jac_body, rerr, as_ieks, cfg->adaptive ? 1 : 0,
-                    (cfg->flags & PNDE_FLAG_REFERENCE_QUIRKS) && cfg->diffusion == PNDE_DIFF_FIXED);
+                    (cfg->flags & PNDE_FLAG_REFERENCE_QUIRKS) && cfg->diffusion == PNDE_DIFF_FIXED,
+                    !(cfg->flags & PNDE_FLAG_ONE_THREAD));
     if (!ops) {
       g_create_error = rerr;
       return PNDE_ERR_ARG;
@@ -329,7 +330,9 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
     owns = true;
     // adaptive kernels park the pre-step state in shared memory (STATE_LEN x 128 doubles per CTA): refuse what
     // cannot be launched now instead of failing at the first pnde_run with an opaque "invalid value"
-    const size_t stash = (size_t)(ops->rec - 1 - ops->nd) * 128 * sizeof(double);
+    const bool lanes = cfg->alg == PNDE_ALG_EK1 && !as_ieks && ops->D >= 10 && ops->d % 2 == 0 && !(cfg->flags & PNDE_FLAG_ONE_THREAD) &&
+                       !((cfg->flags & PNDE_FLAG_REFERENCE_QUIRKS) && cfg->diffusion == PNDE_DIFF_FIXED);
+    const size_t stash = (size_t)(ops->rec - 1 - ops->nd) * 128 * sizeof(double) / (lanes ? 2 : 1) + (lanes ? (size_t)64 * (ops->D * (ops->D - ops->d) + cfg->order + 1) * 8 : 0);
     if (cfg->adaptive && stash > 227 * 1024) {
       rtc_destroy(ops);
       g_create_error = "adaptive steps with d = " + std::to_string(custom->d) + ", order = " + std::to_string(cfg->order) +

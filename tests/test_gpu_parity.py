@@ -486,19 +486,23 @@ LV_SRC = dict(d=2, n_params=4,
               jac="J[0][0] = p[0]-p[1]*u[1]; J[0][1] = -p[1]*u[0]; J[1][0] = p[3]*u[1]; J[1][1] = -p[2]+p[3]*u[0];")
 
 
-@pytest.mark.parametrize("kind,smooth", [("EK1", True), ("EK0", False)])
-def test_custom_vector_field_equals_catalogue(kind, smooth):
-    """The same ODE through NVRTC and through the built-in catalogue runs the same kernel template."""
+@pytest.mark.parametrize("kind,smooth,order", [("EK1", True, 3), ("EK0", False, 3), ("EK1", True, 5)])
+def test_custom_vector_field_equals_catalogue(kind, smooth, order):
+    """The same ODE through NVRTC and through the built-in catalogue runs the same kernel template (order 5: the
+    lane-group filter and smoother, compiled at run time for the user's field like for the catalogue)."""
     import odefilters_b200 as B
 
-    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=3, smooth=smooth)
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=order, smooth=smooth)
     u0, p = PROBLEMS["lotka_volterra"]
     a = B.solve(B.ODEProblem("lotka_volterra", u0, (0.0, 2.0), p), alg)
     b = B.solve(B.ODEProblem(B.CustomVectorField(**LV_SRC), u0, (0.0, 2.0), p), alg)
     assert a.destats == b.destats and np.array_equal(a.t, b.t)
-    assert rel(b.x_filt.mu, a.x_filt.mu) < 1e-13 and rel(b.x_filt.Sigma, a.x_filt.Sigma) < 1e-10
+    assert rel(b.x_filt.mu[:, :2], a.x_filt.mu[:, :2]) < 1e-13
+    assert rel(b.x_filt.mu, a.x_filt.mu) < (1e-13 if order <= 3 else 1e-9)
+    assert rel(b.x_filt.Sigma, a.x_filt.Sigma) < (1e-10 if order <= 3 else 1e-7)
     if smooth:
-        assert rel(b.x_smooth.mu, a.x_smooth.mu) < 1e-12
+        assert rel(b.x_smooth.mu[:, :2], a.x_smooth.mu[:, :2]) < 1e-12
+        assert rel(b.x_smooth.mu, a.x_smooth.mu) < (1e-12 if order <= 3 else 1e-6)
         assert b(0.77).mu.shape == (2,) and rel(b(0.77).mu, a(0.77).mu) < 1e-12   # dense output kernel via NVRTC
         assert b.sample(3, seed=1).shape == (len(b), 2, 3)
 
