@@ -496,8 +496,10 @@ def test_custom_vector_field_equals_catalogue(kind, smooth, order):
     u0, p = PROBLEMS["lotka_volterra"]
     a = B.solve(B.ODEProblem("lotka_volterra", u0, (0.0, 2.0), p), alg)
     b = B.solve(B.ODEProblem(B.CustomVectorField(**LV_SRC), u0, (0.0, 2.0), p), alg)
-    assert a.destats == b.destats and np.array_equal(a.t, b.t)
-    assert rel(b.x_filt.mu[:, :2], a.x_filt.mu[:, :2]) < 1e-13
+    assert a.destats == b.destats
+    # (order 5: nvcc and NVRTC contract a few products differently, the adaptive grid then agrees to rounding, not bitwise)
+    assert np.array_equal(a.t, b.t) if order <= 3 else np.allclose(a.t, b.t, rtol=1e-9, atol=0)
+    assert rel(b.x_filt.mu[:, :2], a.x_filt.mu[:, :2]) < (1e-13 if order <= 3 else 1e-9)
     assert rel(b.x_filt.mu, a.x_filt.mu) < (1e-13 if order <= 3 else 1e-9)
     assert rel(b.x_filt.Sigma, a.x_filt.Sigma) < (1e-10 if order <= 3 else 1e-7)
     if smooth:
