@@ -21,13 +21,13 @@ __global__ void __launch_bounds__(128) convert_kernel(const ConvertParams c) {
   const long long o = c.offsets[tr - c.traj_begin] + slot;
   if (c.t) c.t[o] = base[0];
   double g[ND];
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < ND; ++i) g[i] = c.calibrate ? c.final_diff[(long long)i * n + tr] : base[(long long)(1 + i) * n];
   if (c.diffusion) {
     for (int i = 0; i < c.nd_out; ++i) c.diffusion[o * c.nd_out + i] = (i < ND) ? g[i] : g[0];
   }
   double dimscale[d];
-#pragma unroll
+PNDE_UNROLL
   for (int a = 0; a < d; ++a) dimscale[a] = c.calibrate ? (c.is_mv ? g[a < ND ? a : 0] : g[0]) : 1.0;
   // full packed covariance into registers/local, then emit what was asked for
   double mean[D];
@@ -35,14 +35,14 @@ __global__ void __launch_bounds__(128) convert_kernel(const ConvertParams c) {
   if (c.which == 0) {
     typename M::State st;
     M::load(st, base + (long long)(1 + ND) * n, n);
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) mean[i] = st.m[i];
     double sc[q + 1];
-#pragma unroll
+PNDE_UNROLL
     for (int k = 0; k <= q; ++k) sc[k] = 1.0;
     if constexpr (M::IS_EK1) {
       const double gs = sqrt(dimscale[0]);
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k <= q; ++k) sc[k] = gs;
       M::final_cov(st, sc, cov, 1);
     } else {

@@ -22,6 +22,16 @@
 #include <cuda_runtime.h>
 #endif
 
+// Every loop over matrix entries is written `PNDE_UNROLL for (...)`.  Ahead-of-time and small run-time compiled models
+// unroll them completely (all entries become named registers: the design of these kernels).  PNDE_ROLLED keeps them as
+// loops over arrays in local memory: the general-(d, q) fallback of rtc_model.cu for user ODEs whose state is too large
+// to unroll (d > 8 with EK1, d > 16 with EK0) -- every kernel then works for any dimension, slowly.
+#ifdef PNDE_ROLLED
+#define PNDE_UNROLL _Pragma("unroll 1")
+#else
+#define PNDE_UNROLL _Pragma("unroll")
+#endif
+
 namespace pnde {
 
 constexpr int QMAX = 7;
@@ -63,12 +73,12 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // x <- A x with A = Atilde (x) I_dc, Atilde[i][j] = 1/(j-i)!  (src/priors.jl:15-27).
 template <int dc, int q>
 __device__ __forceinline__ void apply_A(double (&x)[dc * (q + 1)]) {
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k <= q; ++k) {
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < dc; ++a) {
       double acc = x[k * dc + a];
-#pragma unroll
+PNDE_UNROLL
       for (int j = k + 1; j <= q; ++j)
         acc = (j - k == 1) ? acc + x[j * dc + a] : fma(inv_factorial(j - k), x[j * dc + a], acc);
       x[k * dc + a] = acc;
@@ -89,43 +99,43 @@ struct Factor {
   __host__ __device__ static constexpr int lz(int j, int i) { return j * NZ - (j * (j - 1)) / 2 + (i - j); }
 
   __device__ __forceinline__ void zero() {
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < dc; ++a)
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) W[a][i] = 0.0;
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < NLZ; ++i) Lz[i] = 0.0;
   }
   // rows of block k scaled by s[k]  (Diagonal * SRGaussian, src/ProbNumDiffEq.jl:58)
   __device__ __forceinline__ void scale_blocks(const double (&s)[q + 1]) {
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < dc; ++a)
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) W[a][i] *= s[i / dc];
-#pragma unroll
+PNDE_UNROLL
     for (int j = 0; j < NZ; ++j)
-#pragma unroll
+PNDE_UNROLL
       for (int i = j; i < NZ; ++i) Lz[lz(j, i)] *= s[(2 * dc + i) / dc];
   }
   // rows of coordinate a scaled by s[a] (apply_diffusion with a Diagonal, src/ProbNumDiffEq.jl:38)
   __device__ __forceinline__ void scale_all(double s) {
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < dc; ++a)
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) W[a][i] *= s;
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < NLZ; ++i) Lz[i] *= s;
   }
   // packed lower triangle (by rows) of  diag(s) S S' diag(s),  s[k] per block
   __device__ __forceinline__ void cov_entry_all(const double (&s)[q + 1], double* out, long long stride) const {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) {
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j <= i; ++j) {
         double acc = 0.0;
-#pragma unroll
+PNDE_UNROLL
         for (int a = 0; a < dc; ++a) acc = fma(W[a][i], W[a][j], acc);
-#pragma unroll
+PNDE_UNROLL
         for (int c = 0; c < NZ; ++c) {
           if (i >= 2 * dc + c && j >= 2 * dc + c) acc = fma(Lz[lz(c, i - 2 * dc)], Lz[lz(c, j - 2 * dc)], acc);
         }
@@ -135,20 +145,20 @@ struct Factor {
   }
   __device__ __forceinline__ void store(double* base, long long stride) const {
     int o = 0;
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < dc; ++a)
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) base[(long long)(o++) * stride] = W[a][i];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < (NZ > 0 ? NZ * (NZ + 1) / 2 : 0); ++i) base[(long long)(o++) * stride] = Lz[i];
   }
   __device__ __forceinline__ void load(const double* base, long long stride) {
     int o = 0;
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < dc; ++a)
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) W[a][i] = base[(long long)(o++) * stride];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < (NZ > 0 ? NZ * (NZ + 1) / 2 : 0); ++i) Lz[i] = base[(long long)(o++) * stride];
     if (NZ == 0) Lz[0] = 0.0;
   }
@@ -165,16 +175,16 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
   constexpr int D = dc * (q + 1);
   constexpr int NZ = D - 2 * dc;
   double sL[q + 1][2 > q + 1 ? 2 : q + 1];  // sig * Ltilde[k][k']
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k <= q; ++k)
-#pragma unroll
+PNDE_UNROLL
     for (int kk = 0; kk <= k; ++kk) sL[k][kk] = sig * C.Lt[k][kk];
 
   double E[D][D];
   // rows 0..dc-1: the prior rows of block 0, the only non-triangular part of sig (T Q_L)'
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < dc; ++i) {
-#pragma unroll
+PNDE_UNROLL
     for (int j = 0; j < D; ++j) {
       if (j < dc) {
         double v = (i == j) ? pi1 * sL[1][0] : 0.0;
@@ -187,38 +197,38 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
     }
   }
   // bottom rows: (T A s)' for every factor column s
-#pragma unroll
+PNDE_UNROLL
   for (int c = 0; c < dc; ++c) {
     double w[D];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) w[i] = F.W[c][i];
     apply_A<dc, q>(w);
-#pragma unroll
+PNDE_UNROLL
     for (int b = 0; b < dc; ++b) {
       double y = pi1 * w[dc + b];
       if (HASJ) {
-#pragma unroll
+PNDE_UNROLL
         for (int bb = 0; bb < dc; ++bb) y = fma(-Jp[b][bb], w[bb], y);
       }
       E[dc + c][b] = y;
       E[dc + c][dc + b] = w[b];
     }
-#pragma unroll
+PNDE_UNROLL
     for (int i = 2 * dc; i < D; ++i) E[dc + c][i] = w[i];
   }
-#pragma unroll
+PNDE_UNROLL
   for (int c = 0; c < NZ; ++c) {
     double w[D];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) w[i] = (i >= 2 * dc + c) ? F.Lz[Factor<dc, q>::lz(c, i - 2 * dc)] : 0.0;
     // A w, skipping the structurally zero entries below 2dc+c (c is a compile-time constant here)
-#pragma unroll
+PNDE_UNROLL
     for (int k = 0; k <= q; ++k) {
-#pragma unroll
+PNDE_UNROLL
       for (int a = 0; a < dc; ++a) {
         bool any = (k * dc + a >= 2 * dc + c);
         double acc = any ? w[k * dc + a] : 0.0;
-#pragma unroll
+PNDE_UNROLL
         for (int j = k + 1; j <= q; ++j) {
           if (j * dc + a >= 2 * dc + c) {
             const double cf = inv_factorial(j - k);
@@ -233,22 +243,22 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
         w[k * dc + a] = acc;
       }
     }
-#pragma unroll
+PNDE_UNROLL
     for (int b = 0; b < dc; ++b) {
       double y = pi1 * w[dc + b];
       if (HASJ) {
-#pragma unroll
+PNDE_UNROLL
         for (int bb = 0; bb < dc; ++bb) y = fma(-Jp[b][bb], w[bb], y);
       }
       E[2 * dc + c][b] = y;
       E[2 * dc + c][dc + b] = w[b];
     }
-#pragma unroll
+PNDE_UNROLL
     for (int i = 2 * dc; i < D; ++i) E[2 * dc + c][i] = w[i];
   }
 
   // Householder sweep over the primed columns
-#pragma unroll
+PNDE_UNROLL
   for (int c = 0; c < D; ++c) {
     const int first = (c < dc) ? 0 : (c < 2 * dc ? c - dc + 1 : dc);  // active dense rows [first, D)
     const int kc = c / dc, ac = c % dc;
@@ -261,7 +271,7 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
       pv = sL[kc][kc];
     // squared norm in two interleaved chains (halves the dependent-FMA latency)
     double n2a = pv * pv, n2b = E[first][c] * E[first][c];
-#pragma unroll
+PNDE_UNROLL
     for (int i = first + 1; i < D; ++i) {
       if ((i - first) & 1)
         n2a = fma(E[i][c], E[i][c], n2a);
@@ -277,7 +287,7 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
     const double beta = nzcol ? fast_rcp(fma(fabs(pv), nrm, n2)) : 0.0;  // 1 / (||x|| (||x|| + |pv|))
     double Rrow[D];
     Rrow[c] = -snrm;
-#pragma unroll
+PNDE_UNROLL
     for (int j = c + 1; j < D; ++j) {
       // pivot-row entry (compile-time sparsity for the prior rows)
       bool pnz;
@@ -295,7 +305,7 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
       double w = pnz ? v0 * prj : 0.0;
       bool started = pnz;
       {
-#pragma unroll
+PNDE_UNROLL
         for (int i = first; i < D; ++i) {
           if (!started) {
             w = E[i][c] * E[i][j];
@@ -307,34 +317,34 @@ __device__ __forceinline__ void cov_filter_step(Factor<dc, q>& F, const double (
       }
       const double s = beta * w;
       Rrow[j] = pnz ? fma(-s, v0, prj) : -s * v0;
-#pragma unroll
+PNDE_UNROLL
       for (int i = first; i < D; ++i) E[i][j] = fma(-s, E[i][c], E[i][j]);
     }
     // consume the finished row of R
     if (c < dc) {
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j < D; ++j) Rtop[c][j] = (j >= c) ? Rrow[j] : 0.0;
       Rinv[c] = -copysign(rn, pv);  // 1 / R[c][c] (0 for a zero column)
     } else if (c < 2 * dc) {
       const int a = c - dc;
-#pragma unroll
+PNDE_UNROLL
       for (int b = 0; b < dc; ++b) F.W[a][b] = (b >= a) ? Rrow[dc + b] : 0.0;
-#pragma unroll
+PNDE_UNROLL
       for (int i = 2 * dc; i < D; ++i) F.W[a][i] = Rrow[i];
     } else {
       const int j0 = c - 2 * dc;
-#pragma unroll
+PNDE_UNROLL
       for (int i = j0; i < NZ; ++i) F.Lz[Factor<dc, q>::lz(j0, i)] = Rrow[2 * dc + i];
     }
   }
   // block 1 of the posterior factor is slaved to block 0: x_1 = (Jp x_0) / pi1  (H S+ = 0)
-#pragma unroll
+PNDE_UNROLL
   for (int a = 0; a < dc; ++a) {
-#pragma unroll
+PNDE_UNROLL
     for (int b = 0; b < dc; ++b) {
       double v = 0.0;
       if (HASJ) {
-#pragma unroll
+PNDE_UNROLL
         for (int bb = 0; bb < dc; ++bb) v = fma(Jp[b][bb], F.W[a][bb], v);
         v *= ipi1;
       }

@@ -82,7 +82,7 @@ __device__ __forceinline__ void precond_scales(double h, double (&P)[q + 1], dou
   // PI_k = h^(q+1/2-k): PI_q = sqrt(h), PI_{k-1} = PI_k * h
   double v = sqrt(h);
   PI[q] = v;
-#pragma unroll
+PNDE_UNROLL
   for (int k = q - 1; k >= 0; --k) {
     v *= h;
     PI[k] = v;
@@ -91,7 +91,7 @@ __device__ __forceinline__ void precond_scales(double h, double (&P)[q + 1], dou
   const double ih = 1.0 / h;
   double w = 1.0 / PI[q];
   P[q] = w;
-#pragma unroll
+PNDE_UNROLL
   for (int k = q - 1; k >= 0; --k) {
     w *= ih;
     P[k] = w;
@@ -162,7 +162,7 @@ struct DenseEK1 {
   };
 
   __device__ __forceinline__ static void scale(State& s, const double (&sc)[q + 1]) {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) s.m[i] *= sc[i / d];
     s.F.scale_blocks(sc);
   }
@@ -176,24 +176,24 @@ struct DenseEK1 {
                                               const double* ulin = nullptr) {
     apply_A<d, q>(s.m);  // predict_mean!  src/filtering.jl:22-25
     double uhat[d], fu[d], J[d][d], Jp[d][d], z[d];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) uhat[i] = pi0 * s.m[i];  // src/perform_step.jl:44
     VF::template f<double>(uhat, p, fu);                  // :106
     VF::jac(ulin ? ulin : uhat, p, J);                    // :111-122 (IEKS: at the previous iterate's sol(t))
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) {
       z[i] = fma(pi1, s.m[d + i], -fu[i]);  // :108
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j < d; ++j) Jp[i][j] = pi0 * J[i][j];
     }
     // B = H Q H' with H = (E1 - J E0) P^-1  (:125; src/diffusions.jl:77)
     double B[d][d];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) {
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j <= i; ++j) {
         double acc = 0.0;
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < d; ++k) acc = fma(Jp[i][k], Jp[j][k], acc);
         acc *= C.Qt[0][0];
         acc = fma(-pi1 * C.Qt[0][1], Jp[i][j] + Jp[j][i], acc);
@@ -207,22 +207,22 @@ struct DenseEK1 {
       // sigma^2 = z' B^-1 z / d via Cholesky of the d x d matrix (src/diffusions.jl:77-79)
       double Lb[d][d], yb[d];
       double ss = 0.0;
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j < d; ++j) {
         double djj = B[j][j];
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < j; ++k) djj = fma(-Lb[j][k], Lb[j][k], djj);
         const double il = (djj > 0.0) ? fast_rsqrt(djj) : 0.0;
         Lb[j][j] = djj * il;
-#pragma unroll
+PNDE_UNROLL
         for (int i = j + 1; i < d; ++i) {
           double v = B[i][j];
-#pragma unroll
+PNDE_UNROLL
           for (int k = 0; k < j; ++k) v = fma(-Lb[i][k], Lb[j][k], v);
           Lb[i][j] = v * il;
         }
         double yy = z[j];
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < j; ++k) yy = fma(-Lb[j][k], yb[k], yy);
         yb[j] = yy * il;
         ss = fma(yb[j], yb[j], ss);
@@ -235,10 +235,10 @@ struct DenseEK1 {
     // innovation: S_z = G G', G = Rtop[:, :d]' lower triangular; y = G^-1 z
     double y[d];
     double yy2 = 0.0, dets = 1.0;
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < d; ++a) {
       double acc = z[a];
-#pragma unroll
+PNDE_UNROLL
       for (int b = 0; b < a; ++b) acc = fma(-Rtop[b][a], y[b], acc);
       y[a] = acc * Rinv[a];
       yy2 = fma(y[a], y[a], yy2);
@@ -249,29 +249,29 @@ struct DenseEK1 {
     if (diffusion != DIFF_DYNAMIC) local[0] = yy2 * (1.0 / double(d));  // src/diffusions.jl:25,52
     // mean update: mu+ = mu- - K z  (src/filtering.jl:87) in primed coordinates
     double m0old[d];
-#pragma unroll
+PNDE_UNROLL
     for (int b = 0; b < d; ++b) {
       m0old[b] = s.m[b];
       double acc = s.m[b];
-#pragma unroll
+PNDE_UNROLL
       for (int a = 0; a < d; ++a) acc = fma(-Rtop[a][d + b], y[a], acc);
       s.m[b] = acc;
     }
-#pragma unroll
+PNDE_UNROLL
     for (int i = 2 * d; i < D; ++i) {
       double acc = s.m[i];
-#pragma unroll
+PNDE_UNROLL
       for (int a = 0; a < d; ++a) acc = fma(-Rtop[a][i], y[a], acc);
       s.m[i] = acc;
     }
-#pragma unroll
+PNDE_UNROLL
     for (int b = 0; b < d; ++b) {
       double acc = fu[b];
-#pragma unroll
+PNDE_UNROLL
       for (int bb = 0; bb < d; ++bb) acc = fma(Jp[b][bb], s.m[bb] - m0old[bb], acc);
       s.m[d + b] = acc * ipi1;
     }
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) {
       u_new[i] = pi0 * s.m[i];              // src/perform_step.jl:70
       err[i] = sqrt(local[0] * B[i][i]);    // :155
@@ -279,12 +279,12 @@ struct DenseEK1 {
   }
 
   __device__ __forceinline__ static void store(const State& s, double* base, long long stride) {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) base[(long long)i * stride] = s.m[i];
     s.F.store(base + (long long)D * stride, stride);
   }
   __device__ __forceinline__ static void load(State& s, const double* base, long long stride) {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) s.m[i] = base[(long long)i * stride];
     s.F.load(base + (long long)D * stride, stride);
   }
@@ -315,9 +315,9 @@ struct KronEK0 {
   };
 
   __device__ __forceinline__ static void scale(State& s, const double (&sc)[q + 1]) {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) s.m[i] *= sc[i / d];
-#pragma unroll
+PNDE_UNROLL
     for (int f = 0; f < NF; ++f) s.F[f].scale_blocks(sc);
   }
 
@@ -327,11 +327,11 @@ struct KronEK0 {
                                               const double* = nullptr) {
     apply_A<d, q>(s.m);
     double uhat[d], fu[d], z[d];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) uhat[i] = pi0 * s.m[i];
     VF::template f<double>(uhat, p, fu);
     double zz = 0.0;
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) {
       z[i] = fma(pi1, s.m[d + i], -fu[i]);
       zz = fma(z[i], z[i], zz);
@@ -341,7 +341,7 @@ struct KronEK0 {
     double R[NF][1][q + 1], Ri[NF][1];
     if (MVDYN) {
       // src/diffusions.jl:104-108: Sigma_ii = max(z_i^2 / Q0_11, eps)
-#pragma unroll
+PNDE_UNROLL
       for (int a = 0; a < d; ++a) {
         local[a] = fmax(z[a] * z[a] / B, 2.220446049250313e-16);
         cov_filter_step<1, q, false>(s.F[a < NF ? a : 0], Jp0, sqrt(local[a]), pi1, ipi1, C, R[a < NF ? a : 0],
@@ -356,14 +356,14 @@ struct KronEK0 {
       cov_filter_step<1, q, false>(s.F[0], Jp0, sig, pi1, ipi1, C, R[0], Ri[0]);
     }
     double yy2 = 0.0, dets = 1.0;
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < d; ++a) {
       const int f = MVDYN ? a : 0;
       const double ya = z[a] * Ri[f][0];
       yy2 = fma(ya, ya, yy2);
       dets *= fabs(R[f][0][0]);
       s.m[a] = fma(-R[f][0][1], ya, s.m[a]);
-#pragma unroll
+PNDE_UNROLL
       for (int k = 2; k <= q; ++k) s.m[k * d + a] = fma(-R[f][0][k], ya, s.m[k * d + a]);
       s.m[d + a] = fu[a] * ipi1;
     }
@@ -372,10 +372,10 @@ struct KronEK0 {
     if (diffusion == DIFF_FIXED || diffusion == DIFF_FIXED_MAP) local[0] = yy2 / double(d);
     if (diffusion == DIFF_FIXED_MV) {
       const double S11 = R[0][0][0] * R[0][0][0];  // src/diffusions.jl:136-138
-#pragma unroll
+PNDE_UNROLL
       for (int a = 0; a < d; ++a) local[a] = z[a] * z[a] / S11;
     }
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) {
       u_new[i] = pi0 * s.m[i];
       const bool mv = (diffusion == DIFF_DYNAMIC_MV || diffusion == DIFF_FIXED_MV);
@@ -384,15 +384,15 @@ struct KronEK0 {
   }
 
   __device__ __forceinline__ static void store(const State& s, double* base, long long stride) {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) base[(long long)i * stride] = s.m[i];
-#pragma unroll
+PNDE_UNROLL
     for (int f = 0; f < NF; ++f) s.F[f].store(base + (long long)(D + f * Fac::LEN) * stride, stride);
   }
   __device__ __forceinline__ static void load(State& s, const double* base, long long stride) {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) s.m[i] = base[(long long)i * stride];
-#pragma unroll
+PNDE_UNROLL
     for (int f = 0; f < NF; ++f) s.F[f].load(base + (long long)(D + f * Fac::LEN) * stride, stride);
   }
   // calibration by the final global diffusion (src/integrator_utils.jl:7-12): scalar or per dimension
@@ -400,18 +400,18 @@ struct KronEK0 {
   __device__ __forceinline__ static void final_cov(const State& s, const double (&sc)[q + 1], double* cov,
                                                    long long stride, const double (&dimscale)[d]) {
     // Sigma[(k,a),(k',a')] = delta_aa' * dimscale[a] * sc[k] sc[k'] * (F_a F_a')[k][k']
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) {
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j <= i; ++j) {
         const int ki = i / d, ai = i % d, kj = j / d, aj = j % d;
         double v = 0.0;
         if (ai == aj) {
           const Fac& F = s.F[MVDYN ? ai : 0];
           // rows of the 1-d factor: row 0 = block 0, row 1 = block 1, ...
-#pragma unroll
+PNDE_UNROLL
           for (int c = 0; c < 1; ++c) v = fma(F.W[c][ki], F.W[c][kj], v);
-#pragma unroll
+PNDE_UNROLL
           for (int c = 0; c < Fac::NZ; ++c)
             if (ki >= 2 + c && kj >= 2 + c) v = fma(F.Lz[Fac::lz(c, ki - 2)], F.Lz[Fac::lz(c, kj - 2)], v);
           v *= sc[ki] * sc[kj] * dimscale[ai];
@@ -431,7 +431,7 @@ __device__ __forceinline__ double initdt(const double* u0, const double* p, cons
   double f0[d], f1[d], u1[d], sk[d];
   VF::template f<double>(u0, p, f0);
   double d0 = 0.0, d1 = 0.0;
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < d; ++i) {
     sk[i] = K.abstol + fabs(u0[i]) * K.reltol;
     const double a = u0[i] / sk[i], b = f0[i] / sk[i];
@@ -443,11 +443,11 @@ __device__ __forceinline__ double initdt(const double* u0, const double* p, cons
   double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
   dt0 = fmin(dt0, K.dtmax);
   if (dt0 < 10.0 * 2.220446049250313e-16) return 1e-6;
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < d; ++i) u1[i] = fma(dt0, f0[i], u0[i]);
   VF::template f<double>(u1, p, f1);
   double d2 = 0.0;
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < d; ++i) {
     const double c = (f1[i] - f0[i]) / sk[i];
     d2 = fma(c, c, d2);
@@ -485,9 +485,9 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
   const bool is_mv = (diffusion == DIFF_DYNAMIC_MV || diffusion == DIFF_FIXED_MV);
 
   double p[VF::np], u0[d];
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < VF::np; ++i) p[i] = prm.p[(long long)i * n + tid];
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < d; ++i) u0[i] = prm.u0[(long long)i * n + tid];
 
   extern __shared__ double stash[];  // ADAPTIVE only: STATE_LEN x blockDim doubles
@@ -496,17 +496,17 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
   if constexpr (M::IS_EK1) {
     st.F.zero();
   } else {
-#pragma unroll
+PNDE_UNROLL
     for (int f = 0; f < M::NF; ++f) st.F[f].zero();
   }
 
   double t = K.t0;
   int iter = 0, nacc = 0, nrej = 0, nfe = 0, ret = RET_SUCCESS, nsaved = 0;
   double gsaved[ND];  // last saved global diffusion (sol.diffusions[end])
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < ND; ++i) gsaved[i] = 1.0;  // initial_diffusion, src/diffusions.jl:8
   double uprev[d];
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < d; ++i) uprev[i] = u0[i];
   // log-likelihood (src/perform_step.jl:66,91) = -1/2 sum (quad + 2 log detS + d log 2pi) over committed
   // steps; the log of the running product of detS is taken lazily (mantissa / exponent split).
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
     }
     double* base = prm.hist + ((long long)nsaved * REC) * n + tid;
     base[0] = tt;
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < ND; ++i) base[(long long)(1 + i) * n] = g[i];
     M::store(sv, base + (long long)(1 + ND) * n, n);
     ++nsaved;
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
   bool accepted_prev = true;
   double hcur = -1.0;  // fixed-step mode: the h the state is currently preconditioned with (<0: natural)
   double Pk[q + 1], PIk[q + 1];
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k <= q; ++k) Pk[k] = PIk[k] = 1.0;
 
   while (t < K.t1) {
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
     } else if (dt != hcur) {
       double Pn[q + 1], PIn[q + 1], sc[q + 1];
       precond_scales<q>(dt, Pn, PIn);
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k <= q; ++k) {
         sc[k] = Pn[k] * PIk[k];
         Pk[k] = Pn[k];
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
       hcur = dt;
     }
     double unew[d], err[d], local[ND], quad, detS;
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < ND; ++i) local[i] = 1.0;
     if constexpr (LIN::enabled) {
       double ulin[d];
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
     ++nfe;
     // global diffusion (src/diffusions.jl): success_iter == number of accepted steps so far
     double gcur[ND];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < ND; ++i) {
       if (!is_mv && i > 0) {
         gcur[i] = 1.0;
@@ -632,14 +632,14 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
     if (ADAPTIVE) {
       // calculate_residuals! + ODE_DEFAULT_NORM (src/perform_step.jl:78-84)
       double acc = 0.0;
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < d; ++i) {
         const double r = dt * err[i] / (K.abstol + fmax(fabs(uprev[i]), fabs(unew[i])) * K.reltol);
         acc = fma(r, r, acc);
       }
       EEst = sqrt(acc / double(d));
     }
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) {
       uprev[i] = unew[i];  // integ.u .= u_filt, even when rejected (:86)
       finite = finite && (fabs(unew[i]) <= 1.79769313486231570e308);
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
     }
     accepted_prev = accept;
     if (accept) {
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < ND; ++i) gsaved[i] = gcur[i];
       // savevalues! (src/integrator_utils.jl:33-48)
       const bool want = (prm.save_mode == SAVE_EVERY) ||
@@ -726,20 +726,20 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
 
   // ---- outputs ----
   double sc[q + 1];
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k <= q; ++k) sc[k] = (ADAPTIVE || hcur < 0.0) ? 1.0 : PIk[k];
   if (prm.mean) {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) prm.mean[(long long)i * n + tid] = st.m[i] * sc[i / d];
   }
   // postamble! calibration for static models (src/integrator_utils.jl:4-18)
   double dimscale[d];
-#pragma unroll
+PNDE_UNROLL
   for (int a = 0; a < d; ++a) dimscale[a] = 1.0;
   double ll = -0.5 * (ll_quad + 2.0 * (ll_log + log(ll_mant) + double(ll_exp) * 0.6931471805599453) +
                       double(ll_n) * double(d) * 1.8378770664093453);
   if (is_static && nacc > 0) {
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < d; ++a) dimscale[a] = is_mv ? gsaved[a < ND ? a : 0] : gsaved[0];
     ll = nan("");
   }
@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
     if constexpr (M::IS_EK1) {
       double sc2[q + 1];
       const double g = sqrt(dimscale[0]);
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k <= q; ++k) sc2[k] = sc[k] * g;
       M::final_cov(st, sc2, prm.cov + tid, n);
     } else {
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(PNDE_FILTER_BLOCK, PNDE_FILTER_MINB) filter_ke
     }
   }
   if (prm.final_diff) {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < ND; ++i) prm.final_diff[(long long)i * n + tid] = gsaved[i];
   }
   if (prm.t_final) prm.t_final[tid] = t;

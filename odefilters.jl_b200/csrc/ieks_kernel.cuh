@@ -34,7 +34,7 @@ struct DenseLin {
     dp.C = prm.C;
     double mean[M::D], cov[M::D * (M::D + 1) / 2];
     dense_state<M>(dp, tr, tval, mean, cov);
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < M::d; ++i) u[i] = mean[i];  // SolProj * posterior(t)  (src/solution.jl:211-214)
     return true;
   }

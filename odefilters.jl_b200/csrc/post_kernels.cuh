@@ -36,13 +36,13 @@ struct Philox {
   __device__ __forceinline__ void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) const {
     uint32_t c[4] = {c0, c1, c2, c3};
     uint32_t k0 = key[0], k1 = key[1];
-#pragma unroll
+PNDE_UNROLL
     for (int r = 0; r < 10; ++r) {
       round(c, k0, k1);
       k0 += 0x9E3779B9u;
       k1 += 0xBB67AE85u;
     }
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < 4; ++i) out[i] = c[i];
   }
   // two independent standard normals from one block
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128) sample_prep_kernel(const SampleParams sp)
   const double h = rn[0] - ri[0];
   if (!(h > 0.0)) return;  // the draw kernel copies the sample across such an interval
   double gfin[ND];
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k < ND; ++k) gfin[k] = sp.calibrate ? sp.final_diff[(long long)k * n + tr] : 1.0;
   double Pk[q + 1], PIk[q + 1];
   precond_scales<q>(h, Pk, PIk);
@@ -146,14 +146,14 @@ __global__ void __launch_bounds__(128) sample_prep_kernel(const SampleParams sp)
   M::load(st, ri + (long long)(1 + ND) * n, n);
   M::scale(st, Pk);
   double mpred[D];
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k < D; ++k) mpred[k] = st.m[k];
   apply_A<d, q>(mpred);
   for (int k = 0; k < D; ++k) {
     o[k] = st.m[k];
     o[D + k] = mpred[k];
   }
-#pragma unroll
+PNDE_UNROLL
   for (int f = 0; f < NF; ++f) {
     // dynamic models: the interval's own diffusion; static models: the final global value.  In the Kronecker form a
     // static per-dimension scale cancels in G and multiplies Y'Y (applied by the draw kernel).
@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(128) sample_prep_kernel(const SampleParams sp)
     SC::cols_from_factor(PT::factor(st, f), cols);
     if (M::IS_EK1 && sp.calibrate) {
       const double cs = sqrt(gfin[0]);
-#pragma unroll
+PNDE_UNROLL
       for (int c = 0; c < R; ++c)
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < DCOV; ++k) cols[c][k] *= cs;
     }
     double Rm[SC::NP], rinv[DCOV];
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(128) sample_draw_kernel(const SampleParams sp)
   rng.key[0] = (uint32_t)sp.seed;
   rng.key[1] = (uint32_t)(sp.seed >> 32);
   double gfin[ND];
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < ND; ++i) gfin[i] = sp.calibrate ? sp.final_diff[(long long)i * n + tr] : 1.0;
   auto rec = [&](int slot) { return sp.hist + ((long long)slot * REC) * n + tr; };
   auto outp = [&](int slot) { return sp.out + ((sp.offsets[tr - sp.traj_begin] + slot) * sp.n_samples + smp) * D; };
@@ -218,19 +218,19 @@ __global__ void __launch_bounds__(128) sample_draw_kernel(const SampleParams sp)
     // last state: s = mu + S xi   (src/solution_sampling.jl:31-32)
     typename M::State st;
     M::load(st, rec(ns - 1) + (long long)(1 + ND) * n, n);
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) s[i] = st.m[i];
-#pragma unroll
+PNDE_UNROLL
     for (int rep = 0; rep < PT::NREP; ++rep) {
       const int f = (NF > 1) ? rep : 0;
       double cols[R][DCOV];
       SC::cols_from_factor(PT::factor(st, f), cols);
       const double cs = calib(rep);
-#pragma unroll
+PNDE_UNROLL
       for (int c = 0; c < R; c += 2) {
         double a, b;
         rng.normal2((uint32_t)(tr + sp.key_offset), (uint32_t)smp, (uint32_t)(ns - 1), (uint32_t)(rep * 64 + c), a, b);
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < DCOV; ++k) {
           s[PT::idx(rep, k)] = fma(cs * cols[c][k], a, s[PT::idx(rep, k)]);
           if (c + 1 < R) s[PT::idx(rep, k)] = fma(cs * cols[c + 1 < R ? c + 1 : 0][k], b, s[PT::idx(rep, k)]);
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128) sample_draw_kernel(const SampleParams sp)
       }
     }
     double* o = outp(ns - 1);
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) o[i] = s[i];
   }
   for (int i = ns - 2; i >= 0; --i) {
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128) sample_draw_kernel(const SampleParams sp)
       double Pk[q + 1], PIk[q + 1];
       precond_scales<q>(h, Pk, PIk);
       double snew[D];
-#pragma unroll
+PNDE_UNROLL
       for (int f = 0; f < NF; ++f) {
         const double* pf = pr + 2 * D + f * SPp::FLEN;
         const double* Rm = pf;
@@ -256,46 +256,46 @@ __global__ void __launch_bounds__(128) sample_draw_kernel(const SampleParams sp)
         const double* X = rinv + DCOV;
         const double* Y = X + DCOV * DCOV;
         constexpr int NR_ = (NF > 1) ? 1 : PT::NREP;  // replicas served by this factor
-#pragma unroll
+PNDE_UNROLL
         for (int rr = 0; rr < NR_; ++rr) {
           const int rep = (NF > 1) ? f : rr;
           // y = R-^-T (P s - m^-), delta = X' y  (the gain applied without ever forming it)
           double y[DCOV];
-#pragma unroll
+PNDE_UNROLL
           for (int k = 0; k < DCOV; ++k) {
             double acc = fma(Pk[k / DC], s[PT::idx(rep, k)], -pr[D + PT::idx(rep, k)]);
-#pragma unroll
+PNDE_UNROLL
             for (int l = 0; l < k; ++l) acc = fma(-Rm[SC::tri(k, l)], y[l], acc);
             y[k] = acc * rinv[k];
           }
           const double ys = (!M::IS_EK1 && sp.calibrate) ? calib(rep) : 1.0;
           double acc[DCOV];
-#pragma unroll
+PNDE_UNROLL
           for (int k = 0; k < DCOV; ++k) {
             double dl = 0.0;
-#pragma unroll
+PNDE_UNROLL
             for (int l = 0; l < DCOV; ++l) dl = fma(X[l * DCOV + k], y[l], dl);
             acc[k] = pr[PT::idx(rep, k)] + dl;
           }
-#pragma unroll
+PNDE_UNROLL
           for (int c = 0; c < R; c += 2) {
             double a, b;
             rng.normal2((uint32_t)(tr + sp.key_offset), (uint32_t)smp, (uint32_t)i, (uint32_t)(rep * 64 + c), a, b);
-#pragma unroll
+PNDE_UNROLL
             for (int k = 0; k < DCOV; ++k) {
               acc[k] = fma(ys * Y[c * DCOV + k], a, acc[k]);
               if (c + 1 < R) acc[k] = fma(ys * Y[(c + 1 < R ? c + 1 : 0) * DCOV + k], b, acc[k]);
             }
           }
-#pragma unroll
+PNDE_UNROLL
           for (int k = 0; k < DCOV; ++k) snew[PT::idx(rep, k)] = acc[k] * PIk[k / DC];
         }
       }
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < D; ++k) s[k] = snew[k];
     }
     double* o = outp(i);
-#pragma unroll
+PNDE_UNROLL
     for (int k = 0; k < D; ++k) o[k] = s[k];
   }
 }
@@ -327,10 +327,10 @@ __device__ __forceinline__ void dense_state(const DenseParams& dp, long long tr,
   }
   const int prev = lo;
   double gfin[ND];
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < ND; ++i) gfin[i] = dp.calibrate ? dp.final_diff[(long long)i * n + tr] : 1.0;
   double dimscale[d];
-#pragma unroll
+PNDE_UNROLL
   for (int a = 0; a < d; ++a)
     dimscale[a] = (dp.calibrate && !M::IS_EK1) ? (dp.is_mv ? gfin[a < ND ? a : 0] : gfin[0]) : 1.0;
   const double dense_cal = (dp.calibrate && M::IS_EK1) ? sqrt(gfin[0]) : 1.0;
@@ -340,10 +340,10 @@ __device__ __forceinline__ void dense_state(const DenseParams& dp, long long tr,
     } else {
       typename M::State st;
       M::load(st, rec(prev) + (long long)(1 + ND) * n, n);
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) mean[i] = st.m[i];
       double sc[q + 1];
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k <= q; ++k) sc[k] = dense_cal;
       if constexpr (M::IS_EK1) M::final_cov(st, sc, cov, 1); else M::final_cov(st, sc, cov, 1, dimscale);
     }
@@ -359,37 +359,37 @@ __device__ __forceinline__ void dense_state(const DenseParams& dp, long long tr,
     M::scale(st, Pk);
     apply_A<d, q>(st.m);
     double mp[D];
-#pragma unroll
+PNDE_UNROLL
     for (int k = 0; k < D; ++k) mp[k] = st.m[k] * PIk[k / d];  // predicted mean, natural coordinates
     double Lp[NF][SC::NP];                                    // predicted factor(s), natural coordinates
     double sig[NF];
     int status = 0;
-#pragma unroll
+PNDE_UNROLL
     for (int f = 0; f < NF; ++f) {
       const double g = dp.calibrate ? (M::IS_EK1 ? gfin[0] : 1.0) : rd[(long long)(1 + (NF > 1 ? f : 0)) * n];
       sig[f] = sqrt(g);
       double cols[R][DCOV];
       SC::cols_from_factor(PT::factor(st, f), cols);
-#pragma unroll
+PNDE_UNROLL
       for (int c = 0; c < R; ++c) {
         double w[DCOV];
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < DCOV; ++k) w[k] = cols[c][k] * dense_cal;
         apply_A<DC, q>(w);
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < DCOV; ++k) cols[c][k] = w[k];
       }
       // factor of A S S' A' + sig^2 Q: triangularise [(A S)' ; sig Q_L'] (predict, src/filtering.jl:33-48)
       double Tt[DCOV][DCOV];
-#pragma unroll
+PNDE_UNROLL
       for (int c = 0; c < DCOV; ++c)
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < DCOV; ++k)
           Tt[c][k] = (k % DC == c % DC && k >= c) ? sig[f] * dp.C.Lt[k / DC][c / DC] : 0.0;  // row c of (sig Q_L)'
       SC::template triangularize<R>(cols, Tt, Lp[f], status);
-#pragma unroll
+PNDE_UNROLL
       for (int r = 0; r < DCOV; ++r)
-#pragma unroll
+PNDE_UNROLL
         for (int c = 0; c <= r; ++c) Lp[f][SC::tri(r, c)] *= PIk[r / DC];
     }
     double ms[D];
@@ -398,20 +398,20 @@ __device__ __forceinline__ void dense_state(const DenseParams& dp, long long tr,
       const double h2 = rec(prev + 1)[0] - tval;
       precond_scales<q>(h2, Pk, PIk);
       const double* sb = dp.smooth + ((long long)(prev + 1) * SREC) * n + tr;
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < D; ++k) ms[k] = sb[(long long)k * n];
       double mcur[D], mpred[D];
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < D; ++k) mcur[k] = mp[k] * Pk[k / d];
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < D; ++k) mpred[k] = mcur[k];
       apply_A<d, q>(mpred);
-#pragma unroll
+PNDE_UNROLL
       for (int f = 0; f < NF; ++f) {
         double Ls[SC::NP];
-#pragma unroll
+PNDE_UNROLL
         for (int r = 0; r < DCOV; ++r)
-#pragma unroll
+PNDE_UNROLL
           for (int c = 0; c <= r; ++c) {
             Ls[SC::tri(r, c)] = sb[(long long)(D + f * SC::NP + SC::tri(r, c)) * n] * Pk[r / DC];
             Lp[f][SC::tri(r, c)] *= Pk[r / DC];
@@ -420,44 +420,44 @@ __device__ __forceinline__ void dense_state(const DenseParams& dp, long long tr,
         SC::cols_from_lower(Lp[f], cols);
         constexpr int NR_ = (NF > 1) ? 1 : PT::NREP;
         double delta[NR_][DCOV];
-#pragma unroll
+PNDE_UNROLL
         for (int rr = 0; rr < NR_; ++rr) {
           const int rep = (NF > 1) ? f : rr;
-#pragma unroll
+PNDE_UNROLL
           for (int k = 0; k < DCOV; ++k)
             delta[rr][k] = fma(Pk[k / DC], ms[PT::idx(rep, k)], -mpred[PT::idx(rep, k)]);
         }
         SC::template step_cols<DCOV, NR_>(cols, sig[f], dp.C, Ls, delta, status);
-#pragma unroll
+PNDE_UNROLL
         for (int rr = 0; rr < NR_; ++rr) {
           const int rep = (NF > 1) ? f : rr;
-#pragma unroll
+PNDE_UNROLL
           for (int k = 0; k < DCOV; ++k)
             mp[PT::idx(rep, k)] = (mcur[PT::idx(rep, k)] + delta[rr][k]) * PIk[k / DC];
         }
-#pragma unroll
+PNDE_UNROLL
         for (int r = 0; r < DCOV; ++r)
-#pragma unroll
+PNDE_UNROLL
           for (int c = 0; c <= r; ++c) Lp[f][SC::tri(r, c)] = Ls[SC::tri(r, c)] * PIk[r / DC];
       }
     }
-#pragma unroll
+PNDE_UNROLL
     for (int k = 0; k < D; ++k) mean[k] = mp[k];
     // covariance from the factor(s)
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i)
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j <= i; ++j) {
         double acc = 0.0;
         if constexpr (M::IS_EK1) {
-#pragma unroll
+PNDE_UNROLL
           for (int k = 0; k <= j; ++k) acc = fma(Lp[0][SC::tri(i, k)], Lp[0][SC::tri(j, k)], acc);
         } else {
           const int ki = i / d, ai = i % d, kj = j / d, aj = j % d;
           if (ai == aj) {
             const int f = (NF > 1) ? ai : 0;
             const int lo2 = ki < kj ? ki : kj;
-#pragma unroll
+PNDE_UNROLL
             for (int k = 0; k <= q; ++k)
               if (k <= lo2) acc = fma(Lp[f][SC::tri(ki, k)], Lp[f][SC::tri(kj, k)], acc);
             acc *= dimscale[ai];

@@ -55,13 +55,13 @@ struct SmoothCov {
   template <int NR1>
   __device__ __forceinline__ static void triangularize_impl(double (&Y)[NR1 > 0 ? NR1 : 1][D], double (&Tt)[D][D],
                                                        double (&L)[NP], int& status) {
-#pragma unroll
+PNDE_UNROLL
     for (int c = 0; c < D; ++c) {
       // pivot: Tt row c is NOT special here; use a virtual zero pivot row -> plain Householder on all
       // rows with the first active row as pivot.  Rows are consumed in order: Y rows then Tt rows.
       // Active rows at step c: all rows with index >= c in the concatenated order.
       double n2 = 0.0;
-#pragma unroll
+PNDE_UNROLL
       for (int i = c; i < NR1 + D; ++i) {
         const double v = (i < NR1) ? Y[i < NR1 ? i : 0][c] : Tt[i - NR1 >= 0 ? i - NR1 : 0][c];
         n2 = fma(v, v, n2);
@@ -74,11 +74,11 @@ struct SmoothCov {
       const double v0 = pv + snrm;
       const double beta = nz ? fast_rcp(fma(fabs(pv), nrm, n2)) : 0.0;
       L[tri(c, c)] = -snrm;
-#pragma unroll
+PNDE_UNROLL
       for (int j = c + 1; j < D; ++j) {
         const double prj = (c < NR1) ? Y[c < NR1 ? c : 0][j] : Tt[c - NR1 >= 0 ? c - NR1 : 0][j];
         double w = v0 * prj;
-#pragma unroll
+PNDE_UNROLL
         for (int i = c + 1; i < NR1 + D; ++i) {
           const double vc = (i < NR1) ? Y[i < NR1 ? i : 0][c] : Tt[i - NR1 >= 0 ? i - NR1 : 0][c];
           const double vj = (i < NR1) ? Y[i < NR1 ? i : 0][j] : Tt[i - NR1 >= 0 ? i - NR1 : 0][j];
@@ -86,7 +86,7 @@ struct SmoothCov {
         }
         const double s = beta * w;
         L[tri(j, c)] = fma(-s, v0, prj);
-#pragma unroll
+PNDE_UNROLL
         for (int i = c + 1; i < NR1 + D; ++i) {
           if (i < NR1) {
             Y[i < NR1 ? i : 0][j] = fma(-s, Y[i < NR1 ? i : 0][c], Y[i < NR1 ? i : 0][j]);
@@ -102,9 +102,9 @@ struct SmoothCov {
 
   // columns of the reduced-rank filtered factor as dense D-vectors
   __device__ __forceinline__ static void cols_from_factor(const Factor<dc, q>& F, double (&cols)[R][D]) {
-#pragma unroll
+PNDE_UNROLL
     for (int c = 0; c < R; ++c) {
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) {
         if (c < dc)
           cols[c][i] = F.W[c < dc ? c : 0][i];
@@ -117,9 +117,9 @@ struct SmoothCov {
   }
   // columns of a packed lower-triangular D x D factor
   __device__ __forceinline__ static void cols_from_lower(const double (&L)[NP], double (&cols)[D][D]) {
-#pragma unroll
+PNDE_UNROLL
     for (int c = 0; c < D; ++c)
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) cols[c][i] = (i >= c) ? L[tri(i, c)] : 0.0;
   }
 
@@ -131,26 +131,26 @@ struct SmoothCov {
   __device__ __forceinline__ static void stage1_impl(double (&Er)[NR][D], const double sig, const IwpConsts& C,
                                                 double (&Rm)[NP], double (&rinv)[D], XV& X) {
     double sL[q + 1][q + 1];
-#pragma unroll
+PNDE_UNROLL
     for (int k = 0; k <= q; ++k)
-#pragma unroll
+PNDE_UNROLL
       for (int kk = 0; kk <= k; ++kk) sL[k][kk] = sig * C.Lt[k][kk];
     double El[NR][D];
-#pragma unroll
+PNDE_UNROLL
     for (int c = 0; c < NR; ++c) {
       double w[D];
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) w[i] = Er[c][i];
       apply_A<dc, q>(w);
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) El[c][i] = w[i];
     }
-#pragma unroll
+PNDE_UNROLL
     for (int c = 0; c < D; ++c) {
       const int kc = c / dc, ac = c % dc;
       const double pv = sL[kc][kc];
       double n2 = pv * pv;
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < NR; ++i) n2 = fma(El[i][c], El[i][c], n2);
       const bool nz = n2 > 0.0;
       const double rn = nz ? fast_rsqrt(n2) : 0.0;
@@ -159,26 +159,26 @@ struct SmoothCov {
       const double beta = nz ? fast_rcp(fma(pv, nrm, n2)) : 0.0;
       Rm[tri(c, c)] = -nrm;
       rinv[c] = -rn;
-#pragma unroll
+PNDE_UNROLL
       for (int j = c + 1; j < D; ++j) {
         const bool pnz = (j % dc == ac);
         const double prj = pnz ? sL[j / dc][kc] : 0.0;
         double w = pnz ? v0 * prj : 0.0;
-#pragma unroll
+PNDE_UNROLL
         for (int i = 0; i < NR; ++i) w = (i == 0 && !pnz) ? El[i][c] * El[i][j] : fma(El[i][c], El[i][j], w);
         const double s = beta * w;
         Rm[tri(j, c)] = pnz ? fma(-s, v0, prj) : -s * v0;
-#pragma unroll
+PNDE_UNROLL
         for (int i = 0; i < NR; ++i) El[i][j] = fma(-s, El[i][c], El[i][j]);
       }
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j < D; ++j) {
         double w = El[0][c] * Er[0][j];
-#pragma unroll
+PNDE_UNROLL
         for (int i = 1; i < NR; ++i) w = fma(El[i][c], Er[i][j], w);
         const double s = beta * w;
         X.set(c, j, -s * v0);
-#pragma unroll
+PNDE_UNROLL
         for (int i = 0; i < NR; ++i) Er[i][j] = fma(-s, El[i][c], Er[i][j]);
       }
     }
@@ -188,20 +188,20 @@ struct SmoothCov {
   template <int NREP, class XV>
   __device__ __forceinline__ static void apply_gain_impl(const double (&Rm)[NP], const double (&rinv)[D], const XV& X,
                                                     double (&delta)[NREP][D]) {
-#pragma unroll
+PNDE_UNROLL
     for (int r = 0; r < NREP; ++r) {
       double y[D];
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) {
         double acc = delta[r][i];
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < i; ++k) acc = fma(-Rm[tri(i, k)], y[k], acc);
         y[i] = acc * rinv[i];
       }
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) {
         double acc = 0.0;
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k < D; ++k) acc = fma(X.get(k, i), y[k], acc);
         delta[r][i] = acc;
       }
@@ -213,22 +213,22 @@ struct SmoothCov {
                                                           const RegMat<D>& X, const double (&Ls)[NP],
                                                           double (&Tt)[D][D]) {
     double Z[NP];
-#pragma unroll
+PNDE_UNROLL
     for (int c = 0; c < D; ++c) {
-#pragma unroll
+PNDE_UNROLL
       for (int i = c; i < D; ++i) {
         double acc = Ls[tri(i, c)];
-#pragma unroll
+PNDE_UNROLL
         for (int k = c; k < i; ++k) acc = fma(-Rm[tri(i, k)], Z[tri(k, c)], acc);
         Z[tri(i, c)] = acc * rinv[i];
       }
     }
-#pragma unroll
+PNDE_UNROLL
     for (int c = 0; c < D; ++c) {
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < D; ++i) {
         double acc = X.get(c, i) * Z[tri(c, c)];
-#pragma unroll
+PNDE_UNROLL
         for (int k = c + 1; k < D; ++k) acc = fma(X.get(k, i), Z[tri(k, c)], acc);
         Tt[c][i] = acc;
       }
@@ -255,11 +255,11 @@ struct SmoothCov {
   // <- triangular factor of [R_acc ; rows].  Reflector c = [R_acc[c][c] ; rows[:, c]] (length NCH + 1).
   template <int NCH>
   __device__ __forceinline__ static void qr_update_rows_impl(double (&Racc)[NP], double (&rows)[NCH][D], int& status) {
-#pragma unroll
+PNDE_UNROLL
     for (int c = 0; c < D; ++c) {
       const double pv = Racc[tri(c, c)];
       double n2 = pv * pv;
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < NCH; ++i) n2 = fma(rows[i][c], rows[i][c], n2);
       const bool nz = n2 > 0.0;
       const double rn = nz ? fast_rsqrt(n2) : 0.0;
@@ -269,15 +269,15 @@ struct SmoothCov {
       const double beta = nz ? fast_rcp(fma(fabs(pv), nrm, n2)) : 0.0;
       Racc[tri(c, c)] = -snrm;
       if (!(n2 == n2)) status |= 1;
-#pragma unroll
+PNDE_UNROLL
       for (int j = c + 1; j < D; ++j) {
         const double prj = Racc[tri(j, c)];
         double w = v0 * prj;
-#pragma unroll
+PNDE_UNROLL
         for (int i = 0; i < NCH; ++i) w = fma(rows[i][c], rows[i][j], w);
         const double s = beta * w;
         Racc[tri(j, c)] = fma(-s, v0, prj);
-#pragma unroll
+PNDE_UNROLL
         for (int i = 0; i < NCH; ++i) rows[i][j] = fma(-s, rows[i][c], rows[i][j]);
       }
     }
@@ -298,12 +298,12 @@ struct SmoothCov {
     apply_gain<1>(Rm, rinv, Xs, delta);
     // Z = R-^-T (P L^s): forward substitution row by row
     double Z[NP];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) {
-#pragma unroll
+PNDE_UNROLL
       for (int c = 0; c <= i; ++c) {
         double acc = Lsv[tri(i, c) * lst] * Pk[i / dc];
-#pragma unroll
+PNDE_UNROLL
         for (int k = c; k < i; ++k) acc = fma(-Rm[tri(i, k)], Z[tri(k, c)], acc);
         Z[tri(i, c)] = acc * rinv[i];
       }
@@ -312,35 +312,35 @@ struct SmoothCov {
 #pragma unroll kSmoothUnroll
     for (int i = 0; i < D; ++i) {
       double xc[D];
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < D; ++k) xc[k] = Xs.get(k, i);
-#pragma unroll
+PNDE_UNROLL
       for (int c = 0; c < D; ++c) {
         double acc = xc[c] * Z[tri(c, c)];
-#pragma unroll
+PNDE_UNROLL
         for (int k = c + 1; k < D; ++k) acc = fma(xc[k], Z[tri(k, c)], acc);
         Xs.set(c, i, acc);
       }
     }
     // triangularise [Y ; T'] by row blocks
     double Racc[NP];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < NP; ++i) Racc[i] = 0.0;
     qr_update_rows<NR>(Racc, cols, status);
     constexpr int CH = 4;
 #pragma unroll kSmoothUnroll
     for (int r0 = 0; r0 < D; r0 += CH) {
       double rows[CH][D];
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < CH; ++i)
-#pragma unroll
+PNDE_UNROLL
         for (int j = 0; j < D; ++j) rows[i][j] = (r0 + i < D) ? Xs.get(r0 + i < D ? r0 + i : 0, j) : 0.0;
       qr_update_rows<CH>(Racc, rows, status);
     }
     // L^s_i = R', back to natural coordinates
-#pragma unroll
+PNDE_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+PNDE_UNROLL
       for (int c = 0; c <= j; ++c) Lsv[tri(j, c) * lst] = Racc[tri(j, c)] * PIk[j / dc];
   }
 
@@ -419,16 +419,16 @@ struct SmoothModel<DenseEK1<VF, q_>> {
   static constexpr bool USE_SMEM = (D < 10);  // shared-memory scratch of the smoother kernel (see there)
   __device__ static void load_cov(const double* sb, long long n, double* mean, double* cov) {
     double L[SC::NP];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) mean[i] = sb[(long long)i * n];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < SC::NP; ++i) L[i] = sb[(long long)(D + i) * n];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i)
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j <= i; ++j) {
         double acc = 0.0;
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k <= j; ++k) acc = fma(L[SC::tri(i, k)], L[SC::tri(j, k)], acc);
         cov[SC::tri(i, j)] = acc;
       }
@@ -443,26 +443,26 @@ struct SmoothModel<KronEK0<VF, q_, MVDYN>> {
   static constexpr int SREC = D + NF * SC::NP + d;  // mean, factors, per-dimension calibration scale
   static constexpr bool USE_SMEM = false;
   __device__ static void load_cov(const double* sb, long long n, double* mean, double* cov) {
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) mean[i] = sb[(long long)i * n];
     double L[NF][SC::NP];
-#pragma unroll
+PNDE_UNROLL
     for (int f = 0; f < NF; ++f)
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < SC::NP; ++i) L[f][i] = sb[(long long)(D + f * SC::NP + i) * n];
     double ds[d];
-#pragma unroll
+PNDE_UNROLL
     for (int a = 0; a < d; ++a) ds[a] = sb[(long long)(D + NF * SC::NP + a) * n];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i)
-#pragma unroll
+PNDE_UNROLL
       for (int j = 0; j <= i; ++j) {
         const int ki = i / d, ai = i % d, kj = j / d, aj = j % d;
         double acc = 0.0;
         if (ai == aj) {
           const int f = MVDYN ? ai : 0;
           const int lo = ki < kj ? ki : kj;
-#pragma unroll
+PNDE_UNROLL
           for (int k = 0; k <= q; ++k)
             if (k <= lo) acc = fma(L[f][SC::tri(ki, k)], L[f][SC::tri(kj, k)], acc);
           acc *= ds[ai];
@@ -498,10 +498,10 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
   // diffusion (src/integrator_utils.jl:7-12); for fixedMV this is a per-dimension scale which the
   // Kronecker form carries OUTSIDE the (shared) factor.
   double gfin[ND];
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < ND; ++i) gfin[i] = sp.calibrate ? sp.final_diff[(long long)i * n + tid] : 1.0;
   double dimscale[d];
-#pragma unroll
+PNDE_UNROLL
   for (int a = 0; a < d; ++a) dimscale[a] = (sp.calibrate && !M::IS_EK1) ? (sp.is_mv ? gfin[a < ND ? a : 0] : gfin[0]) : 1.0;
   const double dense_cal = (sp.calibrate && M::IS_EK1) ? sqrt(gfin[0]) : 1.0;
 
@@ -521,15 +521,15 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
   double* Lsv = sm_dyn + (size_t)DCOV * DCOV * lst + threadIdx.x;
   auto write = [&](int slot) {
     double* o = srec(slot);
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) o[(long long)i * n] = ms[i];
-#pragma unroll
+PNDE_UNROLL
     for (int f = 0; f < NF; ++f)
-#pragma unroll
+PNDE_UNROLL
       for (int i = 0; i < SC::NP; ++i)
         o[(long long)(D + f * SC::NP + i) * n] = USE_SMEM ? Lsv[i * lst] : Ls[f][i];
     if constexpr (!M::IS_EK1) {
-#pragma unroll
+PNDE_UNROLL
       for (int a = 0; a < d; ++a) o[(long long)(D + NF * SC::NP + a) * n] = dimscale[a];
     }
   };
@@ -537,16 +537,16 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
   auto from_filtered = [&](int slot) {
     typename M::State st;
     M::load(st, rec(slot) + (long long)(1 + ND) * n, n);
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < D; ++i) ms[i] = st.m[i];
-#pragma unroll
+PNDE_UNROLL
     for (int f = 0; f < NF; ++f) {
       const Factor<DC, q>* F;
       if constexpr (M::IS_EK1) F = &st.F; else F = &st.F[f];
       double Y[SC::R][DCOV], Tt[DCOV][DCOV];
-#pragma unroll
+PNDE_UNROLL
       for (int c = 0; c < SC::R; ++c)
-#pragma unroll
+PNDE_UNROLL
         for (int i = 0; i < DCOV; ++i) {
           if (c < DC)
             Y[c][i] = F->W[c < DC ? c : 0][i] * dense_cal;
@@ -555,13 +555,13 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
                           ? F->Lz[Factor<DC, q>::lz(c - DC >= 0 ? c - DC : 0, i - 2 * DC >= 0 ? i - 2 * DC : 0)] * dense_cal
                           : 0.0;
         }
-#pragma unroll
+PNDE_UNROLL
       for (int c = 0; c < DCOV; ++c)
-#pragma unroll
+PNDE_UNROLL
         for (int i = 0; i < DCOV; ++i) Tt[c][i] = 0.0;
       SC::template triangularize<SC::R>(Y, Tt, Ls[f], status);
       if constexpr (USE_SMEM) {
-#pragma unroll
+PNDE_UNROLL
         for (int i = 0; i < SC::NP; ++i) Lsv[i * lst] = Ls[0][i];
       }
     }
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
     // the records are streamed once, backwards: pull the next one (i-1) towards L1/L2 while this step computes
     if (i > PNDE_PREFETCH_AHEAD) {
       const double* rp = rec(i - PNDE_PREFETCH_AHEAD);
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < REC; ++k) asm volatile(PNDE_PREFETCH_OP " [%0];" ::"l"(rp + (long long)k * n));
     }
     const double h = rn[0] - ri[0];
@@ -587,83 +587,83 @@ __global__ void __launch_bounds__(128) smoother_kernel(const SmoothParams sp) {
     M::scale(st, Pk);  // x[i] = P * x[i]  (src/smoothing.jl:23)
     // diffusion of the interval t[i] -> t[i+1] is stored with state i+1 (src/integrator_utils.jl:44)
     double sig[NF];
-#pragma unroll
+PNDE_UNROLL
     for (int f = 0; f < NF; ++f) {
       const double g = sp.calibrate ? (M::IS_EK1 ? gfin[0] : 1.0) : rn[(long long)(1 + (NF > 1 ? f : 0)) * n];
       sig[f] = sqrt(g);
     }
     // delta = P m_next_smoothed - A P m_i ; mean replicas laid out per factor coordinate
     double mpred[D];
-#pragma unroll
+PNDE_UNROLL
     for (int k = 0; k < D; ++k) mpred[k] = st.m[k];
     apply_A<d, q>(mpred);
     if constexpr (!USE_SMEM) {
-#pragma unroll
+PNDE_UNROLL
       for (int f = 0; f < NF; ++f) {
         // scale smoothed factor at i+1 into P(h) coordinates
-#pragma unroll
+PNDE_UNROLL
         for (int r = 0; r < DCOV; ++r)
-#pragma unroll
+PNDE_UNROLL
           for (int c = 0; c <= r; ++c) Ls[f][SC::tri(r, c)] *= Pk[r / DC];
       }
     }
     if constexpr (M::IS_EK1 && !USE_SMEM) {
       st.F.scale_all(dense_cal);
       double delta[1][D];
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < D; ++k) delta[0][k] = fma(Pk[k / d], ms[k], -mpred[k]);
       SC::template step<1>(st.F, sig[0], sp.C, Ls[0], delta, status);
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < D; ++k) ms[k] = (st.m[k] + delta[0][k]) * PIk[k / d];
     } else if constexpr (M::IS_EK1) {
       st.F.scale_all(dense_cal);
       double delta[1][D];
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < D; ++k) delta[0][k] = fma(Pk[k / d], ms[k], -mpred[k]);
       double cols[SC::R][D];
       SC::cols_from_factor(st.F, cols);
       SC::template step_cols_smem<SC::R>(cols, sig[0], sp.C, Xs, Lsv, Pk, PIk, delta, status);
-#pragma unroll
+PNDE_UNROLL
       for (int k = 0; k < D; ++k) ms[k] = (st.m[k] + delta[0][k]) * PIk[k / d];
     } else if constexpr (NF == 1) {
       // Kronecker, shared factor: d mean replicas, replica a holds coordinates (k, a), k = 0..q.
       // With a static per-dimension calibration the scale cancels in G, so the shared factor is
       // smoothed uncalibrated and dimscale is applied at output.
       double delta[d][q + 1];
-#pragma unroll
+PNDE_UNROLL
       for (int a = 0; a < d; ++a)
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k <= q; ++k) delta[a][k] = fma(Pk[k], ms[k * d + a], -mpred[k * d + a]);
       const double sg = sp.calibrate ? 1.0 : sig[0];
       SC::template step<d>(st.F[0], sg, sp.C, Ls[0], delta, status);
-#pragma unroll
+PNDE_UNROLL
       for (int a = 0; a < d; ++a)
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k <= q; ++k) ms[k * d + a] = (st.m[k * d + a] + delta[a][k]) * PIk[k];
     } else {
       // dynamicMV: one factor per dimension, one replica each
-#pragma unroll
+PNDE_UNROLL
       for (int a = 0; a < d; ++a) {
         double delta[1][q + 1];
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k <= q; ++k) delta[0][k] = fma(Pk[k], ms[k * d + a], -mpred[k * d + a]);
         SC::template step<1>(st.F[a < NF ? a : 0], sig[a < NF ? a : 0], sp.C, Ls[a < NF ? a : 0], delta, status);
-#pragma unroll
+PNDE_UNROLL
         for (int k = 0; k <= q; ++k) ms[k * d + a] = (st.m[k * d + a] + delta[0][k]) * PIk[k];
       }
     }
     if constexpr (!USE_SMEM) {
-#pragma unroll
+PNDE_UNROLL
       for (int f = 0; f < NF; ++f) {
-#pragma unroll
+PNDE_UNROLL
         for (int r = 0; r < DCOV; ++r) {
-#pragma unroll
+PNDE_UNROLL
           for (int c = 0; c <= r; ++c) Ls[f][SC::tri(r, c)] *= PIk[r / DC];
           if (!(Ls[f][SC::tri(r, r)] == Ls[f][SC::tri(r, r)])) status |= 1;
         }
       }
     }
-#pragma unroll
+PNDE_UNROLL
     for (int k = 0; k < D; ++k)
       if (!(ms[k] == ms[k])) status |= 1;
     }

@@ -20,21 +20,21 @@ struct Jet {
 template <int N>
 __device__ __forceinline__ Jet<N> operator+(const Jet<N>& a, const Jet<N>& b) {
   Jet<N> r;
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < N; ++i) r.c[i] = a.c[i] + b.c[i];
   return r;
 }
 template <int N>
 __device__ __forceinline__ Jet<N> operator-(const Jet<N>& a, const Jet<N>& b) {
   Jet<N> r;
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < N; ++i) r.c[i] = a.c[i] - b.c[i];
   return r;
 }
 template <int N>
 __device__ __forceinline__ Jet<N> operator-(const Jet<N>& a) {
   Jet<N> r;
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < N; ++i) r.c[i] = -a.c[i];
   return r;
 }
@@ -63,7 +63,7 @@ __device__ __forceinline__ Jet<N> operator-(double b, const Jet<N>& a) {
 template <int N>
 __device__ __forceinline__ Jet<N> operator*(const Jet<N>& a, double b) {
   Jet<N> r;
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < N; ++i) r.c[i] = a.c[i] * b;
   return r;
 }
@@ -74,17 +74,17 @@ __device__ __forceinline__ Jet<N> operator*(double b, const Jet<N>& a) {
 template <int N>
 __device__ __forceinline__ Jet<N> operator/(const Jet<N>& a, double b) {
   Jet<N> r;
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < N; ++i) r.c[i] = a.c[i] / b;
   return r;
 }
 template <int N>
 __device__ __forceinline__ Jet<N> operator*(const Jet<N>& a, const Jet<N>& b) {  // Cauchy product
   Jet<N> r;
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k < N; ++k) {
     double s = a.c[0] * b.c[k];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 1; i <= k; ++i) s = fma(a.c[i], b.c[k - i], s);
     r.c[k] = s;
   }
@@ -106,10 +106,10 @@ template <int N>
 __device__ __forceinline__ Jet<N> operator/(const Jet<N>& a, const Jet<N>& b) {
   Jet<N> r;
   const double ib = 1.0 / b.c[0];
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k < N; ++k) {
     double s = a.c[k];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 1; i <= k; ++i) s = fma(-b.c[i], r.c[k - i], s);
     r.c[k] = s * ib;
   }
@@ -118,7 +118,7 @@ __device__ __forceinline__ Jet<N> operator/(const Jet<N>& a, const Jet<N>& b) {
 template <int N>
 __device__ __forceinline__ Jet<N> operator/(double a, const Jet<N>& b) {
   Jet<N> x;
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < N; ++i) x.c[i] = 0.0;
   x.c[0] = a;
   return x / b;
@@ -127,10 +127,10 @@ template <int N>
 __device__ __forceinline__ Jet<N> exp(const Jet<N>& a) {
   Jet<N> r;
   r.c[0] = ::exp(a.c[0]);
-#pragma unroll
+PNDE_UNROLL
   for (int k = 1; k < N; ++k) {
     double s = 0.0;
-#pragma unroll
+PNDE_UNROLL
     for (int i = 1; i <= k; ++i) s = fma(double(i) * a.c[i], r.c[k - i], s);
     r.c[k] = s / double(k);
   }
@@ -141,10 +141,10 @@ __device__ __forceinline__ Jet<N> log(const Jet<N>& a) {
   Jet<N> r;
   r.c[0] = ::log(a.c[0]);
   const double ia = 1.0 / a.c[0];
-#pragma unroll
+PNDE_UNROLL
   for (int k = 1; k < N; ++k) {
     double s = 0.0;
-#pragma unroll
+PNDE_UNROLL
     for (int i = 1; i < k; ++i) s = fma(double(i) * r.c[i], a.c[k - i], s);
     r.c[k] = (a.c[k] - s / double(k)) * ia;
   }
@@ -154,10 +154,10 @@ template <int N>
 __device__ __forceinline__ void sincos_jet(const Jet<N>& a, Jet<N>& sn, Jet<N>& cs) {
   sn.c[0] = ::sin(a.c[0]);
   cs.c[0] = ::cos(a.c[0]);
-#pragma unroll
+PNDE_UNROLL
   for (int k = 1; k < N; ++k) {
     double ss = 0.0, cc = 0.0;
-#pragma unroll
+PNDE_UNROLL
     for (int i = 1; i <= k; ++i) {
       ss = fma(double(i) * a.c[i], cs.c[k - i], ss);
       cc = fma(double(i) * a.c[i], sn.c[k - i], cc);
@@ -183,10 +183,10 @@ __device__ __forceinline__ Jet<N> sqrt(const Jet<N>& a) {
   Jet<N> r;
   r.c[0] = ::sqrt(a.c[0]);
   const double ih = 0.5 / r.c[0];
-#pragma unroll
+PNDE_UNROLL
   for (int k = 1; k < N; ++k) {
     double s = a.c[k];
-#pragma unroll
+PNDE_UNROLL
     for (int i = 1; i < k; ++i) s = fma(-r.c[i], r.c[k - i], s);
     r.c[k] = s * ih;
   }
@@ -303,24 +303,24 @@ template <class VF, int q>
 __device__ __forceinline__ void taylor_init(const double* u0, const double* p, double* m /* [d(q+1)] */) {
   constexpr int d = VF::d;
   Jet<q + 1> x[d];
-#pragma unroll
+PNDE_UNROLL
   for (int i = 0; i < d; ++i) {
-#pragma unroll
+PNDE_UNROLL
     for (int k = 0; k <= q; ++k) x[i].c[k] = 0.0;
     x[i].c[0] = u0[i];
   }
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k < q; ++k) {
     Jet<q + 1> fx[d];
     VF::template f<Jet<q + 1>>(x, p, fx);
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) x[i].c[k + 1] = fx[i].c[k] / double(k + 1);
   }
   double fact = 1.0;
-#pragma unroll
+PNDE_UNROLL
   for (int k = 0; k <= q; ++k) {
     if (k > 0) fact *= double(k);
-#pragma unroll
+PNDE_UNROLL
     for (int i = 0; i < d; ++i) m[k * d + i] = fact * x[i].c[k];
   }
 }
