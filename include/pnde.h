@@ -149,12 +149,14 @@ int pnde_default_config(pnde_config* cfg, int32_t alg, int32_t order, int32_t vf
 /* alg_cache (src/caches.jl:42-114): validates the configuration, builds the IWP constants
  * (src/priors.jl:7-59), binds the device. */
 int pnde_create(const pnde_config* cfg, pnde_handle** out);
-/* Any autonomous user ODE (d <= 8 for EK1, d <= 16 for EK0): the vector field and its Jacobian are given as CUDA C++ statement lists and
+/* Any autonomous user ODE.  D = d (q+1) <= 16 (EK1) / 64 (EK0): unrolled into registers like the catalogue; larger, up
+ * to D <= 96 (EK1) / 1024 (EK0), d <= 128: the same kernels with rolled loops and arrays in local memory (slow, general).
+ * The vector field and its Jacobian are given as CUDA C++ statement lists and
  * compiled at run time (NVRTC) into the same kernels as the catalogue.  f_body assigns du[i] from u[] and p[]
  * and must be generic in the scalar type T (it is also evaluated on truncated Taylor series for the exact
  * initial state, src/state_initialization.jl:15-42): + - * / exp log sin cos sqrt are available.  jac_body
- * assigns J[i][j] = d f_i / d u_j in doubles (what src/jacobian.jl:6-22 obtains from ModelingToolkit); it may
- * be NULL for EK0.  cfg->vf_kind must be PNDE_VF_CUSTOM.  Example (Lotka-Volterra):
+ * assigns J[i][j] = d f_i / d u_j in doubles (what src/jacobian.jl:6-22 obtains from ModelingToolkit; entries it does
+ * not assign are zero); it may be NULL for EK0.  cfg->vf_kind must be PNDE_VF_CUSTOM.  Example (Lotka-Volterra):
  *   f_body   "du[0] = p[0]*u[0] - p[1]*u[0]*u[1]; du[1] = -p[2]*u[1] + p[3]*u[0]*u[1];"
  *   jac_body "J[0][0] = p[0]-p[1]*u[1]; J[0][1] = -p[1]*u[0]; J[1][0] = p[3]*u[1]; J[1][1] = -p[2]+p[3]*u[0];" */
 int pnde_create_custom(const pnde_config* cfg, int32_t d, int32_t n_params, const char* f_body,

@@ -490,7 +490,11 @@ PNDE_UNROLL
 PNDE_UNROLL
   for (int i = 0; i < d; ++i) u0[i] = prm.u0[(long long)i * n + tid];
 
+#ifdef PNDE_ROLLED
+  typename M::State saved;  // general-(d, q) fallback: the state is in local memory anyway, so is its pre-step copy
+#else
   extern __shared__ double stash[];  // ADAPTIVE only: STATE_LEN x blockDim doubles
+#endif
   typename M::State st;  // natural coordinates between steps when ADAPTIVE, P(hcur) coordinates otherwise
   taylor_init<VF, q>(u0, p, st.m);
   if constexpr (M::IS_EK1) {
@@ -579,7 +583,11 @@ PNDE_UNROLL
     if (ADAPTIVE) {
       // the pre-step state is parked in shared memory ([element][thread], conflict free) instead of a second
       // register copy; it is only read back when the step is rejected
+#ifdef PNDE_ROLLED
+      saved = st;
+#else
       M::store(st, stash + threadIdx.x, blockDim.x);
+#endif
       precond_scales<q>(dt, Pk, PIk);
       M::scale(st, Pk);  // x = P * x   (src/perform_step.jl:38)
     } else if (dt != hcur) {
@@ -650,7 +658,11 @@ PNDE_UNROLL
       if (commit) {
         M::scale(st, PIk);  // PI * x_filt (:75)
       } else {
+#ifdef PNDE_ROLLED
+        st = saved;
+#else
         M::load(st, stash + threadIdx.x, blockDim.x);
+#endif
       }
     }
     if (commit) {

@@ -263,9 +263,13 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
   } else if (custom) {
     // EK1 carries a dense D x (D - d) factor per thread: d <= 8.  EK0's covariance is the (q+1) x q Kronecker factor
     // whatever d is; only the mean grows (d (q + 1) doubles per thread): d <= 16.
-    const int dmax = (cfg->alg == PNDE_ALG_EK0) ? 16 : 8;
-    if (custom->d < 1 || custom->d > dmax || custom->np < 0 || custom->np > 64) {
-      g_create_error = "custom vector field: d must be in 1..8 (EK1) / 1..16 (EK0) and n_params in 0..64";
+    // Up to D = d (q+1) = 16 (EK1) / 64 (EK0) the kernels are unrolled into registers like the catalogue models; beyond
+    // that they are compiled with their loops rolled and their arrays in local memory (PNDE_ROLLED, cov_engine.cuh):
+    // any dimension works, at a fraction of the speed.  EK1 carries D x D arrays per thread: D <= 96.
+    const int Dc = custom->d * (cfg->order + 1);
+    const int Dmax = (cfg->alg == PNDE_ALG_EK0) ? 1024 : 96;
+    if (custom->d < 1 || custom->d > 128 || Dc > Dmax || custom->np < 0 || custom->np > 64) {
+      g_create_error = "custom vector field: d must be in 1..128 with d (q+1) <= 96 (EK1) / 1024 (EK0), n_params in 0..64";
       return PNDE_ERR_ARG;
     }
   } else {
@@ -330,10 +334,11 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
     owns = true;
     // adaptive kernels park the pre-step state in shared memory (STATE_LEN x 128 doubles per CTA): refuse what
     // cannot be launched now instead of failing at the first pnde_run with an opaque "invalid value"
-    const bool lanes = cfg->alg == PNDE_ALG_EK1 && !as_ieks && ops->D >= 10 && ops->d % 2 == 0 && !(cfg->flags & PNDE_FLAG_ONE_THREAD) &&
+    const bool rolled = rtc_rolled(cfg->alg, custom->d, cfg->order) && strncmp(custom->f_body ? custom->f_body : "", "@catalogue:", 11) != 0;
+    const bool lanes = !rolled && cfg->alg == PNDE_ALG_EK1 && !as_ieks && ops->D >= 10 && ops->d % 2 == 0 && !(cfg->flags & PNDE_FLAG_ONE_THREAD) &&
                        !((cfg->flags & PNDE_FLAG_REFERENCE_QUIRKS) && cfg->diffusion == PNDE_DIFF_FIXED);
     const size_t stash = (size_t)(ops->rec - 1 - ops->nd) * 128 * sizeof(double) / (lanes ? 2 : 1) + (lanes ? (size_t)64 * (ops->D * (ops->D - ops->d) + cfg->order + 1) * 8 : 0);
-    if (cfg->adaptive && stash > 227 * 1024) {
+    if (cfg->adaptive && !rolled && stash > 227 * 1024) {
       rtc_destroy(ops);
       g_create_error = "adaptive steps with d = " + std::to_string(custom->d) + ", order = " + std::to_string(cfg->order) +
                        " need " + std::to_string(stash) + " B of shared memory per CTA for the pre-step state (limit 232448): "

@@ -16,6 +16,7 @@ const ModelOps* rtc_build(int alg, int q, bool mvdyn, int d, int np, const char*
                           std::string& err, bool ieks = false, int adaptive = -1, bool quirk_check = false,
                           bool lane_groups = true);
 void rtc_destroy(const ModelOps* ops);
+bool rtc_rolled(int alg, int d, int q);  // would this user model be built with rolled loops (general-(d, q) fallback)?
 // compile-only validation of the source (needs libnvrtc, not a GPU)
 bool rtc_check(int alg, int q, bool mvdyn, int d, int np, const char* f_body, const char* jac_body, std::string& err,
                bool ieks = false);

@@ -3,6 +3,9 @@
 // src/jacobian.jl:6-22 builds symbolic Jacobians with ModelingToolkit -- here f and J are
 // device code selected by the PNDE_VF_* enum of include/pnde.h).
 #pragma once
+#ifndef PNDE_UNROLL  // (cov_engine.cuh defines it; stand-alone includes unroll)
+#define PNDE_UNROLL _Pragma("unroll")
+#endif
 #ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #endif

@@ -1377,3 +1377,56 @@ def test_large_dense_ek1_adaptive_against_oracle(d, q, diffusion):
     assert w["cov"] < 1e-6
     if diffusion == "dynamic":
         assert abs(sg.log_likelihood - so.log_likelihood) < 1e-6 * abs(so.log_likelihood)
+
+
+def _ring(d):
+    """du_i = -p0 u_i + p1 u_{i+1} u_{i-1} on a ring: an arbitrary-d user ODE with a sparse analytic Jacobian."""
+    import odefilters_b200 as B
+
+    f = "; ".join(f"du[{i}] = -p[0]*u[{i}] + p[1]*u[{(i + 1) % d}]*u[{(i + d - 1) % d}]" for i in range(d)) + ";"
+    j = "; ".join(f"J[{i}][{i}] = -p[0]; J[{i}][{(i + 1) % d}] = p[1]*u[{(i + d - 1) % d}]; "
+                  f"J[{i}][{(i + d - 1) % d}] = p[1]*u[{(i + 1) % d}]" for i in range(d)) + ";"
+
+    def fo(u, p, t):
+        return [-p[0] * u[i] + p[1] * u[(i + 1) % d] * u[(i + d - 1) % d] for i in range(d)]
+
+    def jo(u, p, t):
+        J = [[0.0 * u[0] for _ in range(d)] for _ in range(d)]
+        for i in range(d):
+            J[i][i] = -p[0] + 0.0 * u[0]
+            J[i][(i + 1) % d] = p[1] * u[(i + d - 1) % d]
+            J[i][(i + d - 1) % d] = p[1] * u[(i + 1) % d]
+        return J
+
+    return B.CustomVectorField(d=d, n_params=2, f=f, jac=j), O.VectorField(f"ring{d}", d, 2, fo, jo)
+
+
+@pytest.mark.parametrize("d,kind,q,adaptive", [(12, "EK1", 2, True), (24, "EK1", 3, False), (40, "EK0", 3, True), (6, "EK1", 3, True)])
+def test_general_dimension_fallback(d, kind, q, adaptive):
+    """Any (d, q): beyond D = 16 (EK1) / 64 (EK0) a user ODE is compiled with rolled loops and local-memory arrays
+    (PNDE_ROLLED) -- the same kernels, so filter, smoother, dense output and sampling all work; against the oracle."""
+    import odefilters_b200 as B
+
+    cv, vf = _ring(d)
+    rng = np.random.default_rng(7)
+    u0, p = list(1.0 + 0.3 * rng.standard_normal(d)), [0.7, 0.4]
+    kw = dict(abstol=1e-6, reltol=1e-4) if adaptive else dict(adaptive=False, dt=0.02)
+    tspan = (0.0, 0.6)
+    so = O.solve_ivp(O.Problem(vf, u0, tspan, p), O.Alg(kind, q, "dynamic", True), **kw)
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, smooth=True)
+    sg = B.solve(B.ODEProblem(cv, u0, tspan, p), alg, **kw)
+    assert sg.retcode == "Success" and len(sg.t) == len(so.t)
+    assert (sg.destats["naccept"], sg.destats["nreject"], sg.destats["nf"]) == (so.naccept, so.nreject, so.nf)
+    assert rel(sg.x_filt.mu[:, :d], np.array([g.mu[:d] for g in so.x_filt])) < 1e-9
+    assert rel(sg.u, np.array(so.u)) < 1e-8
+    hs = float(np.max(np.diff(so.t)))
+    wf, _ = block_errors(sg.x_filt.mu, sg.x_filt.Sigma, np.array([g.mu for g in so.x_filt]),
+                         np.array([g.Sigma.mat for g in so.x_filt]), d, q, hs)
+    ws, _ = block_errors(sg.x_smooth.mu, sg.x_smooth.Sigma, np.array([g.mu for g in so.x_smooth]),
+                         np.array([g.Sigma.mat for g in so.x_smooth]), d, q, hs)
+    report("general_dimension", d=d, alg=kind, q=q, adaptive=adaptive, filt=wf, smooth=ws)
+    assert wf["mean"] < 1e-6 and wf["cov"] < 1e-6 and ws["mean"] < 1e-5 and ws["cov"] < 1e-5
+    tq = 0.37
+    ref = O.dense_eval(so, tq)
+    assert rel(sg(tq).mu, ref.mu) < 1e-7                                  # dense output kernel
+    assert sg.sample(3, seed=2).shape == (len(sg), d, 3)                   # sampling kernels
