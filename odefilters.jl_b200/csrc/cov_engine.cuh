@@ -25,9 +25,13 @@
 // Every loop over matrix entries is written `PNDE_UNROLL for (...)`.  Ahead-of-time and small run-time compiled models
 // unroll them completely (all entries become named registers: the design of these kernels).  PNDE_ROLLED keeps them as
 // loops over arrays in local memory: the general-(d, q) fallback of rtc_model.cu for user ODEs whose state is too large
-// to unroll (d > 8 with EK1, d > 16 with EK0) -- every kernel then works for any dimension, slowly.
+// to unroll (D > 16 with EK1, D > 64 with EK0) -- every kernel then works for any dimension, slowly.  Rolled means "no
+// pragma", not "unroll 1": the compiler still unrolls what its own heuristics find worthwhile, and -- the reason this
+// is not `unroll 1` -- NVVM 12.9 miscompiled that variant (a local array filled by a loop marked nounroll and read at
+// constant indices after a large inlined call had two of its elements replaced by undef; seen as NaN constants in the
+// PTX of filter_kernel, and as a wrong initial step size on the device).
 #ifdef PNDE_ROLLED
-#define PNDE_UNROLL _Pragma("unroll 1")
+#define PNDE_UNROLL
 #else
 #define PNDE_UNROLL _Pragma("unroll")
 #endif

@@ -1306,8 +1306,9 @@ def test_custom_field_d12_ek0():
     assert (sg.destats["naccept"], sg.destats["nreject"]) == (so.naccept, so.nreject) and sg.retcode == "Success"
     assert rel(sg.u, np.array([g.mu[:d] for g in so.x_filt])) < 1e-9
     assert rel(np.diagonal(sg.x_filt.Sigma, axis1=1, axis2=2)[:, :d], np.array([np.diag(g.Sigma.mat)[:d] for g in so.x_filt])) < 1e-6
-    with pytest.raises(RuntimeError):  # EK1 stays at d <= 8 (dense factor per thread)
-        B.solve(B.ODEProblem(B.CustomVectorField(d=d, n_params=2, f=f, jac="J[0][0] = 0.0;"), u0, (0.0, 1.0), p), B.EK1(order=2))
+    with pytest.raises(RuntimeError):  # beyond the documented limits of the general-(d, q) fallback (EK1: D <= 96)
+        B.solve(B.ODEProblem(B.CustomVectorField(d=40, n_params=2, f="du[0] = 0.0;", jac="J[0][0] = 0.0;"),
+                             [1.0] * 40, (0.0, 1.0), p), B.EK1(order=2))
 
 
 @pytest.mark.parametrize("d,q,diffusion,adaptive", [(8, 3, "dynamic", False), (40, 2, "fixed", False), (12, 3, "dynamic", True)])
@@ -1401,7 +1402,42 @@ def _ring(d):
     return B.CustomVectorField(d=d, n_params=2, f=f, jac=j), O.VectorField(f"ring{d}", d, 2, fo, jo)
 
 
-@pytest.mark.parametrize("d,kind,q,adaptive", [(12, "EK1", 2, True), (24, "EK1", 3, False), (40, "EK0", 3, True), (6, "EK1", 3, True)])
+@pytest.mark.parametrize("kind,q,diffusion", [("EK1", 3, "dynamic"), ("EK0", 2, "fixed"), ("EK0", 3, "dynamicMV"), ("EK1", 1, "fixedMAP")])
+def test_rolled_build_matches_unrolled(kind, q, diffusion, monkeypatch):
+    """Differential test of the general-(d, q) fallback: the SAME small user ODE built rolled (PNDE_FORCE_ROLLED=1) and
+    unrolled must take the same steps and agree to rounding in filter, smoother, dense output and samples."""
+    import odefilters_b200 as B
+
+    f = "du[0] = u[0] - u[0]*u[0]*u[0]/3.0 - u[1] + p[3]; du[1] = p[2]*(u[0] + p[0] - p[1]*u[1]);"
+    j = "J[0][0] = 1.0 - u[0]*u[0]; J[0][1] = -1.0; J[1][0] = p[2]; J[1][1] = -p[2]*p[1];"
+    u0, p, tspan = [-1.0, 1.0], [0.2, 0.2, 3.0, 0.5], (0.0, 8.0)
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, diffusionmodel=diffusion, smooth=True)
+    out = []
+    for rolled in (False, True):
+        if rolled:
+            monkeypatch.setenv("PNDE_FORCE_ROLLED", "1")
+        cv = B.CustomVectorField(d=2, n_params=4, f=f, jac=j)
+        for kw in (dict(abstol=1e-7, reltol=1e-5), dict(adaptive=False, dt=0.05)):
+            sg = B.solve(B.ODEProblem(cv, u0, tspan, p), alg, **kw)
+            assert sg.retcode == "Success"
+            out.append((rolled, sg, sg(np.linspace(0.3, 7.7, 9)), sg.sample(2, seed=5)))
+    monkeypatch.delenv("PNDE_FORCE_ROLLED")
+    for (_, a, da, sa), (_, b, db, sb) in zip(out[:2], out[2:]):
+        assert len(a.t) == len(b.t) and a.destats == b.destats
+        np.testing.assert_allclose(b.t, a.t, rtol=1e-12)
+        sc = np.abs(a.x_filt.mu).max(axis=0) + 1e-300
+        assert np.max(np.abs(a.x_filt.mu - b.x_filt.mu) / sc) < 1e-9
+        assert np.max(np.abs(a.x_smooth.mu - b.x_smooth.mu) / sc) < 1e-8
+        for x, y in ((a.x_filt.Sigma, b.x_filt.Sigma), (a.x_smooth.Sigma, b.x_smooth.Sigma)):
+            sd = np.sqrt(np.abs(np.diagonal(x, axis1=1, axis2=2)).max(axis=0))
+            sd = np.maximum(sd, 1e-12 * sd.max())  # (pinned blocks of the EK0 have zero variance)
+            assert np.max(np.abs(x - y) / np.outer(sd, sd)) < 1e-7
+        assert rel(db.mu, da.mu) < 1e-8 and rel(sb, sa) < 1e-6
+        np.testing.assert_allclose(b.log_likelihood, a.log_likelihood, rtol=1e-8, equal_nan=True)
+
+
+@pytest.mark.parametrize("d,kind,q,adaptive", [(12, "EK1", 2, True), (24, "EK1", 3, False), (40, "EK0", 3, True), (6, "EK1", 3, True),
+                                               (40, "EK0", 2, False)])
 def test_general_dimension_fallback(d, kind, q, adaptive):
     """Any (d, q): beyond D = 16 (EK1) / 64 (EK0) a user ODE is compiled with rolled loops and local-memory arrays
     (PNDE_ROLLED) -- the same kernels, so filter, smoother, dense output and sampling all work; against the oracle."""
