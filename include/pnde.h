@@ -73,7 +73,10 @@ extern "C" {
                                     factored covariance Sigma = Ctilde (x) I_d, history / smoothing available (the
                                     getters then return the packed Ctilde where other paths return Sigma, and
                                     pnde_get_marginals ONE covariance entry per state, Ctilde[0][0]); EK1: dense
-                                    D = d (q+1) <= 5120, final state only (BASELINE config 4) */
+                                    D = d (q+1) <= 5120 (BASELINE config 4), fixed or adaptive steps; with save_mode !=
+                                    PNDE_SAVE_FINAL the history holds the solution marginals of every saved state (a full
+                                    state would be a 100 MB factor at D = 4096): pnde_get_marginals(PNDE_HIST_FILTERED)
+                                    returns u [total][d] and cov_u = diag(Sigma_u) [total][d]; no smoothing */
 #define PNDE_VF_LINEAR1 7        /* du = p u, d = 1 (test/convergence.jl:10) */
 #define PNDE_VF_CUSTOM 100       /* user source, compiled at run time: pnde_create_custom */
 
@@ -233,7 +236,7 @@ int pnde_get_history_sqrt(pnde_handle* h, int32_t which, int64_t traj_begin, int
                           double* sqrt);
 
 /* sol.pu (src/integrator_utils.jl:45): marginals of the solution block, same CSR layout:
- * u [total][d], cov_u [total][d(d+1)/2]. */
+ * u [total][d], cov_u [total][d(d+1)/2]  (Lorenz-96 EK0: [total][1]; Lorenz-96 EK1: [total][d], see PNDE_VF_LORENZ96). */
 int pnde_get_marginals(pnde_handle* h, int32_t which, int64_t traj_begin, int64_t traj_end,
                        int64_t* offsets, double* t, double* u, double* cov_u);
 

@@ -405,6 +405,8 @@ class FilterSolver:
         self.ncov = int(self.lib.pnde_cov_len(self._h))
         # Lorenz-96 EK0: covariance returned as the Kronecker factor Ctilde (EK1 returns the full matrix)
         self.kron = prob.f == "lorenz96" and alg.kind == L.ALG_EK0
+        # Lorenz-96 EK1 (large-D dense path): the saved history holds the solution marginals only (u, diag Sigma_u)
+        self.bigdense = prob.f == "lorenz96" and alg.kind == L.ALG_EK1
         self.n = 0
         self.is_mv = alg.diffusionmodel in ("dynamicMV", "fixedMV")
 
@@ -530,7 +532,9 @@ class FilterSolver:
         t = empty(total)
         mean = empty((total, DM))
         # large-d Kronecker path: the packed Ctilde (Sigma = Ctilde (x) I_d); marginals: one entry, Ctilde[0][0]
-        cov = empty((total, (1 if marginals else self.ncov) if self.kron else DM * (DM + 1) // 2))
+        # large-D dense path: marginals only, cov_u = diag(Sigma_u), d entries per state
+        cov = empty((total, (1 if marginals else self.ncov) if self.kron else
+                     (self.d if (self.bigdense and marginals) else DM * (DM + 1) // 2)))
         if marginals:
             self._check(self.lib.pnde_get_marginals(self._h, which, lo, hi, offsets.ctypes.data, t.ctypes.data,
                                                     mean.ctypes.data, cov.ctypes.data), "pnde_get_marginals")
@@ -618,6 +622,8 @@ class FilterSolver:
         else:
             if self.kron:
                 return self._kron_solution(i, counts, final)
+            if self.bigdense:
+                return self._bigdense_solution(i, counts, final)
             _, t, mean, cov, diffs = self.history(L.HIST_FILTERED, i, i + 1)
             xf = _GaussianList(mean, _unpack_lower(cov, D), self.history_sqrt(L.HIST_FILTERED, i, i + 1)[1])
             xs = None
@@ -638,6 +644,18 @@ class FilterSolver:
             retcode=L.RETCODES.get(int(counts["retcode"][i]), "Failure"), prob=self.prob, alg=self.alg,
             _solver=self, _index=i)
 
+
+    def _bigdense_solution(self, i: int, counts: dict, final=None) -> ProbODESolution:
+        """Large-D dense EK1 path with history: a saved full state would be a (D-d) x D factor (100 MB at D = 4096), so
+        the history holds sol.t, sol.u and the marginal variances diag(Sigma_u) [N, d]; x_filt is the final state."""
+        _, t, u, var, _ = self.history(L.HIST_FILTERED, i, i + 1, marginals=True)
+        mean, cov, _, ll = final or self.final()
+        xf = _GaussianList(mean[i:i + 1], _unpack_lower(cov[i:i + 1], self.D))
+        pu = _GaussianList(u, var)
+        return ProbODESolution(
+            t=t, u=pu.mu, pu=pu, x_filt=xf, x_smooth=None, diffusions=np.zeros(0), log_likelihood=float(ll[i]),
+            destats={k: int(counts[k][i]) for k in ("naccept", "nreject", "nf", "njacs")},
+            retcode=L.RETCODES.get(int(counts["retcode"][i]), "Failure"), prob=self.prob, alg=self.alg, _solver=self, _index=i)
 
     def _kron_solution(self, i: int, counts: dict, final=None) -> ProbODESolution:
         """Large-d Kronecker path with history: Sigma = Ctilde (x) I_d is never expanded.  x_filt / x_smooth carry the

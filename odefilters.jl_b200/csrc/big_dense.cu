@@ -395,7 +395,7 @@ __global__ void pack_cov_kernel(const double* full, int D, double cal, double* o
 __global__ void write_outputs_kernel(StepCtx c, double* mean, double* t_final, double* loglik, double* final_diff,
                                      int* retcode, int* naccept, int* nreject, int* nf, int* njacs, int* n_saved,
                                      long long n, long long tr, double t, int is_static, int ret_host, int nrej,
-                                     int nfe) {
+                                     int nfe, int nsaved) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c.D) mean[(long long)i * n + tr] = c.m[i];
   if (i == 0) {
@@ -411,8 +411,28 @@ __global__ void write_outputs_kernel(StepCtx c, double* mean, double* t_final, d
     nreject[tr] = nrej;
     nf[tr] = nfe;
     njacs[tr] = sc->nacc + nrej;
-    n_saved[tr] = 0;
+    n_saved[tr] = nsaved;
   }
+}
+
+// savevalues! (src/integrator_utils.jl:33-48) for this path: the solution marginals of one accepted state.
+//   u = E0 m,  diag(Sigma_u)_b = sum over the factor columns of S[.][b]^2   (Sigma = S' S, natural coordinates)
+__global__ void __launch_bounds__(256) save_marginals_kernel(StepCtx c, double* base, long long n, double t, int initial) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = c.d, D = c.D;
+  if (b == 0) {
+    base[0] = t;
+    base[n] = initial ? 1.0 : c.sc->global_saved;  // initial_diffusion, src/diffusions.jl:8
+  }
+  if (b >= d) return;
+  double var = 0.0;
+  if (!initial)
+    for (int r = 0; r < D - d; ++r) {
+      const double v = c.S[(size_t)r * D + b];
+      var = fma(v, v, var);
+    }
+  base[(long long)(2 + b) * n] = c.m[b];
+  base[(long long)(2 + d + b) * n] = var;
 }
 
 double ulp_host(double x) {
@@ -518,6 +538,23 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
     ++*launches;
     double t = A.K.t0;
     long long iter = 0;
+    int nsaved = 0, nacc_host = 0;
+    bool hist_full = false;
+    const int REC = 2 + 2 * d;
+    auto save = [&](double tt, int initial) {
+      if (!A.hist) return;
+      if (nsaved >= A.max_saved) {
+        hist_full = true;
+        return;
+      }
+      save_marginals_kernel<<<(d + 255) / 256, 256, 0, s>>>(c, A.hist + ((long long)nsaved * REC) * A.n + tr, A.n, tt, initial);
+      ++*launches;
+      ++nsaved;
+    };
+    auto want_save = [&](double tt) {
+      return A.save_mode == SAVE_EVERY || (A.save_mode == SAVE_STRIDE && (nacc_host % A.save_stride == 0 || !(tt < A.K.t1)));
+    };
+    save(t, 1);
     const int trsv_smem = d * 8;
     BCK(cudaFuncSetAttribute(trsv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsv_smem));
     // one attempted step (fixed h): every launch below depends on the step only through h
@@ -568,6 +605,12 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
         ++nfe;
         const double ttmp = t + h;
         t = (fabs(ttmp - A.K.t1) < 10.0 * ulp_host(fmax(t, A.K.t1))) ? A.K.t1 : ttmp;
+        ++nacc_host;
+        if (want_save(t)) save(t, 0);
+        if (hist_full) {  // fixed steps: the capacity follows from the grid; a full history is a caller error
+          ret_host = RET_HISTORY_FULL;
+          break;
+        }
       }
     } else {
       // OrdinaryDiffEq's loop (loopheader!, perform_step!, loopfooter!, PI controller) on the host:
@@ -634,6 +677,11 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
           qold = fmax(EEst, K.qoldinit);
           t = (fabs(ttmp - K.t1) < 10.0 * ulp_host(fmax(t, K.t1))) ? K.t1 : ttmp;
           dtpropose = fmax(K.dtmin, fmin(K.dtmax, dt / qc));
+          ++nacc_host;
+          // (EEst == 1 exactly is accepted but not committed, src/perform_step.jl:89: the saved state is then the old one,
+          // like in the reference)
+          if (want_save(t)) save(t, 0);
+          if (hist_full) ret_host = RET_HISTORY_FULL;  // keep stepping without saving: naccept + 1 is the capacity needed
         } else {
           ++nrej;
         }
@@ -642,7 +690,7 @@ cudaError_t big_run(const BigRunArgs& A, cudaStream_t s, long long* launches) {
     }
     write_outputs_kernel<<<(D + TB - 1) / TB, TB, 0, s>>>(c, A.mean, A.t_final, A.loglik, A.final_diff, A.retcode,
                                                           A.naccept, A.nreject, A.nf, A.njacs, A.n_saved, A.n, tr, t,
-                                                          is_static ? 1 : 0, ret_host, nrej, nfe);
+                                                          is_static ? 1 : 0, ret_host, nrej, nfe, nsaved);
     ++*launches;
     if (A.cov) {
       // Sigma = S' S over the factor columns (rows of S): full D x D by the same DMMA kernel, then packed

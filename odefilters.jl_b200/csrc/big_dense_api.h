@@ -25,6 +25,11 @@ struct BigRunArgs {
   int* njacs;
   int* n_saved;
   void* work;        // big_work_bytes(d, q) bytes of device memory
+  // history of the solution marginals (a saved full state would be a (D-d) x D factor: 100 MB at D = 4096):
+  // record = [t, diffusion of the interval, u[d], diag(Sigma_u)[d]], layout [slot][2 + 2d][n]; null: final state only
+  double* hist;
+  long long max_saved;
+  int save_mode, save_stride;
   IwpConsts C;
   CtrlParams K;
 };

@@ -256,8 +256,8 @@ static int create_impl(const pnde_config* cfg, pnde_handle** out, const CustomVf
       g_create_error = "Lorenz-96: MV diffusion models are not built for the large-d path";
       return PNDE_ERR_UNSUPPORTED;
     }
-    if (cfg->alg == PNDE_ALG_EK1 && (cfg->save_mode != PNDE_SAVE_FINAL || cfg->smooth)) {
-      g_create_error = "Lorenz-96 EK1 (dense): only save_mode = PNDE_SAVE_FINAL (no smoothing) is built";
+    if (cfg->alg == PNDE_ALG_EK1 && cfg->smooth) {
+      g_create_error = "Lorenz-96 EK1 (dense): smoothing is not built (the saved history holds the solution marginals only)";
       return PNDE_ERR_UNSUPPORTED;
     }
   } else if (custom) {
@@ -512,7 +512,8 @@ static int lorenz_srec(const pnde_handle* h) { return (h->cfg.order + 1) * (h->c
 int64_t pnde_record_len(const pnde_handle* h) {
   if (!h) return 0;
   if (h->ops) return h->ops->rec;
-  return (h->lorenz && h->cfg.alg == PNDE_ALG_EK0) ? lorenz_rec(h) : 0;
+  if (h->lorenz && h->cfg.alg == PNDE_ALG_EK1) return 2 + 2 * h->d;  // large-D dense path: t, diffusion, u, diag(Sigma_u)
+  return h->lorenz ? lorenz_rec(h) : 0;
 }
 int64_t pnde_cov_len(const pnde_handle* h) { return h ? h->ncov : 0; }
 
@@ -736,6 +737,10 @@ int pnde_run(pnde_handle* h) {
     ba.njacs = fp.njacs;
     ba.n_saved = fp.n_saved;
     ba.work = h->bigwork.p;
+    ba.hist = (c.save_mode != PNDE_SAVE_FINAL) ? h->hist.as<double>() : nullptr;
+    ba.max_saved = h->max_saved;
+    ba.save_mode = c.save_mode;
+    ba.save_stride = c.save_stride;
     ba.C = fp.C;
     ba.K = fp.K;
     long long nl = 0;
@@ -1138,6 +1143,32 @@ static int multi_csr(pnde_handle* h, int64_t tb, int64_t te, int64_t* offsets, F
   return PNDE_OK;
 }
 
+// History of the large-D dense path (records [t, diffusion, u[d], diag(Sigma_u)[d]], layout [slot][2 + 2d][n]) ->
+// the caller's CSR arrays; static diffusion models: calibrated by the final global diffusion like every other path
+// (src/integrator_utils.jl:4-18).  One thread per (saved state, dimension).
+static __global__ void __launch_bounds__(256) bigdense_convert_kernel(const double* hist, const double* final_diff,
+                                                                       const int* naccept, const long long* offsets,
+                                                                       long long n, long long tb, long long te, int d,
+                                                                       int calibrate, double* t, double* u, double* var) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = offsets[te - tb];
+  if (idx >= total * d) return;
+  const long long g = idx / d;
+  const int b = (int)(idx % d);
+  long long lo = 0, hi = te - tb;  // trajectory of state g: last i with offsets[i] <= g
+  while (hi - lo > 1) {
+    const long long mid = (lo + hi) / 2;
+    if (offsets[mid] <= g) lo = mid; else hi = mid;
+  }
+  const long long tr = tb + lo, slot = g - offsets[lo];
+  const int REC = 2 + 2 * d;
+  const double* r = hist + (slot * REC) * n + tr;
+  const double cal = (calibrate && naccept[tr] > 0) ? final_diff[tr] : 1.0;
+  if (b == 0) t[g] = r[0];
+  u[g * d + b] = r[(long long)(2 + b) * n];
+  var[g * d + b] = cal * r[(long long)(2 + d + b) * n];
+}
+
 extern "C" {
 
 static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t te, int64_t* offsets, double* t,
@@ -1146,8 +1177,9 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
   if (h->cfg.save_mode == PNDE_SAVE_FINAL) return h->fail(PNDE_ERR_STATE, "no history was saved (save_mode = final)");
   if (h->multi()) {
-    const bool kron = h->lorenz && h->cfg.alg == PNDE_ALG_EK0;
-    const int64_t DM = marginals ? h->d : h->D, NC = kron ? (marginals ? 1 : h->ncov) : DM * (DM + 1) / 2;
+    const bool kron = h->lorenz && h->cfg.alg == PNDE_ALG_EK0, bigd = h->lorenz && h->cfg.alg == PNDE_ALG_EK1;
+    const int64_t DM = marginals ? h->d : h->D;
+    const int64_t NC = kron ? (marginals ? 1 : h->ncov) : ((bigd && marginals) ? h->d : DM * (DM + 1) / 2);
     const int df0 = h->cfg.diffusion;
     const int64_t ndo = (df0 == PNDE_DIFF_DYNAMIC_MV || df0 == PNDE_DIFF_FIXED_MV) ? h->d : 1;
     return multi_csr(h, tb, te, offsets, [&](pnde_handle* kid, int64_t lo, int64_t hi, int64_t* offs, int64_t base) {
@@ -1161,7 +1193,10 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   if (tb < 0 || te > h->n || tb >= te || !offsets) return h->fail(PNDE_ERR_ARG, "bad trajectory range");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   const ModelOps* o = h->ops;
-  if (!o && !(h->lorenz && h->cfg.alg == PNDE_ALG_EK0)) return h->fail(PNDE_ERR_UNSUPPORTED, "no history on this path");
+  const bool bigdense = !o && h->lorenz && h->cfg.alg == PNDE_ALG_EK1;
+  if (bigdense && (!marginals || which != PNDE_HIST_FILTERED))
+    return h->fail(PNDE_ERR_UNSUPPORTED, "the large-D dense path saves the solution marginals only: use pnde_get_marginals(PNDE_HIST_FILTERED)");
+  if (!o && !h->lorenz) return h->fail(PNDE_ERR_UNSUPPORTED, "no history on this path");
   if (!o && sqrt_out) return h->fail(PNDE_ERR_UNSUPPORTED, "the large-d path returns Ctilde, not D x D factors");
   std::vector<int> ns;
   int rc = fetch_i32(h, h->n_saved, ns);
@@ -1172,6 +1207,29 @@ static int get_history_impl(pnde_handle* h, int32_t which, int64_t tb, int64_t t
   for (long long i = 0; i < ntr; ++i) off[(size_t)i + 1] = off[(size_t)i] + ns[(size_t)(tb + i)];
   const long long total = off[(size_t)ntr];
   for (long long i = 0; i <= ntr; ++i) offsets[i] = off[(size_t)i];
+  if (bigdense) {
+    // large-D dense path: u [total][d], cov_u = diag(Sigma_u) [total][d] (the d x d matrix is never formed per state)
+    const size_t dd = (size_t)h->d, nml = (size_t)total * dd;
+    CK(h->scratch_off.ensure(((size_t)ntr + 1) * 8), "alloc offsets");
+    CK(h->scratch_out.ensure(((size_t)total + 2 * nml) * 8 + 64), "alloc history staging");
+    CK(cudaMemcpyAsync(h->scratch_off.p, off.data(), ((size_t)ntr + 1) * 8, cudaMemcpyHostToDevice, h->stream), "H2D offsets");
+    double* lt = h->scratch_out.as<double>();
+    const int dfl = h->cfg.diffusion;
+    int calibrate = (dfl == PNDE_DIFF_FIXED || dfl == PNDE_DIFF_FIXED_MAP);
+    if (h->cfg.flags & PNDE_FLAG_REFERENCE_QUIRKS) calibrate = 0;  // quirk (a): sol.pu of an un-smoothed solve
+    if (total > 0) {
+      const long long work = total * (long long)dd;
+      bigdense_convert_kernel<<<(unsigned)((work + 255) / 256), 256, 0, h->stream>>>(
+          h->hist.as<double>(), h->final_diff.as<double>(), h->naccept.as<int>(), h->scratch_off.as<long long>(), h->n, tb, te,
+          h->d, calibrate, lt, lt + total, lt + total + nml);
+      CK(cudaGetLastError(), "marginal history converter launch");
+    }
+    if (t) CK(cudaMemcpyAsync(t, lt, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream), "D2H t");
+    if (mean) CK(cudaMemcpyAsync(mean, lt + total, nml * 8, cudaMemcpyDeviceToHost, h->stream), "D2H u");
+    if (cov) CK(cudaMemcpyAsync(cov, lt + total + nml, nml * 8, cudaMemcpyDeviceToHost, h->stream), "D2H var");
+    CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+    return PNDE_OK;
+  }
   if (!o) {
     // large-d Kronecker path: mean [total][D] (marginals: [total][d]), cov = packed Ctilde [total][(q+1)(q+2)/2]
     // (marginals: ONE entry per state, Ctilde[0][0]: Sigma_u = Ctilde[0][0] I_d), diffusion [total]

@@ -1358,6 +1358,30 @@ def test_large_d_path_history_d1024():
     assert np.all(np.isfinite(sg.x_smooth.mu)) and sg.pu.Sigma.shape == (51,)
 
 
+@pytest.mark.parametrize("d,q,diffusion,adaptive", [(32, 2, "dynamic", False), (32, 3, "dynamic", True), (64, 1, "fixed", True),
+                                                    (32, 2, "fixedMAP", False)])
+def test_large_dense_ek1_marginal_history(d, q, diffusion, adaptive):
+    """The large-D dense EK1 path with every accepted step saved: sol.t, sol.u and the marginal variances diag(Sigma_u)
+    of all saved states against the dense oracle (savevalues!, src/integrator_utils.jl:33-48; static models calibrated
+    by the final diffusion, :4-18)."""
+    import odefilters_b200 as B
+
+    u0 = _lorenz_inputs(d)
+    kw = dict(abstol=1e-5, reltol=1e-3) if adaptive else dict(adaptive=False, dt=0.01)
+    so = O.solve_ivp(O.Problem(O.lorenz96(d), list(u0), (0.0, 0.1), [8.0]), O.Alg("EK1", q, diffusion, False), **kw)
+    sg = B.solve(B.ODEProblem("lorenz96", u0, (0.0, 0.1), (8.0,)), B.EK1(order=q, diffusionmodel=diffusion, smooth=False), **kw)
+    assert sg.retcode == "Success" and len(sg.t) == len(so.t) == so.naccept + 1
+    assert rel(sg.t, so.t) < 1e-12
+    assert rel(sg.u, np.array(so.u)) < 1e-9
+    var_o = np.array([np.diag(g.Sigma.mat)[:d] for g in so.x_filt])
+    assert np.all(sg.pu.Sigma[0] == 0.0) and rel(sg.pu.Sigma[1:], var_o[1:]) < 1e-6
+    report("large_dense_history", d=d, q=q, diffusion=diffusion, adaptive=adaptive, n_states=len(sg.t),
+           u=rel(sg.u, np.array(so.u)), var=rel(sg.pu.Sigma[1:], var_o[1:]))
+    with pytest.raises(RuntimeError):  # the marginal history cannot be smoothed: refused at create time
+        B.FilterSolver(B.ODEProblem("lorenz96", u0, (0.0, 0.1), (8.0,)), B.EK1(order=q, smooth=True), adaptive=False, dt=0.01,
+                       save_everystep=True)
+
+
 @pytest.mark.parametrize("d,q,diffusion", [(32, 2, "dynamic"), (32, 3, "dynamic"), (64, 1, "fixed")])
 def test_large_dense_ek1_adaptive_against_oracle(d, q, diffusion):
     """The blocked-QR dense EK1 path with PI-controlled steps (controller on the host, EEst from the device):
