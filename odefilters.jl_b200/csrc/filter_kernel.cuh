@@ -144,6 +144,21 @@ __device__ __forceinline__ double ulp_of(double x) {  // Julia eps(x)
   return __longlong_as_double(bits + 1) - x;
 }
 
+// "Sliver" intervals.  OrdinaryDiffEq advances t += dt and snaps to t1 only within 10 ulp, so a fixed-step run whose dt
+// is not a binary fraction ends with one more step over what the recursion lost to rounding (test/diffusions.jl with
+// dt = 1e-4: a last step of 9.4e-14; an adaptive run can end the same way).  The filter takes that step exactly like the
+// reference does (it is a genuine re-measurement at the updated mean).  With a dynamic diffusion model the backward
+// recursions (smoother, sampler, dense output) take it as well: the sliver's own local diffusion is huge and makes the
+// gain harmless.  With a STATIC model the backward gain across the sliver is, to rounding, the identity on the range
+// of the covariance, evaluated in P(h) coordinates through a matrix with condition number ~h^-(2q+1): the reference's
+// dense arithmetic returns the next state (oracle: smoothed[N-1] = filtered[N] in every component), the triangular
+// solves of these kernels amplified rounding by 1e10 in the highest derivative.  An interval no longer than the
+// rounding error that ns additions can accumulate is therefore treated, for static models, like the reference
+// treats h == 0 (src/smoothing.jl:13-16): the next state is carried across.
+__device__ __forceinline__ bool sliver_interval(double h, double ta, double tb, int ns, int static_model) {
+  return h == 0.0 || (static_model && h <= 2.0 * double(ns) * ulp_of(fmax(fabs(ta), fabs(tb))));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Model: EK1 with the full D x D covariance (src/perform_step.jl, alg isa EK1)
 // ---------------------------------------------------------------------------------------------

@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(LORENZ_THREADS) lorenz96_smoother_kernel(const
     const double* ri = rec(i);
     const double* rn = rec(i + 1);
     const double h = rn[0] - ri[0];
-    if (h != 0.0) {
+    if (!sliver_interval(h, ri[0], rn[0], ns, sp.calibrate)) {  // (h == 0 or a sliver: the state is carried across, filter_kernel.cuh)
       double Pk[q + 1], PIk[q + 1];
       precond_scales<q>(h, Pk, PIk);
       Fac F;

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) sample_prep_kernel(const SampleParams sp)
   const double* ri = rec(i);
   const double* rn = rec(i + 1);
   const double h = rn[0] - ri[0];
-  if (!(h > 0.0)) return;  // the draw kernel copies the sample across such an interval
+  if (sliver_interval(h, ri[0], rn[0], ns, sp.calibrate)) return;  // h == 0 or a sliver: the draw kernel copies the sample across
   double gfin[ND];
 PNDE_UNROLL
   for (int k = 0; k < ND; ++k) gfin[k] = sp.calibrate ? sp.final_diff[(long long)k * n + tr] : 1.0;
@@ -243,7 +243,7 @@ PNDE_UNROLL
   }
   for (int i = ns - 2; i >= 0; --i) {
     const double h = rec(i + 1)[0] - rec(i)[0];
-    if (h > 0.0) {
+    if (!sliver_interval(h, rec(i)[0], rec(i + 1)[0], ns, sp.calibrate)) {
       const double* pr = sp.scratch + ((tr - sp.traj_begin) * (sp.max_saved - 1) + i) * SPp::LEN;
       double Pk[q + 1], PIk[q + 1];
       precond_scales<q>(h, Pk, PIk);
@@ -334,12 +334,17 @@ PNDE_UNROLL
   for (int a = 0; a < d; ++a)
     dimscale[a] = (dp.calibrate && !M::IS_EK1) ? (dp.is_mv ? gfin[a < ND ? a : 0] : gfin[0]) : 1.0;
   const double dense_cal = (dp.calibrate && M::IS_EK1) ? sqrt(gfin[0]) : 1.0;
-  if (rec(prev)[0] == tval) {  // exact hit: the stored state (src/solution.jl:172-176)
+  // exact hit: the stored state (src/solution.jl:172-176); a query closer than a sliver (filter_kernel.cuh) to the
+  // right neighbour of a smoothed solution takes that neighbour (the backward step across it is not evaluated)
+  int hit = (rec(prev)[0] == tval) ? prev : -1;
+  if (hit < 0 && dp.smoothed && prev + 1 < ns && sliver_interval(rec(prev + 1)[0] - tval, tval, rec(prev + 1)[0], ns, dp.calibrate))
+    hit = prev + 1;
+  if (hit >= 0) {
     if (dp.smoothed) {
-      SM::load_cov(dp.smooth + ((long long)prev * SREC) * n + tr, n, mean, cov);
+      SM::load_cov(dp.smooth + ((long long)hit * SREC) * n + tr, n, mean, cov);
     } else {
       typename M::State st;
-      M::load(st, rec(prev) + (long long)(1 + ND) * n, n);
+      M::load(st, rec(hit) + (long long)(1 + ND) * n, n);
 PNDE_UNROLL
       for (int i = 0; i < D; ++i) mean[i] = st.m[i];
       double sc[q + 1];

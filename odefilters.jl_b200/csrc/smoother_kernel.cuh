@@ -579,7 +579,8 @@ PNDE_UNROLL
       for (int k = 0; k < REC; ++k) asm volatile(PNDE_PREFETCH_OP " [%0];" ::"l"(rp + (long long)k * n));
     }
     const double h = rn[0] - ri[0];
-    if (h != 0.0) {  // h == 0: the state is kept as it is (src/smoothing.jl:13-16); one copy of write() below
+    // h == 0 (or a sliver, filter_kernel.cuh): the state is kept as it is (src/smoothing.jl:13-16); one copy of write() below
+    if (!sliver_interval(h, ri[0], rn[0], ns, sp.calibrate)) {
     double Pk[q + 1], PIk[q + 1];
     precond_scales<q>(h, Pk, PIk);
     typename M::State st;

@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(PNDE_WSMOOTH_BLOCK, 1) wide_smoother_kernel(co
     const double* ri = rec(ii);
     const double* rn = rec(alive ? ii + 1 : 0);
     const double h = alive ? rn[0] - ri[0] : 1.0;
-    const bool work = alive && h != 0.0;  // h == 0: the state is kept as it is (src/smoothing.jl:13-16)
+    // h == 0 (or a sliver, filter_kernel.cuh): the state is kept as it is (src/smoothing.jl:13-16)
+    const bool work = alive && !sliver_interval(h, ri[0], rn[0], ns, sp.calibrate);
     double Pk[q + 1], PIk[q + 1];
     precond_scales<q>(work ? h : 1.0, Pk, PIk);
     const double g = sp.calibrate ? gfin : (alive ? rn[(long long)n] : 1.0);
