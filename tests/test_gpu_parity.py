@@ -1542,3 +1542,52 @@ def test_reference_convergence_jl(kind, q, ks):
     for n in (("final", "l2", "linf") if kind == "EK0" else ("l2",)):
         tol = 0.3 if (kind == "EK1" or (q >= 4 and n != "final")) else 0.2  # TESTTOL, TESTTOL + 0.1
         assert abs(est[n] - (q + 1)) <= tol, (n, est)
+
+
+_REF_PROBS = {  # DiffEqProblemLibrary problems used by test/correctness.jl
+    "lotka_volterra": ([1.0, 1.0], (0.0, 1.0), (1.5, 1.0, 3.0, 1.0)),
+    "fhn_lib": ([1.0, 1.0], (0.0, 1.0), (0.7, 0.8, 1 / 12.5, 0.5)),
+}
+
+
+def _true_solution(name, t_eval):
+    from scipy.integrate import solve_ivp as scipy_ivp
+
+    u0, tspan, p = _REF_PROBS[name]
+    f = lambda t, u: O.CATALOGUE[name].f(list(u), list(p), t)  # noqa: E731
+    return scipy_ivp(f, tspan, u0, method="DOP853", rtol=1e-13, atol=1e-13, t_eval=t_eval).y.T
+
+
+def _isapprox(x, y, rtol):
+    """Julia isapprox on arrays: norm(x - y) <= rtol * max(norm(x), norm(y))."""
+    return np.linalg.norm(x - y) <= rtol * max(np.linalg.norm(x), np.linalg.norm(y))
+
+
+@pytest.mark.parametrize("name", ["lotka_volterra", "fhn_lib"])
+@pytest.mark.parametrize("kind,diffusion", [("EK0", "fixed"), ("EK0", "dynamic"), ("EK0", "fixedMAP"), ("EK0", "fixedMV"),
+                                            ("EK0", "dynamicMV"), ("EK1", "fixed"), ("EK1", "dynamic"), ("EK1", "fixedMAP")])
+def test_reference_correctness_jl(name, kind, diffusion):
+    """test/correctness.jl verbatim on the CUDA path: (i) constant steps dt = 5e-3, orders 1, 3, 5: sol.u ≈ true solution
+    with rtol = 1e-5 (:20-41); (ii) adaptive steps with the default tolerances, orders 2, 4, 6: sol.u and the dense output
+    on a 0.01 grid ≈ true solution with rtol = 1e-3 (:44-77).  smooth = true is the algorithms' default."""
+    import odefilters_b200 as B
+
+    u0, tspan, p = _REF_PROBS[name]
+    Alg = B.EK0 if kind == "EK0" else B.EK1
+    worst = {}
+    for q in (1, 3, 5):
+        sg = B.solve(B.ODEProblem(name, u0, tspan, p), Alg(order=q, diffusionmodel=diffusion), adaptive=False, dt=5e-3)
+        truth = _true_solution(name, sg.t)
+        worst[f"const_q{q}"] = float(np.linalg.norm(sg.u - truth) / np.linalg.norm(truth))
+        assert sg.retcode == "Success" and _isapprox(sg.u, truth, 1e-5), (q, worst)
+    t_eval = np.arange(0.0, 1.0 + 1e-12, 0.01)
+    dense_truth = _true_solution(name, t_eval)
+    for q in (2, 4, 6):
+        sg = B.solve(B.ODEProblem(name, u0, tspan, p), Alg(order=q, diffusionmodel=diffusion))
+        truth = _true_solution(name, sg.t)
+        worst[f"adaptive_q{q}"] = float(np.linalg.norm(sg.u - truth) / np.linalg.norm(truth))
+        assert sg.retcode == "Success" and _isapprox(sg.u, truth, 1e-3), (q, worst)
+        dense = sg(t_eval).mu
+        worst[f"dense_q{q}"] = float(np.linalg.norm(dense - dense_truth) / np.linalg.norm(dense_truth))
+        assert _isapprox(dense, dense_truth, 1e-3), (q, worst)
+    report("reference_correctness_jl", problem=name, alg=kind, diffusion=diffusion, **worst)
