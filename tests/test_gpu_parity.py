@@ -1591,3 +1591,47 @@ def test_reference_correctness_jl(name, kind, diffusion):
         worst[f"dense_q{q}"] = float(np.linalg.norm(dense - dense_truth) / np.linalg.norm(dense_truth))
         assert _isapprox(dense, dense_truth, 1e-3), (q, worst)
     report("reference_correctness_jl", problem=name, alg=kind, diffusion=diffusion, **worst)
+
+
+def test_reference_smoothing_and_specific_problems_jl():
+    """The remaining solver-level tests of the reference, verbatim on the CUDA path:
+    test/smoothing.jl:13-21 (small dt, large q), :24-48 (smooth vs. non-smooth against a high-accuracy solution),
+    test/specific_problems.jl:17-23 (smoothing with small constant steps, fixed diffusion), :26-39 (analytic linear
+    problem with the default algorithms), :47-50 (stiff Van der Pol, mu = 1e6), :64-69 (logistic, order 4),
+    :140-143 (Lotka-Volterra on (0, 10)), test/ieks.jl:10-13 and test/state_init.jl:9-40 (exact initial derivatives of
+    the 2-d linear problem up to order 6)."""
+    import odefilters_b200 as B
+
+    lv = B.ODEProblem("lotka_volterra", *_REF_PROBS["lotka_volterra"])
+    fhn = B.ODEProblem("fhn_lib", *_REF_PROBS["fhn_lib"])
+
+    def ok(sol):
+        return sol.retcode == "Success" and np.all(np.isfinite(sol.u)) and sol.t[-1] == sol.prob.tspan[1]
+
+    # test/smoothing.jl
+    assert ok(B.solve(lv, B.EK0(order=4, smooth=True, diffusionmodel="dynamic"), adaptive=False, dt=1e-4))
+    s_non = B.solve(lv, B.EK0(order=3, smooth=False), dense=False, adaptive=False, dt=1e-2)
+    s_smo = B.solve(lv, B.EK0(order=3, smooth=True), adaptive=False, dt=1e-2)
+    assert np.allclose(s_non.t, s_smo.t) and np.array_equal(s_non.u[-1], s_smo.u[-1]) and not np.array_equal(s_non.u[-2], s_smo.u[-2])
+    best = _true_solution("lotka_volterra", s_smo.t)
+    e_non, e_smo = np.linalg.norm(s_non.u - best, axis=1), np.linalg.norm(s_smo.u - best, axis=1)
+    assert 2 * e_non.max() > e_smo.max() and 2 * e_non.sum() > e_smo.sum()
+    # test/specific_problems.jl
+    for Alg in (B.EK0, B.EK1):
+        assert ok(B.solve(fhn, Alg(order=4, diffusionmodel="fixed", smooth=True), adaptive=False, dt=1e-3))
+    lin = B.ODEProblem("linear1", [0.5], (0.0, 1.0), (1.01,))
+    for Alg in (B.EK0, B.EK1):
+        sol = B.solve(lin, Alg())
+        assert ok(sol) and abs(sol.u[-1, 0] - 0.5 * np.exp(1.01)) < 1e-3
+    assert ok(B.solve(B.ODEProblem("vanderpol", [0.0, 3.0 ** 0.5], (0.0, 1.0), (1e6,)), B.EK1(order=3)))
+    logi = B.ODEProblem("logistic", [0.1], (0.0, 5.0), (3.0,))
+    for Alg in (B.EK0, B.EK1):
+        assert ok(B.solve(logi, Alg(order=4)))
+    assert ok(B.solve(B.ODEProblem("lotka_volterra", [1.0, 1.0], (0.0, 10.0), (1.5, 1.0, 3.0, 1.0)), B.EK1(order=3)))
+    # test/ieks.jl
+    assert ok(B.solve_ieks(fhn, B.IEKS(order=4, diffusionmodel="fixed")))
+    # test/state_init.jl: u^(k)(0) = p^k u0 for du = p u
+    a, b, u0 = 1.1, -0.5, [0.1, 1.0]
+    sol = B.solve(B.ODEProblem("linear2", u0, (0.0, 5.0), (a, b)), B.EK0(order=6, smooth=False), adaptive=False, dt=0.5)
+    truth = np.concatenate([[a ** k * u0[0], b ** k * u0[1]] for k in range(7)])
+    assert np.allclose(sol.x_filt.mu[0], truth, rtol=1e-14, atol=0.0)
