@@ -248,6 +248,14 @@ int pnde_get_marginals(pnde_handle* h, int32_t which, int64_t traj_begin, int64_
 int pnde_sample(pnde_handle* h, int64_t traj_begin, int64_t traj_end, int32_t n_samples, uint64_t seed,
                 int64_t* offsets, double* t, double* samples);
 
+/* dense_sample_states (src/solution_sampling.jl:63-74): `n_samples` joint draws from the smoothing posterior on the
+ * caller's non-decreasing time grid tq[0..n_t) instead of the solver's own grid (the reference: 1000 equidistant points
+ * over the solution's time span): backward sampling through the filtering posterior extrapolated to every grid point.
+ * samples [traj_end - traj_begin][n_t][n_samples][D]; dense_sample (:75-79) is its first d entries of each state.
+ * Needs save_mode = PNDE_SAVE_EVERY; catalogue models. */
+int pnde_dense_sample(pnde_handle* h, int64_t traj_begin, int64_t traj_end, int64_t n_t, const double* tq,
+                      int32_t n_samples, uint64_t seed, double* samples);
+
 /* perform_step! (src/perform_step.jl:27-93) applied once to n caller-supplied states: the entry a step!/callback
  * driver needs, and the teacher-forced unit of the parity protocol.  Stateless with respect to the
  * handle's ensemble; uses the handle's algorithm, order, diffusion model and tolerances.

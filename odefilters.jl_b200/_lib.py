@@ -41,7 +41,7 @@ EXPORTS = [
     "pnde_default_config", "pnde_create", "pnde_create_custom", "pnde_check_custom", "pnde_destroy", "pnde_last_error", "pnde_state_dim", "pnde_n_params",
     "pnde_record_len", "pnde_cov_len", "pnde_solve_ensemble", "pnde_solve_ensemble_to_host", "pnde_upload", "pnde_run", "pnde_synchronize", "pnde_last_run_ms",
     "pnde_last_launch_count", "pnde_smooth", "pnde_query_sizes", "pnde_get_counts", "pnde_get_final",
-    "pnde_get_history", "pnde_get_history_sqrt", "pnde_step_from_state", "pnde_get_marginals", "pnde_sample", "pnde_eval_dense", "pnde_measure_fp64_peak",
+    "pnde_get_history", "pnde_get_history_sqrt", "pnde_step_from_state", "pnde_get_marginals", "pnde_sample", "pnde_dense_sample", "pnde_eval_dense", "pnde_measure_fp64_peak",
     "pnde_measure_hbm_copy", "pnde_host_alloc", "pnde_host_free",
 ]
 
@@ -86,6 +86,7 @@ def load():
     lib.pnde_step_from_state.argtypes = [vp, C.c_int64] + [vp] * 13
     lib.pnde_get_marginals.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, vp, vp, vp, vp]
     lib.pnde_sample.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_uint64, vp, vp, vp]
+    lib.pnde_dense_sample.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32, C.c_uint64, vp]
     lib.pnde_eval_dense.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp]
     lib.pnde_measure_fp64_peak.argtypes = [C.c_int32, dp]
     lib.pnde_measure_hbm_copy.argtypes = [C.c_int32, dp]

@@ -313,6 +313,20 @@ class ProbODESolution:
         """sample(sol, n) (src/solution_sampling.jl:19-23): [len(sol), d, n]."""
         return self.sample_states(n, seed)[:, : self._solver.d, :]
 
+    def dense_sample_states(self, n: int = 1, seed: int = 0, n_times: int = 1000):
+        """dense_sample_states(sol, n) (src/solution_sampling.jl:63-74): (samples [n_times, D, n], times) on
+        range(sol.t[1], sol.t[end], length = 1000)."""
+        if self.x_smooth is None:
+            raise ValueError("sampling not implemented for non-smoothed posteriors")  # :64
+        times = np.linspace(self.t[0], self.t[-1], n_times)
+        smp = self._solver.dense_sample(self._index, self._index + 1, times, n, seed)[0]
+        return np.ascontiguousarray(np.transpose(smp, (0, 2, 1))), times
+
+    def dense_sample(self, n: int = 1, seed: int = 0, n_times: int = 1000):
+        """dense_sample(sol, n) (src/solution_sampling.jl:75-79): (samples [n_times, d, n], times)."""
+        smp, times = self.dense_sample_states(n, seed, n_times)
+        return smp[:, : self._solver.d, :], times
+
 
 @dataclass
 class EnsembleSolution:
@@ -586,6 +600,14 @@ class FilterSolver:
         self._check(self.lib.pnde_sample(self._h, lo, hi, n_samples, seed, offsets.ctypes.data, t.ctypes.data,
                                          smp.ctypes.data), "pnde_sample")
         return offsets, t, smp
+
+    def dense_sample(self, lo: int, hi: int, tq: np.ndarray, n_samples: int, seed: int = 0) -> np.ndarray:
+        """pnde_dense_sample for trajectories [lo, hi): samples [ntr, n_t, n_samples, D] on the time grid tq."""
+        tq = np.ascontiguousarray(tq, dtype=np.float64)
+        smp = np.empty((hi - lo, len(tq), n_samples, self.D))
+        self._check(self.lib.pnde_dense_sample(self._h, lo, hi, len(tq), tq.ctypes.data, n_samples, seed, smp.ctypes.data),
+                    "pnde_dense_sample")
+        return smp
 
     def dense(self, which: int, lo: int, hi: int, tq: np.ndarray):
         """pnde_eval_dense: (mean [ntr, n_t, D], cov [ntr, n_t, D, D]) of trajectories [lo, hi) at times tq."""

@@ -4,6 +4,7 @@
 #include "model_ops.cuh"
 #include "convert_kernel.cuh"
 #include "post_kernels.cuh"
+#include "dense_sample.cuh"
 #include "smoother_kernel.cuh"
 #include "wide_filter.cuh"
 #include "wide_smoother.cuh"
@@ -96,6 +97,16 @@ cudaError_t launch_sample_t(const ModelOps*, const SampleParams& sp, cudaStream_
   const int block = 128;
   const long long ntr = sp.traj_end - sp.traj_begin;
   if (ntr <= 0 || sp.n_samples <= 0) return cudaSuccess;
+  if (sp.tq) {  // dense_sample: the caller's time grid (dense_sample.cuh)
+    if (sp.n_t < 1) return cudaSuccess;
+    if (sp.n_t > 1) {
+      const long long prep = ntr * (sp.n_t - 1);
+      dense_sample_prep_kernel<M><<<(unsigned)((prep + block - 1) / block), block, 0, s>>>(sp);
+    }
+    const long long total = ntr * sp.n_samples;
+    dense_sample_draw_kernel<M><<<(unsigned)((total + block - 1) / block), block, 0, s>>>(sp);
+    return cudaGetLastError();
+  }
   if (sp.max_saved > 1) {
     const long long prep = ntr * (sp.max_saved - 1);
     sample_prep_kernel<M><<<(unsigned)((prep + block - 1) / block), block, 0, s>>>(sp);

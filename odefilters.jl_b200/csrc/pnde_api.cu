@@ -1420,6 +1420,73 @@ int pnde_sample(pnde_handle* h, int64_t tb, int64_t te, int32_t n_samples, uint6
   return PNDE_OK;
 }
 
+int pnde_dense_sample(pnde_handle* h, int64_t tb, int64_t te, int64_t n_t, const double* tq, int32_t n_samples,
+                      uint64_t seed, double* samples) {
+  if (!h) return PNDE_ERR_ARG;
+  if (!h->ran) return h->fail(PNDE_ERR_STATE, "nothing has run");
+  if (h->cfg.save_mode != PNDE_SAVE_EVERY) return h->fail(PNDE_ERR_STATE, "pnde_dense_sample needs save_mode = PNDE_SAVE_EVERY");
+  if (tb < 0 || te > h->n || tb >= te || n_t < 1 || !tq || n_samples < 1 || !samples) return h->fail(PNDE_ERR_ARG, "bad arguments");
+  for (int64_t k = 0; k + 1 < n_t; ++k)
+    if (!(tq[k + 1] >= tq[k])) return h->fail(PNDE_ERR_ARG, "pnde_dense_sample: the time grid must be non-decreasing");
+  if (h->lorenz) return h->fail(PNDE_ERR_UNSUPPORTED, "sampling is not built for the large-d paths");
+  if (h->multi()) {
+    const size_t per = (size_t)n_t * n_samples * h->D;
+    for (size_t k = 0; k < h->kids.size(); ++k) {
+      const int64_t lo = std::max<int64_t>(tb, h->kid_lo[k]), hi = std::min<int64_t>(te, h->kid_lo[k + 1]);
+      if (lo >= hi) continue;
+      const int rc = pnde_dense_sample(h->kids[k], lo - h->kid_lo[k], hi - h->kid_lo[k], n_t, tq, n_samples, seed,
+                                       samples + (size_t)(lo - tb) * per);
+      if (rc != PNDE_OK) return h->fail(rc, h->kids[k]->err);
+    }
+    return PNDE_OK;
+  }
+  if (!h->ops || h->owns_ops)
+    return h->fail(PNDE_ERR_UNSUPPORTED, "pnde_dense_sample is built for the catalogue models (not for run-time compiled fields)");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  const ModelOps* o = h->ops;
+  // scratch record of one grid interval: DenseSamplePrep<M>::LEN = 2 D + NF (NP + DCOV + 2 DCOV^2)
+  const size_t Dq = (size_t)o->q + 1;
+  const size_t dcov = o->ek1 ? (size_t)o->D : Dq, npk = dcov * (dcov + 1) / 2;
+  const size_t nf = o->ek1 ? 1 : ((size_t)o->srec - (size_t)o->D - (size_t)o->d) / npk;
+  const size_t len = 2 * (size_t)o->D + nf * (npk + dcov + 2 * dcov * dcov);
+  const long long ntr = te - tb;
+  const size_t per_traj = (size_t)std::max<int64_t>(n_t - 1, 1) * len * 8;
+  const long long chunk = std::max<long long>(1, std::min<long long>(ntr, (long long)(((size_t)2 << 30) / per_traj)));
+  CK(h->sample_scratch.ensure((size_t)chunk * per_traj), "alloc sampler scratch");
+  const size_t nout = (size_t)ntr * n_t * n_samples * o->D;
+  CK(h->scratch_out.ensure(((size_t)n_t + nout) * 8 + 64), "alloc sample staging");
+  double* dtq = h->scratch_out.as<double>();
+  double* dout = dtq + n_t;
+  CK(cudaMemcpyAsync(dtq, tq, (size_t)n_t * 8, cudaMemcpyHostToDevice, h->stream), "H2D time grid");
+  const int df = h->cfg.diffusion;
+  SampleParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.n = h->n;
+  sp.n_saved = h->n_saved.as<int>();
+  sp.hist = h->hist.as<double>();
+  sp.final_diff = h->final_diff.as<double>();
+  sp.calibrate = (df == PNDE_DIFF_FIXED || df == PNDE_DIFF_FIXED_MAP || df == PNDE_DIFF_FIXED_MV);
+  sp.is_mv = (df == PNDE_DIFF_DYNAMIC_MV || df == PNDE_DIFF_FIXED_MV);
+  sp.n_samples = n_samples;
+  sp.seed = seed;
+  sp.key_offset = h->global_lo;
+  sp.scratch = h->sample_scratch.as<double>();
+  sp.max_saved = h->max_saved;
+  sp.tq = dtq;
+  sp.n_t = n_t;
+  sp.C = h->C;
+  for (long long c0 = tb; c0 < te; c0 += chunk) {
+    sp.traj_begin = c0;
+    sp.traj_end = std::min<long long>(te, c0 + chunk);
+    sp.out = dout + (size_t)(c0 - tb) * n_t * n_samples * o->D;
+    CK(o->launch_sample(o, sp, h->stream), "dense sample kernel launch");
+    h->launches += 2;
+  }
+  CK(cudaMemcpyAsync(samples, dout, nout * 8, cudaMemcpyDeviceToHost, h->stream), "D2H samples");
+  CK(cudaStreamSynchronize(h->stream), "stream synchronize");
+  return PNDE_OK;
+}
+
 int pnde_step_from_state(pnde_handle* h, int64_t n, const double* mean, const double* sqrt_in, const double* t,
                          const double* dt, const double* p, const double* uprev, double* mean_out, double* cov_out,
                          double* sigma2, double* eest, double* u_out, double* quad_logdet, int32_t* status) {

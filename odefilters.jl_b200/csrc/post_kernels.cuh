@@ -70,6 +70,10 @@ struct SampleParams {
   long long key_offset;  // added to the trajectory index in the generator key (shards of a multi-device ensemble)
   double* out;  // [total][n_samples][D]
   double* scratch;  // [traj_end - traj_begin][max_saved - 1][SamplePrep<M>::LEN]: the per-interval backward kernels
+  // dense_sample (dense_sample.cuh): backward sampling on the caller's grid tq[0..n_t) instead of the saved one; out is
+  // then [traj][n_t][n_samples][D] and scratch [traj][n_t - 1][DenseSamplePrep<M>::LEN].  nullptr: the saved grid
+  const double* tq;
+  long long n_t;
   IwpConsts C;
 };
 

@@ -1635,3 +1635,50 @@ def test_reference_smoothing_and_specific_problems_jl():
     sol = B.solve(B.ODEProblem("linear2", u0, (0.0, 5.0), (a, b)), B.EK0(order=6, smooth=False), adaptive=False, dt=0.5)
     truth = np.concatenate([[a ** k * u0[0], b ** k * u0[1]] for k in range(7)])
     assert np.allclose(sol.x_filt.mu[0], truth, rtol=1e-14, atol=0.0)
+
+
+@pytest.mark.parametrize("kind,q,diffusion", [("EK1", 2, "dynamic"), ("EK0", 3, "dynamic"), ("EK0", 2, "dynamicMV"),
+                                              ("EK1", 3, "fixed"), ("EK0", 2, "fixedMV")])
+def test_dense_sample_statistics(kind, q, diffusion):
+    """dense_sample_states / dense_sample (src/solution_sampling.jl:63-79): backward sampling on a dense time grid.  The
+    moments of the draws at every grid time against the exact law of the reference's recursion, evaluated with the
+    ORACLE's predict / smooth; shapes and the 3-sigma test as in test/solution.jl:74-79."""
+    import odefilters_b200 as B
+
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, diffusionmodel=diffusion, smooth=True)
+    kw = dict(tspan=(0.0, 2.0), adaptive=False, dt=0.1)
+    sol = gpu_solve("lotka_volterra", alg, **kw)
+    so = oracle_solve("lotka_volterra", O.Alg(kind, q, diffusion, True), **kw)
+    n, nt, D = 6000, 61, 2 * (q + 1)
+    S, times = sol.dense_sample_states(n, seed=5, n_times=nt)
+    assert S.shape == (nt, D, n) and times.shape == (nt,) and times[0] == sol.t[0] and times[-1] == sol.t[-1]
+    assert np.array_equal(S, sol.dense_sample_states(n, seed=5, n_times=nt)[0])      # reproducible
+    assert not np.array_equal(S, sol.dense_sample_states(n, seed=6, n_times=nt)[0])
+    assert np.allclose(S[0, :2, :], 1.0, rtol=1e-13, atol=0)                           # the initial state is exact
+    # the law of the reference's dense draws: its backward recursion (:36-59) with the draws replaced by their mean and
+    # covariance is the RTS recursion over the extrapolated filter states of the grid (it ignores the measurements that
+    # lie strictly inside a grid interval, so it is NOT sol(t) unless the grid contains the solver's)
+    xs = [O.posterior_at(so, float(t), smoothed=False) for t in times]
+    post = [None] * nt
+    post[-1] = cur = xs[-1]
+    for i in range(nt - 2, -1, -1):
+        dt_ = times[i + 1] - times[i]
+        sigma2 = so.diffusions[int(np.sum(np.asarray(so.t) <= times[i])) - 1]
+        P = O.preconditioner_diag(2, q, dt_)
+        sm, _ = O.smooth(O.Gaussian(P * xs[i].mu, O.SRMatrix(P[:, None] * xs[i].Sigma.squareroot)),
+                         O.Gaussian(P * cur.mu, O.SRMatrix(P[:, None] * cur.Sigma.squareroot)), so.A,
+                         O.apply_diffusion(so.Q, sigma2))
+        post[i] = cur = O.Gaussian(sm.mu / P, O.SRMatrix(sm.Sigma.squareroot / P[:, None]))
+    mo = np.array([g.mu for g in post])
+    sdo = np.sqrt(np.maximum(np.array([np.diag(g.Sigma.mat) for g in post]), 0))
+    ok = sdo > 1e-10 * np.abs(mo).max(axis=0)
+    m_emp, s_emp = S.mean(axis=2), S.std(axis=2)
+    zmean = np.abs(m_emp - mo)[ok] / (sdo[ok] / np.sqrt(n))
+    rstd = np.abs(s_emp[ok] / sdo[ok] - 1)
+    report("dense_sample", alg=kind, q=q, diffusion=diffusion, worst_mean_z=float(zmean.max()), worst_std_rel=float(rstd.max()))
+    assert zmean.max() < 6 and rstd.max() < 6 / np.sqrt(2 * n)
+    smp, dts = sol.dense_sample(10, seed=3)                                            # the reference's defaults
+    assert smp.shape == (1000, 2, 10) and dts.shape == (1000,)
+    dense = sol(dts)
+    std = np.sqrt(np.maximum(np.diagonal(dense.Sigma, axis1=1, axis2=2), 0))
+    assert np.sum(np.abs(smp - dense.mu[:, :, None]) > 3 * std[:, :, None]) < 0.05 * smp.size
