@@ -252,7 +252,7 @@ int pnde_sample(pnde_handle* h, int64_t traj_begin, int64_t traj_end, int32_t n_
  * caller's non-decreasing time grid tq[0..n_t) instead of the solver's own grid (the reference: 1000 equidistant points
  * over the solution's time span): backward sampling through the filtering posterior extrapolated to every grid point.
  * samples [traj_end - traj_begin][n_t][n_samples][D]; dense_sample (:75-79) is its first d entries of each state.
- * Needs save_mode = PNDE_SAVE_EVERY; catalogue models. */
+ * Needs save_mode = PNDE_SAVE_EVERY. */
 int pnde_dense_sample(pnde_handle* h, int64_t traj_begin, int64_t traj_end, int64_t n_t, const double* tq,
                       int32_t n_samples, uint64_t seed, double* samples);
 

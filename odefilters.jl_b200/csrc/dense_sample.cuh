@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) dense_sample_prep_kernel(const SamplePara
   using PT = PostTraits<M>;
   using SC = typename PT::SC;
   using SPp = DenseSamplePrep<M>;
-  constexpr int d = M::d, q = M::q, D = M::D, ND = M::ND, REC = M::REC, NF = PT::NF, DC = PT::DC, DCOV = PT::DCOV;
+  constexpr int d = M::d, q = M::q, D = M::D, REC = M::REC, NF = PT::NF, DC = PT::DC, DCOV = PT::DCOV;
   const long long ntr = sp.traj_end - sp.traj_begin;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= ntr * (sp.n_t - 1)) return;

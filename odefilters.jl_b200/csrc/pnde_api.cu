@@ -1440,8 +1440,7 @@ int pnde_dense_sample(pnde_handle* h, int64_t tb, int64_t te, int64_t n_t, const
     }
     return PNDE_OK;
   }
-  if (!h->ops || h->owns_ops)
-    return h->fail(PNDE_ERR_UNSUPPORTED, "pnde_dense_sample is built for the catalogue models (not for run-time compiled fields)");
+  if (!h->ops) return h->fail(PNDE_ERR_UNSUPPORTED, "pnde_dense_sample: not built for this path");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   const ModelOps* o = h->ops;
   // scratch record of one grid interval: DenseSamplePrep<M>::LEN = 2 D + NF (NP + DCOV + 2 DCOV^2)

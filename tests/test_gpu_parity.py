@@ -1682,3 +1682,19 @@ def test_dense_sample_statistics(kind, q, diffusion):
     dense = sol(dts)
     std = np.sqrt(np.maximum(np.diagonal(dense.Sigma, axis1=1, axis2=2), 0))
     assert np.sum(np.abs(smp - dense.mu[:, :, None]) > 3 * std[:, :, None]) < 0.05 * smp.size
+
+
+def test_dense_sample_custom_field_equals_catalogue():
+    """pnde_dense_sample through NVRTC (user field, its own lazily compiled module) draws what the catalogue build draws."""
+    import odefilters_b200 as B
+
+    f = "du[0] = p[0]*u[0] - p[1]*u[0]*u[1]; du[1] = -p[2]*u[1] + p[3]*u[0]*u[1];"
+    j = "J[0][0] = p[0]-p[1]*u[1]; J[0][1] = -p[1]*u[0]; J[1][0] = p[3]*u[1]; J[1][1] = -p[2]+p[3]*u[0];"
+    cv = B.CustomVectorField(d=2, n_params=4, f=f, jac=j)
+    u0, tspan, p = _REF_PROBS["lotka_volterra"]
+    for Alg in (B.EK1, B.EK0):
+        a = B.solve(B.ODEProblem("lotka_volterra", u0, tspan, p), Alg(order=2), adaptive=False, dt=0.05)
+        b = B.solve(B.ODEProblem(cv, u0, tspan, p), Alg(order=2), adaptive=False, dt=0.05)
+        sa, ta = a.dense_sample_states(8, seed=4, n_times=50)
+        sb, tb = b.dense_sample_states(8, seed=4, n_times=50)
+        assert np.array_equal(ta, tb) and np.allclose(sa, sb, rtol=1e-9, atol=1e-12)
