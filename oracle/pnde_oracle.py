@@ -1255,6 +1255,29 @@ def dense_eval(sol: Solution, tval: float) -> Gaussian:
     return affine(E0, posterior_at(sol, tval))
 
 
+def dense_sample_law(sol: Solution, times) -> List[Gaussian]:
+    """Marginal law N(mean, cov) of dense_sample_states' draws at every time of `times`
+    (src/solution_sampling.jl:63-74 -> :24-62): the reference draws backwards through the filtering
+    posterior extrapolated to the grid (interp(...; smoothed=false), :66), x_k = m_k + G_k (x_{k+1} - m_k^-) + noise,
+    with the diffusion of the solver interval that contains t_k (:41-42).  Replacing each draw by its mean and
+    covariance is the RTS recursion over those extrapolated states; it ignores the measurements strictly inside a
+    grid interval, so it equals sol(t) only when the grid contains the solver's."""
+    assert sol.smoothed
+    d, q = sol.d, sol.q
+    xs = [posterior_at(sol, float(t), smoothed=False) for t in times]
+    out = [None] * len(xs)
+    out[-1] = cur = xs[-1]
+    for i in range(len(xs) - 2, -1, -1):
+        dt = times[i + 1] - times[i]
+        diffusion = sol.diffusions[int(np.sum(np.asarray(sol.t) <= times[i])) - 1]
+        P = preconditioner_diag(d, q, dt)
+        sm, _ = smooth(Gaussian(P * xs[i].mu, SRMatrix(P[:, None] * xs[i].Sigma.squareroot)),
+                       Gaussian(P * cur.mu, SRMatrix(P[:, None] * cur.Sigma.squareroot)), sol.A,
+                       apply_diffusion(sol.Q, diffusion))
+        out[i] = cur = Gaussian(sm.mu / P, SRMatrix(sm.Sigma.squareroot / P[:, None]))
+    return out
+
+
 def sample_states(sol: Solution, n: int, normals: np.ndarray) -> np.ndarray:
     """src/solution_sampling.jl:24-62 with the standard-normal draws supplied by
     the caller: normals[i, :, j] is the D-vector used at time index i for path j

@@ -1655,20 +1655,8 @@ def test_dense_sample_statistics(kind, q, diffusion):
     assert np.array_equal(S, sol.dense_sample_states(n, seed=5, n_times=nt)[0])      # reproducible
     assert not np.array_equal(S, sol.dense_sample_states(n, seed=6, n_times=nt)[0])
     assert np.allclose(S[0, :2, :], 1.0, rtol=1e-13, atol=0)                           # the initial state is exact
-    # the law of the reference's dense draws: its backward recursion (:36-59) with the draws replaced by their mean and
-    # covariance is the RTS recursion over the extrapolated filter states of the grid (it ignores the measurements that
-    # lie strictly inside a grid interval, so it is NOT sol(t) unless the grid contains the solver's)
-    xs = [O.posterior_at(so, float(t), smoothed=False) for t in times]
-    post = [None] * nt
-    post[-1] = cur = xs[-1]
-    for i in range(nt - 2, -1, -1):
-        dt_ = times[i + 1] - times[i]
-        sigma2 = so.diffusions[int(np.sum(np.asarray(so.t) <= times[i])) - 1]
-        P = O.preconditioner_diag(2, q, dt_)
-        sm, _ = O.smooth(O.Gaussian(P * xs[i].mu, O.SRMatrix(P[:, None] * xs[i].Sigma.squareroot)),
-                         O.Gaussian(P * cur.mu, O.SRMatrix(P[:, None] * cur.Sigma.squareroot)), so.A,
-                         O.apply_diffusion(so.Q, sigma2))
-        post[i] = cur = O.Gaussian(sm.mu / P, O.SRMatrix(sm.Sigma.squareroot / P[:, None]))
+    # the exact law of the reference's dense draws (oracle.dense_sample_law: NOT sol(t) unless the grid contains the solver's)
+    post = O.dense_sample_law(so, times)
     mo = np.array([g.mu for g in post])
     sdo = np.sqrt(np.maximum(np.array([np.diag(g.Sigma.mat) for g in post]), 0))
     ok = sdo > 1e-10 * np.abs(mo).max(axis=0)

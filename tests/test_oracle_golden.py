@@ -256,3 +256,15 @@ def test_ieks_oracle_first_iterate_is_ek1_and_iterates_contract():
     s = O.solve_ieks(O.Problem(O.CATALOGUE["fhn_lib"], [1.0, 1.0], (0.0, 10.0), [0.7, 0.8, 1 / 12.5, 0.5]),
                      O.IEKS(order=4, diffusionmodel="fixed"), iterations=3)
     assert s.retcode == "Success" and s.t[-1] == 10.0 and s.smoothed
+
+
+def test_dense_sample_law_on_the_solver_grid_is_the_smoother():
+    """oracle.dense_sample_law (the marginal law of src/solution_sampling.jl:63-74's draws) pinned on the one case with
+    a known answer: on the solver's own grid the backward recursion is smooth_all (src/smoothing.jl:4-28)."""
+    vf = O.CATALOGUE["lotka_volterra"]
+    so = O.solve_ivp(O.Problem(vf, [1.0, 1.0], (0.0, 2.0), [1.5, 1.0, 3.0, 1.0]), O.Alg("EK1", 2, "dynamic", True),
+                     adaptive=False, dt=0.1)
+    law = O.dense_sample_law(so, np.array(so.t))
+    for i in range(1, len(so.t)):
+        assert np.allclose(law[i].mu, so.x_smooth[i].mu, rtol=1e-10, atol=1e-12)
+        assert np.allclose(law[i].Sigma.mat, so.x_smooth[i].Sigma.mat, rtol=1e-8, atol=1e-16)
