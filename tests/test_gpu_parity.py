@@ -1686,3 +1686,26 @@ def test_dense_sample_custom_field_equals_catalogue():
         sa, ta = a.dense_sample_states(8, seed=4, n_times=50)
         sb, tb = b.dense_sample_states(8, seed=4, n_times=50)
         assert np.array_equal(ta, tb) and np.allclose(sa, sb, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind,q,diffusion", [("EK1", 4, "fixed"), ("EK1", 5, "fixedMAP"), ("EK0", 4, "fixed"), ("EK1", 3, "fixed")])
+def test_static_diffusion_across_a_sliver_interval(kind, q, diffusion):
+    """dt = 0.05 on (0, 5): 100 additions of 0.05 fall 11 ulp short of 5 -- outside OrdinaryDiffEq's 10-ulp snap -- and a
+    step of 9.8e-15 follows.  With a static diffusion model the backward recursions carry the state across that sliver
+    (filter_kernel.cuh, sliver_interval): smoothed solution against the oracle for the one-thread smoother (D = 8), the
+    lane-group smoother (D = 10, 12) and the Kronecker smoother, plus sampling and dense output at the sliver."""
+    import odefilters_b200 as B
+
+    kw = dict(adaptive=False, dt=0.05, tspan=(0.0, 5.0))
+    so = oracle_solve("lotka_volterra", O.Alg(kind, q, diffusion, True), **dict(kw))
+    alg = (B.EK1 if kind == "EK1" else B.EK0)(order=q, diffusionmodel=diffusion, smooth=True)
+    sg = gpu_solve("lotka_volterra", alg, **dict(kw))
+    assert len(sg.t) == len(so.t) == 102 and 0.0 < sg.t[-1] - sg.t[-2] < 1e-13
+    err = rel(sg.u, np.array(so.u))
+    report("static_sliver", alg=kind, q=q, diffusion=diffusion, rel_u=err)
+    assert err < 1e-8
+    assert np.array_equal(sg.x_smooth.mu[-2], sg.x_smooth.mu[-1])       # carried across
+    smp = sg.sample(4, seed=1)
+    assert np.all(np.isfinite(smp)) and np.array_equal(smp[-2], smp[-1])
+    mid = 0.5 * (sg.t[-2] + sg.t[-1]) if sg.t[-2] < 0.5 * (sg.t[-2] + sg.t[-1]) < sg.t[-1] else sg.t[-1]
+    assert np.allclose(sg(mid).mu, sg.u[-1], rtol=1e-12)
