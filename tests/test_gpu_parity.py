@@ -1046,6 +1046,8 @@ def test_multi_device_single_call_is_bitwise_the_single_device_result(ndev):
         assert np.array_equal(x, y)
     for x, y in zip(a.sample(lo, hi, 3, seed=5), b.sample(lo, hi, 3, seed=5)):
         assert np.array_equal(x, y)  # the generator is keyed by the GLOBAL trajectory index
+    tg = np.linspace(0.0, 2.0, 17)
+    assert np.array_equal(a.dense_sample(lo, hi, tg, 3, seed=9), b.dense_sample(lo, hi, tg, 3, seed=9))
     # pipelined host-to-host entry point and the high-level API
     pf = B.ODEProblem("fhn_readme", [-1.0, 1.0], (0.0, 1.0), (0.2, 0.2, 3.0))
     Pf = np.stack([rng.uniform(0.1, 0.3, 70001), rng.uniform(0.1, 0.3, 70001), rng.uniform(2, 4, 70001)], axis=1)
