@@ -1,0 +1,76 @@
+"""Randomised differential run: GPU path vs the oracle over problems x algorithms x orders x diffusion models x step modes.
+Prints one line per case and a summary of the cases that disagree (grid length, counts, or solution beyond 1e-6)."""
+import os, sys, json, time
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+import pnde_oracle as O
+import odefilters_b200 as B
+
+PROBS = {"lotka_volterra": ([1.0, 1.0], (1.5, 1.0, 3.0, 1.0)), "fhn_lib": ([1.0, 1.0], (0.7, 0.8, 1 / 12.5, 0.5)),
+         "fhn_readme": ([-1.0, 1.0], (0.2, 0.2, 3.0)), "vanderpol": ([0.0, 3.0 ** 0.5], (5.0,)),
+         "logistic": ([0.1], (3.0,)), "linear2": ([0.1, 1.0], (1.1, -0.5))}
+def run(seed=0, ncase=60, verbose=True):
+    """Returns (cases that disagree, number of cases)."""
+    rng = np.random.default_rng(seed)
+    bad = []
+    for case in range(ncase):
+        name = rng.choice(list(PROBS))
+        u0, p = PROBS[name]
+        kind = rng.choice(["EK0", "EK1"])
+        q = int(rng.integers(1, 6))
+        diffs = ["dynamic", "fixed", "fixedMAP"] + (["dynamicMV", "fixedMV"] if kind == "EK0" else [])
+        diffusion = rng.choice(diffs)
+        T = float(rng.choice([0.5, 1.0, 2.0, 3.0]))
+        adaptive = bool(rng.integers(0, 2))
+        smooth = bool(rng.integers(0, 2))
+        kw = dict(abstol=float(rng.choice([1e-4, 1e-6, 1e-8])), reltol=float(rng.choice([1e-2, 1e-3, 1e-5]))) if adaptive else \
+            dict(adaptive=False, dt=float(rng.choice([0.1, 0.05, 0.03, 0.02, 0.01, 7e-3])))
+        tag = dict(case=case, prob=name, alg=kind, q=q, diffusion=str(diffusion), T=T, smooth=smooth, **kw)
+        try:
+            so = O.solve_ivp(O.Problem(O.CATALOGUE[name], list(u0), (0.0, T), list(p)), O.Alg(kind, q, str(diffusion), smooth), **kw)
+            o_ok = True
+        except Exception as e:  # the reference throws (e.g. FixedDiffusion with a zero residual)
+            o_ok, so = False, None
+            tag["oracle_error"] = str(e)[:60]
+        alg = (B.EK0 if kind == "EK0" else B.EK1)(order=q, diffusionmodel=str(diffusion), smooth=smooth)
+        sg = B.solve(B.ODEProblem(name, u0, (0.0, T), p), alg, **kw)
+        tag["retcode"] = sg.retcode
+        if o_ok:
+            same_len = len(sg.t) == len(so.t)
+            tag["n"] = (len(sg.t), len(so.t))
+            tag["counts"] = (sg.destats["naccept"], sg.destats["nreject"], so.naccept, so.nreject)
+            if same_len:
+                uo = np.array(so.u)
+                tag["rel_u"] = float(np.max(np.abs(sg.u - uo)) / max(np.max(np.abs(uo)), 1e-300))
+            if not same_len or tag.get("rel_u", 1.0) > 1e-6 or sg.retcode != "Success":
+                # is the reference arithmetic itself ill-conditioned here?  its own answer for u0 moved by one ulp
+                uo = np.array(so.u)
+                if not np.all(np.isfinite(uo)):
+                    tag["class"] = "reference arithmetic overflows too (the oracle does not stop at NaN, the kernel returns Unstable)"
+                else:
+                    u1 = list(u0)
+                    j = next(i for i, v in enumerate(u1) if v != 0.0)  # (a zero component has no ulp to move by)
+                    u1[j] = float(np.nextafter(u1[j], 2 * abs(u1[j])))
+                    try:
+                        s2 = O.solve_ivp(O.Problem(O.CATALOGUE[name], u1, (0.0, T), list(p)), O.Alg(kind, q, str(diffusion), smooth), **kw)
+                        if len(s2.t) != len(so.t):
+                            tag["class"] = "ill-conditioned: the oracle's own grid changes with a 1-ulp change of u0"
+                        else:
+                            self_rel = float(np.max(np.abs(np.array(s2.u) - uo)) / max(np.max(np.abs(uo)), 1e-300))
+                            tag["oracle_self_rel_u"] = self_rel
+                            tag["class"] = ("ill-conditioned: the oracle moves by %.1e for a 1-ulp change of u0" % self_rel
+                                            if self_rel > 0.01 * tag.get("rel_u", 1.0) else "UNEXPLAINED")
+                    except Exception as e:
+                        tag["class"] = "ill-conditioned: the oracle throws for a 1-ulp change of u0 (%s)" % str(e)[:40]
+                bad.append(tag)
+        if verbose:
+            print(json.dumps(tag), flush=True)
+    return bad, ncase
+
+
+if __name__ == "__main__":
+    bad, ncase = run(int(sys.argv[1]) if len(sys.argv) > 1 else 0, int(sys.argv[2]) if len(sys.argv) > 2 else 60)
+    print("DISAGREE", len(bad), "of", ncase, "UNEXPLAINED", sum(1 for b in bad if b.get("class") == "UNEXPLAINED"))
+    for b in bad:
+        print("  ", json.dumps(b))
