@@ -46,8 +46,8 @@ def run(seed=0, ncase=60, verbose=True):
             if not same_len or tag.get("rel_u", 1.0) > 1e-6 or sg.retcode != "Success":
                 # is the reference arithmetic itself ill-conditioned here?  its own answer for u0 moved by one ulp
                 uo = np.array(so.u)
-                if not np.all(np.isfinite(uo)):
-                    tag["class"] = "reference arithmetic overflows too (the oracle does not stop at NaN, the kernel returns Unstable)"
+                if not np.all(np.isfinite(uo)) or so.retcode == "Unstable":
+                    tag["class"] = "the reference arithmetic overflows too (Unstable in both; the kernels stop at the first non-finite state, check_error! one step later at the first NaN)"
                 else:
                     u1 = list(u0)
                     j = next(i for i, v in enumerate(u1) if v != 0.0)  # (a zero component has no ulp to move by)

@@ -1129,6 +1129,13 @@ def solve_ivp(prob: Problem, alg: Alg, *, adaptive=True, dt=None, abstol=1e-6, r
         if not (cur_dt == cur_dt):
             sol.retcode = "DtNaN"
             break
+        # check_error! (OrdinaryDiffEq): unstable_check(dt, u, p, t) = any(isnan, u) -> :Unstable
+        try:
+            if np.isnan(np.asarray(u, dtype=float)).any():
+                sol.retcode = "Unstable"
+                break
+        except (TypeError, ValueError):
+            pass  # generic scalar types (mpmath, duals): no such check
         EEst, u_filt = perform_step(cache, prob, alg, sol, t, cur_dt, adaptive, abstol, reltol, u, success_iter)
         if EEst is not None and not isinstance(EEst, float):
             EEst = float(EEst)  # mpmath arbiter runs: the controller itself stays in Float64 like dt and t
