@@ -407,8 +407,9 @@ def main():
             "nominal_peak": nominal, "flop_per_unit": FLOP_PER_STEP, "units_per_launch": steps_per_launch,
             "launch_ms": k_ms,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel for this workload, one ncu --set full
-            # capture (profiles/r1_filter_kernel_ncu_summary.csv): 51.6 MB + 349.5 MB; algorithmic bytes 408 MB
-            "traffic": 401.0e6 if n == N_TRAJ_PER_GPU else None, "traffic_unit": "bytes per launch",
+            # capture of the final round-2 build (profiles/r2_filter_kernel_ncu_summary.csv): 50.5 MB + 345.4 MB
+            # (round 1: 51.6 + 349.5); algorithmic bytes 408 MB
+            "traffic": 395.8e6 if n == N_TRAJ_PER_GPU else None, "traffic_unit": "bytes per launch",
             "algorithmic_bytes": (BYTES_IN_PER_TRAJ + BYTES_OUT_PER_TRAJ) * n,
             "hbm": {"achieved": (BYTES_IN_PER_TRAJ + BYTES_OUT_PER_TRAJ) * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "peak_source": hbm_src,
